@@ -1,0 +1,687 @@
+// api.cu -- the C ABI of libo3d_b200.so (include/o3d_b200.h): session management, the
+// device-resident time-step stages and the stateless host-pointer module procedures.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "session.h"
+
+// ------------------------------------------------------------------------------------------
+// process-wide state
+// ------------------------------------------------------------------------------------------
+namespace o3d {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+Schemes g_schemes;
+int g_sor_order = O3D_SOR_RED_BLACK;
+static int g_device = 0;
+static int g_device_checked = 0;
+
+int ensure_device() {
+    if (g_device_checked == 1) return O3D_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available (%s); libo3d_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return O3D_ERR_NO_DEVICE;
+    }
+    O3D_CUDA_CHECK(cudaSetDevice(g_device));
+    g_device_checked = 1;
+    return O3D_OK;
+}
+
+int poisson_variant_of(int bx1, int bxn, int by1, int byn) {
+    // src/initialization.f90:283-301: only x and y flags are looked at
+    if (bx1 == 0 && bxn == 0 && by1 == 0 && byn == 0) return 0;
+    if (bx1 == 0 && bxn == 0 && by1 == 1 && byn == 1) return 1;
+    if (bx1 == 1 && bxn == 1 && by1 == 1 && byn == 1) return 2;
+    return -1;
+}
+
+int axis_bc(int b1, int bn, int* out) {
+    // src/initialization.f90:228-242
+    if (b1 == O3D_PERIODIC && bn == O3D_PERIODIC) {
+        *out = O3D_PERIODIC;
+        return O3D_OK;
+    }
+    if (b1 == O3D_FREE_SLIP && bn == O3D_FREE_SLIP) {
+        *out = O3D_FREE_SLIP;
+        return O3D_OK;
+    }
+    set_error("Unrecognized boundary layer types: %d %d", b1, bn);
+    return O3D_ERR_BC;
+}
+
+// ---- session helpers --------------------------------------------------------------------
+double* field(o3d_session* s, int id) {
+    if (id < 0 || id >= O3D_F_COUNT) return nullptr;
+    if (!s->base[id]) {
+        const size_t n = (size_t)s->plane * (size_t)(s->nzl + 2 * R);
+        double* p = nullptr;
+        if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            set_error("cudaMalloc of field %d (%zu bytes) failed", id, n * sizeof(double));
+            return nullptr;
+        }
+        cudaMemsetAsync(p, 0, n * sizeof(double), s->st);
+        s->base[id] = p;
+    }
+    return s->base[id] + (size_t)R * s->plane;
+}
+
+static const int HIST_BASE[4] = {O3D_F_FUX1, O3D_F_FUY1, O3D_F_FUZ1, O3D_F_FPHI1};
+
+int hist_id(const o3d_session* s, int c, int level) { return HIST_BASE[c] + s->lv[c][level - 1]; }
+
+// translate a public field id (logical history levels) to a physical one
+static int phys_id(const o3d_session* s, int id) {
+    for (int c = 0; c < 4; ++c)
+        if (id >= HIST_BASE[c] && id < HIST_BASE[c] + 3) return hist_id(s, c, id - HIST_BASE[c] + 1);
+    return id;
+}
+
+int ensure_partial(o3d_session* s, long long n) {
+    if (n <= s->partial_n) return O3D_OK;
+    if (s->partial) cudaFree(s->partial);
+    s->partial = nullptr;
+    s->partial_n = 0;
+    O3D_CUDA_CHECK(cudaMalloc(&s->partial, (size_t)n * sizeof(double)));
+    s->partial_n = n;
+    return O3D_OK;
+}
+
+static cudaEvent_t get_event(o3d_session* s) {
+    if (!s->free_events.empty()) {
+        cudaEvent_t e = s->free_events.back();
+        s->free_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void span_begin(o3d_session* s, int stage) {
+    if (!s->timers_on) return;
+    o3d_session::Span sp;
+    sp.a = get_event(s);
+    sp.b = nullptr;
+    sp.stage = stage;
+    cudaEventRecord(sp.a, s->st);
+    s->pending.push_back(sp);
+}
+
+void span_end(o3d_session* s, int stage, long long count) {
+    s->t_cnt[stage] += count;
+    if (!s->timers_on) return;
+    for (size_t q = s->pending.size(); q-- > 0;) {
+        if (s->pending[q].stage == stage && !s->pending[q].b) {
+            s->pending[q].b = get_event(s);
+            cudaEventRecord(s->pending[q].b, s->st);
+            return;
+        }
+    }
+}
+
+static void resolve_spans(o3d_session* s) {
+    if (s->pending.empty()) return;
+    cudaStreamSynchronize(s->st);
+    for (auto& sp : s->pending) {
+        if (sp.b) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) s->t_ms[sp.stage] += ms;
+            s->free_events.push_back(sp.b);
+        }
+        s->free_events.push_back(sp.a);
+    }
+    s->pending.clear();
+}
+
+void fill_dims(o3d_session* s) {
+    const o3d_config& c = s->cfg;
+    Dims& g = s->g;
+    g.nx = c.nx, g.ny = c.ny, g.nz = s->nzl;
+    g.bx = (c.nbcx1 == O3D_PERIODIC) ? BM_WRAP : BM_MIRROR;
+    g.by = (c.nbcy1 == O3D_PERIODIC) ? BM_WRAP : BM_MIRROR;
+    const int mz = (c.nbcz1 == O3D_PERIODIC) ? BM_WRAP : BM_MIRROR;
+    const int nr = c.nranks > 1 ? c.nranks : 1;
+    g.bz_lo = (nr > 1 && (c.rank > 0 || mz == BM_WRAP)) ? BM_HALO : mz;
+    g.bz_hi = (nr > 1 && (c.rank < nr - 1 || mz == BM_WRAP)) ? BM_HALO : mz;
+    g.sim2d = c.sim2d;
+    g.gz0 = s->z0;
+    g.gnz = c.nz;
+    s->cx = make_coef(c.dx);
+    s->cy = make_coef(c.dy);
+    s->cz = make_coef(c.dz);
+}
+
+}  // namespace o3d
+
+using namespace o3d;
+
+// ------------------------------------------------------------------------------------------
+// misc entry points
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* o3d_last_error(void) { return g_err; }
+int o3d_abi_version(void) { return O3D_ABI_VERSION; }
+long long o3d_kernel_launches(void) { return g_launches.load(); }
+
+int o3d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int o3d_set_device(int device) {
+    g_device = device;
+    g_device_checked = 0;
+    return ensure_device();
+}
+
+int o3d_host_alloc(void** ptr, unsigned long long bytes) {
+    if (!ptr) return O3D_ERR_INVALID;
+    int rc = ensure_device();
+    if (rc) return rc;
+    O3D_CUDA_CHECK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return O3D_OK;
+}
+int o3d_host_free(void* ptr) {
+    O3D_CUDA_CHECK(cudaFreeHost(ptr));
+    return O3D_OK;
+}
+int o3d_host_register(void* ptr, unsigned long long bytes) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    O3D_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return O3D_OK;
+}
+int o3d_host_unregister(void* ptr) {
+    O3D_CUDA_CHECK(cudaHostUnregister(ptr));
+    return O3D_OK;
+}
+
+int o3d_nccl_unique_id(unsigned char* out128) {
+    if (!out128) return O3D_ERR_INVALID;
+    return nccl_unique_id(out128);
+}
+
+int o3d_set_sor_order(int order) {
+    if (order != O3D_SOR_RED_BLACK && order != O3D_SOR_LEXI_WAVEFRONT) return O3D_ERR_INVALID;
+    g_sor_order = order;
+    return O3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// B. session
+// ------------------------------------------------------------------------------------------
+int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
+    if (!cfg || !out) return O3D_ERR_INVALID;
+    *out = nullptr;
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (cfg->nx < 7 || cfg->ny < 7 || cfg->nz < 7) {
+        set_error("grid extents must be >= 7 (stencil radius 3): %d %d %d", cfg->nx, cfg->ny,
+                  cfg->nz);
+        return O3D_ERR_INVALID;
+    }
+    int b;
+    if ((rc = axis_bc(cfg->nbcx1, cfg->nbcxn, &b))) return rc;
+    if ((rc = axis_bc(cfg->nbcy1, cfg->nbcyn, &b))) return rc;
+    if (cfg->sim2d == 0 && (rc = axis_bc(cfg->nbcz1, cfg->nbczn, &b))) return rc;
+    o3d_session* s = new (std::nothrow) o3d_session();
+    if (!s) return O3D_ERR_INVALID;
+    s->cfg = *cfg;
+    const int nr = cfg->nranks > 1 ? cfg->nranks : 1;
+    s->cfg.nranks = nr;
+    if (nr == 1) s->cfg.rank = 0;
+    if (cfg->rank < 0 || s->cfg.rank >= nr) {
+        delete s;
+        return O3D_ERR_INVALID;
+    }
+    // contiguous z slabs, remainder planes to the low ranks
+    const int q = cfg->nz / nr, r = cfg->nz % nr;
+    s->nzl = q + (s->cfg.rank < r ? 1 : 0);
+    s->z0 = s->cfg.rank * q + (s->cfg.rank < r ? s->cfg.rank : r);
+    if (nr > 1 && s->nzl < 2 * R) {
+        set_error("z slab of %d planes is thinner than two stencil halos", s->nzl);
+        delete s;
+        return O3D_ERR_INVALID;
+    }
+    s->plane = (long long)cfg->nx * cfg->ny;
+    s->nloc = s->plane * s->nzl;
+    for (int f = 0; f < O3D_F_COUNT; ++f) s->base[f] = nullptr;
+    for (int c = 0; c < 4; ++c)
+        for (int l = 0; l < 3; ++l) s->lv[c][l] = l;
+    s->sor_variant = poisson_variant_of(cfg->nbcx1, cfg->nbcxn, cfg->nbcy1, cfg->nbcyn);
+    s->last_iters = 0;
+    s->omega = cfg->omega;
+    s->partial = nullptr;
+    s->partial_n = 0;
+    s->comm = nullptr;
+    s->timers_on = 0;
+    s->use_src = 0;
+    for (int q2 = 0; q2 < 6; ++q2) s->t_ms[q2] = 0.0, s->t_cnt[q2] = 0;
+    s->st = nullptr;
+    s->ctrl_d = nullptr, s->ctrl_h = nullptr, s->flag_d = nullptr, s->flag_h = nullptr;
+    s->scal_d = nullptr, s->scal_h = nullptr;
+    fill_dims(s);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s->ctrl_d, sizeof(SorCtrl));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_h, sizeof(SorCtrl), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&s->flag_d, sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->flag_h, sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&s->scal_d, 64 * sizeof(double));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->scal_h, 64 * sizeof(double), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error("session allocation failed: %s", cudaGetErrorString(e));
+        o3d_session_destroy(s);
+        return O3D_ERR_CUDA;
+    }
+    *s->flag_h = 0;
+    if ((rc = comm_create(s))) {
+        o3d_session_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return O3D_OK;
+}
+
+int o3d_session_destroy(o3d_session* s) {
+    if (!s) return O3D_OK;
+    if (s->st) cudaStreamSynchronize(s->st);
+    comm_destroy(s);
+    for (int f = 0; f < O3D_F_COUNT; ++f)
+        if (s->base[f]) cudaFree(s->base[f]);
+    if (s->partial) cudaFree(s->partial);
+    if (s->ctrl_d) cudaFree(s->ctrl_d);
+    if (s->ctrl_h) cudaFreeHost(s->ctrl_h);
+    if (s->flag_d) cudaFree(s->flag_d);
+    if (s->flag_h) cudaFreeHost(s->flag_h);
+    if (s->scal_d) cudaFree(s->scal_d);
+    if (s->scal_h) cudaFreeHost(s->scal_h);
+    for (auto& sp : s->pending) {
+        cudaEventDestroy(sp.a);
+        if (sp.b) cudaEventDestroy(sp.b);
+    }
+    for (auto e : s->free_events) cudaEventDestroy(e);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+    return O3D_OK;
+}
+
+int o3d_session_slab(const o3d_session* s, int* z0, int* nz_local) {
+    if (!s) return O3D_ERR_INVALID;
+    if (z0) *z0 = s->z0;
+    if (nz_local) *nz_local = s->nzl;
+    return O3D_OK;
+}
+
+int o3d_upload(o3d_session* s, int fid, const double* host) {
+    if (!s || !host) return O3D_ERR_INVALID;
+    double* d = field(s, phys_id(s, fid));
+    if (!d) return O3D_ERR_CUDA;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(d, host, (size_t)s->nloc * sizeof(double),
+                                   cudaMemcpyHostToDevice, s->st));
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    return O3D_OK;
+}
+
+int o3d_download(o3d_session* s, int fid, double* host) {
+    if (!s || !host) return O3D_ERR_INVALID;
+    double* d = field(s, phys_id(s, fid));
+    if (!d) return O3D_ERR_CUDA;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(host, d, (size_t)s->nloc * sizeof(double),
+                                   cudaMemcpyDeviceToHost, s->st));
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    return O3D_OK;
+}
+
+int o3d_device_ptr(o3d_session* s, int fid, double** dptr) {
+    if (!s || !dptr) return O3D_ERR_INVALID;
+    *dptr = field(s, phys_id(s, fid));
+    if (!*dptr) return O3D_ERR_CUDA;
+    // make the lazy zero-fill visible to other streams
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    return O3D_OK;
+}
+
+int o3d_sync(o3d_session* s) {
+    if (!s) return O3D_ERR_INVALID;
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    return O3D_OK;
+}
+
+int o3d_get_omega(const o3d_session* s, double* omega) {
+    if (!s || !omega) return O3D_ERR_INVALID;
+    *omega = s->omega;
+    return O3D_OK;
+}
+int o3d_set_omega(o3d_session* s, double omega) {
+    if (!s) return O3D_ERR_INVALID;
+    s->omega = omega;
+    return O3D_OK;
+}
+
+int o3d_s_enable_timers(o3d_session* s, int on) {
+    if (!s) return O3D_ERR_INVALID;
+    resolve_spans(s);
+    s->timers_on = on;
+    return O3D_OK;
+}
+
+int o3d_s_timers(o3d_session* s, double* ms6, long long* counts6, int reset) {
+    if (!s) return O3D_ERR_INVALID;
+    resolve_spans(s);
+    for (int q = 0; q < 6; ++q) {
+        if (ms6) ms6[q] = s->t_ms[q];
+        if (counts6) counts6[q] = s->t_cnt[q];
+        if (reset) s->t_ms[q] = 0.0, s->t_cnt[q] = 0;
+    }
+    return O3D_OK;
+}
+
+// ---- stages ------------------------------------------------------------------------------
+static int ab_select(const o3d_config& c, int itime, double* adu, double* bdu, double* cdu) {
+    // src/integration.f90:84-105
+    if (c.itscheme == 1 || itime == 1) {
+        *adu = c.adt[0], *bdu = c.bdt[0], *cdu = c.cdt[0];
+    } else if (c.itscheme == 2 || itime == 2) {
+        *adu = c.adt[1], *bdu = c.bdt[1], *cdu = c.cdt[1];
+    } else if (c.itscheme == 3) {
+        *adu = c.adt[2], *bdu = c.bdt[2], *cdu = c.cdt[2];
+    } else {
+        set_error("itscheme: %d unrecognized", c.itscheme);
+        return O3D_ERR_ITSCHEME;
+    }
+    return O3D_OK;
+}
+
+// choose the physical buffer that receives the new f and rotate the logical levels the way the
+// reference copies them (src/integration.f90:176-188, :453-459)
+static int hist_target(o3d_session* s, int c) {
+    const int itscheme = s->cfg.itscheme;
+    if (itscheme == 3) return s->lv[c][2];
+    for (int p = 0; p < 3; ++p)
+        if (p != s->lv[c][1] && p != s->lv[c][2]) return p;
+    return 0;
+}
+static void hist_rotate(o3d_session* s, int c, int target) {
+    const int itscheme = s->cfg.itscheme;
+    if (itscheme == 3) {
+        const int old2 = s->lv[c][1];
+        s->lv[c][0] = target, s->lv[c][1] = target, s->lv[c][2] = old2;
+    } else if (itscheme == 2) {
+        s->lv[c][0] = target, s->lv[c][1] = target;
+    } else {
+        s->lv[c][0] = target;
+    }
+}
+
+int o3d_s_predict_velocity(o3d_session* s, int itime) {
+    if (!s) return O3D_ERR_INVALID;
+    const o3d_config& c = s->cfg;
+    double adu, bdu, cdu;
+    int rc = ab_select(c, itime, &adu, &bdu, &cdu);
+    if (rc) return rc;
+    RhsArgs a;
+    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
+    int tgt[3];
+    for (int k = 0; k < 3; ++k) {
+        a.u[k] = u[k];
+        tgt[k] = hist_target(s, k);
+        a.f2[k] = field(s, HIST_BASE[k] + s->lv[k][1]);
+        a.f3[k] = field(s, HIST_BASE[k] + s->lv[k][2]);
+        a.f1[k] = field(s, HIST_BASE[k] + tgt[k]);
+        a.up[k] = field(s, O3D_F_UX_PRED + k);
+        if (!a.u[k] || !a.f2[k] || !a.f3[k] || !a.f1[k] || !a.up[k]) return O3D_ERR_CUDA;
+    }
+    a.nu_t = field(s, O3D_F_NU_T);
+    if (!a.nu_t) return O3D_ERR_CUDA;
+    a.cx = s->cx, a.cy = s->cy, a.cz = s->cz;
+    a.onere = 1.0 / c.re;  // src/integration.f90:106
+    a.adu = adu, a.bdu = bdu, a.cdu = cdu;
+    const double csd = c.cs * c.delta;
+    a.csd2 = csd * csd;  // (cs*delta)**2, src/les_turbulence.f90:87
+    a.iles = (c.iles == 1);
+    a.zchunk = 0;
+    if (c.nranks > 1 && (rc = comm_exchange(s, u, 3, R))) return rc;
+    span_begin(s, ST_RHS);
+    if (launch_rhs(s->st, s->g, a)) {
+        set_error("rhs kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return O3D_ERR_CUDA;
+    }
+    span_end(s, ST_RHS, 1);
+    for (int k = 0; k < 3; ++k) hist_rotate(s, k, tgt[k]);
+    return O3D_OK;
+}
+
+int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
+    if (!s) return O3D_ERR_INVALID;
+    const o3d_config& c = s->cfg;
+    if (c.multigrid != 1 && s->sor_variant < 0) {
+        set_error("poisson_solver pointer is null for these boundary flags "
+                  "(src/initialization.f90:283-301)");
+        return O3D_ERR_BC;
+    }
+    double* up[3] = {field(s, O3D_F_UX_PRED), field(s, O3D_F_UY_PRED), field(s, O3D_F_UZ_PRED)};
+    double* rhs = field(s, O3D_F_RHS);
+    double* pp = field(s, O3D_F_PP);
+    if (!up[0] || !up[1] || !up[2] || !rhs || !pp) return O3D_ERR_CUDA;
+    int rc;
+    if (c.nranks > 1 && (rc = comm_exchange(s, up + 2, 1, R))) return rc;  // only d/dz needs ghosts
+    span_begin(s, ST_DIV);
+    if (launch_div(s->st, s->g, up[0], up[1], up[2], s->cx, s->cy, s->cz, 1, 1, c.dt, rhs))
+        return O3D_ERR_CUDA;
+    span_end(s, ST_DIV, 1);
+    if (c.multigrid == 1) {
+        int cycles = 0;
+        rc = mg_solve(s, pp, rhs, c.kmax, 5, 4, c.eps, &cycles, dmax);  // src/integration.f90:244
+        if (iters) *iters = cycles;
+        return rc;
+    }
+    return sor_solve(s, pp, rhs, iters, dmax);
+}
+
+int o3d_s_correct_velocity(o3d_session* s) {
+    if (!s) return O3D_ERR_INVALID;
+    const o3d_config& c = s->cfg;
+    double* up[3] = {field(s, O3D_F_UX_PRED), field(s, O3D_F_UY_PRED), field(s, O3D_F_UZ_PRED)};
+    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
+    double* pp = field(s, O3D_F_PP);
+    for (int k = 0; k < 3; ++k)
+        if (!up[k] || !u[k]) return O3D_ERR_CUDA;
+    if (!pp) return O3D_ERR_CUDA;
+    int rc;
+    if (c.nranks > 1 && (rc = comm_exchange(s, &pp, 1, R))) return rc;
+    O3D_CUDA_CHECK(cudaMemsetAsync(s->flag_d, 0, sizeof(int), s->st));
+    span_begin(s, ST_CORR);
+    if (launch_corr(s->st, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d))
+        return O3D_ERR_CUDA;
+    span_end(s, ST_CORR, 1);
+    O3D_CUDA_CHECK(
+        cudaMemcpyAsync(s->flag_h, s->flag_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    if (*s->flag_h) {
+        set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
+        return O3D_ERR_DIVERGED;
+    }
+    return O3D_OK;
+}
+
+int o3d_s_transeq(o3d_session* s, int itime) {
+    if (!s) return O3D_ERR_INVALID;
+    const o3d_config& c = s->cfg;
+    double adu, bdu, cdu;
+    int rc = ab_select(c, itime, &adu, &bdu, &cdu);
+    if (rc) return rc;
+    TranseqArgs a;
+    double* phi = field(s, O3D_F_PHI);
+    double* phi_new = field(s, O3D_F_SCRATCH0);
+    const int tgt = hist_target(s, 3);
+    a.phi = phi;
+    a.phi_new = phi_new;
+    for (int k = 0; k < 3; ++k) a.u[k] = field(s, O3D_F_UX + k);
+    a.nu_t = field(s, O3D_F_NU_T);
+    // src is never assigned in the reference (src/initialization.f90:159): NULL == 0
+    a.src = s->use_src ? field(s, O3D_F_SCRATCH1) : nullptr;
+    a.f2 = field(s, HIST_BASE[3] + s->lv[3][1]);
+    a.f3 = field(s, HIST_BASE[3] + s->lv[3][2]);
+    a.f1 = field(s, HIST_BASE[3] + tgt);
+    if (!phi || !phi_new || !a.u[0] || !a.u[1] || !a.u[2] || !a.nu_t || !a.f2 || !a.f3 || !a.f1)
+        return O3D_ERR_CUDA;
+    const int nb = transeq_blocks(s->g);
+    if ((rc = ensure_partial(s, 3ll * nb))) return rc;
+    a.partial = s->partial;
+    a.cx = s->cx, a.cy = s->cy, a.cz = s->cz;
+    a.resc = c.re * c.sc;
+    a.sc = c.sc;
+    a.adu = adu, a.bdu = bdu, a.cdu = cdu;
+    a.iles = (c.iles == 1);
+    a.zchunk = 0;
+    if (c.nranks > 1 && (rc = comm_exchange(s, &phi, 1, R))) return rc;
+    span_begin(s, ST_TRANSEQ);
+    if (launch_transeq_rhs(s->st, s->g, a)) return O3D_ERR_CUDA;
+    if (launch_sum_partials(s->st, s->partial, nb, 3, s->scal_d)) return O3D_ERR_CUDA;
+    if (c.nranks > 1 && (rc = comm_allreduce(s, s->scal_d, 3, RED_SUM))) return rc;
+    const double count = (double)((long long)c.nx * c.ny * c.nz);
+    if (launch_transeq_clip(s->st, s->nloc, phi_new, phi, s->scal_d, count)) return O3D_ERR_CUDA;
+    span_end(s, ST_TRANSEQ, 1);
+    hist_rotate(s, 3, tgt);
+    return O3D_OK;
+}
+
+int o3d_step(o3d_session* s, int itime, int* iters, double* dmax) {
+    // src/osinco3d_main.f90:105-115
+    int rc;
+    if ((rc = o3d_s_predict_velocity(s, itime))) return rc;
+    if ((rc = o3d_s_correct_pression(s, iters, dmax))) return rc;
+    if ((rc = o3d_s_correct_velocity(s))) return rc;
+    if (s->cfg.nscr == 1 && (rc = o3d_s_transeq(s, itime))) return rc;
+    return O3D_OK;
+}
+
+// ---- diagnostics -------------------------------------------------------------------------
+int o3d_s_divergence(o3d_session* s, int fx, int fy, int fz, int dst, int odd) {
+    if (!s) return O3D_ERR_INVALID;
+    double* f[3] = {field(s, phys_id(s, fx)), field(s, phys_id(s, fy)), field(s, phys_id(s, fz))};
+    double* out = field(s, phys_id(s, dst));
+    if (!f[0] || !f[1] || !f[2] || !out) return O3D_ERR_CUDA;
+    int rc;
+    if (s->cfg.nranks > 1 && (rc = comm_exchange(s, f + 2, 1, R))) return rc;
+    if (launch_div(s->st, s->g, f[0], f[1], f[2], s->cx, s->cy, s->cz, odd, 0, 1.0, out))
+        return O3D_ERR_CUDA;
+    return O3D_OK;
+}
+
+int o3d_s_reduce(o3d_session* s, int fid, int op, double* out) {
+    if (!s || !out || op < 0 || op > 3) return O3D_ERR_INVALID;
+    double* f = field(s, phys_id(s, fid));
+    if (!f) return O3D_ERR_CUDA;
+    int rc;
+    if ((rc = ensure_partial(s, reduce_blocks(s->nloc)))) return rc;
+    if (launch_reduce(s->st, f, s->nloc, op, s->partial, s->scal_d + 8)) return O3D_ERR_CUDA;
+    if (s->cfg.nranks > 1 && (rc = comm_allreduce(s, s->scal_d + 8, 1, op))) return rc;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h + 8, s->scal_d + 8, sizeof(double),
+                                   cudaMemcpyDeviceToHost, s->st));
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    *out = s->scal_h[8];
+    return O3D_OK;
+}
+
+int o3d_s_function_stats(o3d_session* s, int fid, double* stats6) {
+    if (!s || !stats6) return O3D_ERR_INVALID;
+    if (s->cfg.nranks > 1) {
+        set_error("function_stats with argmax is single-rank; use o3d_s_reduce per rank");
+        return O3D_ERR_UNSUPPORTED;
+    }
+    double* f = field(s, phys_id(s, fid));
+    if (!f) return O3D_ERR_CUDA;
+    int rc;
+    if ((rc = ensure_partial(s, 4096))) return rc;
+    if (launch_function_stats(s->st, f, s->g.nx, s->g.ny, s->g.nz, s->partial, s->scal_d + 16))
+        return O3D_ERR_CUDA;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h + 16, s->scal_d + 16, 6 * sizeof(double),
+                                   cudaMemcpyDeviceToHost, s->st));
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    for (int q = 0; q < 6; ++q) stats6[q] = s->scal_h[16 + q];
+    return O3D_OK;
+}
+
+int o3d_s_statistics(o3d_session* s, double t, double* out17) {
+    if (!s || !out17) return O3D_ERR_INVALID;
+    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
+    if (!u[0] || !u[1] || !u[2]) return O3D_ERR_CUDA;
+    const int nb = stats_blocks(s->g);
+    int rc;
+    if ((rc = ensure_partial(s, 16ll * nb))) return rc;
+    if (s->cfg.nranks > 1 && (rc = comm_exchange(s, u, 3, R))) return rc;
+    if (launch_stats(s->st, s->g, u[0], u[1], u[2], s->cx, s->cy, s->cz, 1.0 / s->cfg.re,
+                     s->partial))
+        return O3D_ERR_CUDA;
+    if (launch_sum_partials(s->st, s->partial, nb, 16, s->scal_d + 32)) return O3D_ERR_CUDA;
+    if (s->cfg.nranks > 1 && (rc = comm_allreduce(s, s->scal_d + 32, 16, RED_SUM))) return rc;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h + 32, s->scal_d + 32, 16 * sizeof(double),
+                                   cudaMemcpyDeviceToHost, s->st));
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    const double cnt = (double)((long long)s->cfg.nx * s->cfg.ny * s->cfg.nz);
+    const double* a = s->scal_h + 32;
+    // stats.dat columns, src/IOfunctions.f90:504-552: t, e_k, eps, eps2, dzeta, u2,v2,w2, 9 x d1^2
+    out17[0] = t;
+    out17[1] = a[0] / cnt;
+    out17[2] = a[1] / cnt;
+    out17[3] = a[2] / cnt;
+    out17[4] = a[3] / cnt;
+    for (int q = 0; q < 12; ++q) out17[5 + q] = a[4 + q] / cnt;
+    return O3D_OK;
+}
+
+int o3d_s_rotational(o3d_session* s, int rotx, int roty, int rotz) {
+    if (!s) return O3D_ERR_INVALID;
+    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
+    double* r[3] = {field(s, phys_id(s, rotx)), field(s, phys_id(s, roty)),
+                    field(s, phys_id(s, rotz))};
+    for (int k = 0; k < 3; ++k)
+        if (!u[k] || !r[k]) return O3D_ERR_CUDA;
+    int rc;
+    if (s->cfg.nranks > 1) {
+        // curl uses the even closure for every term; ghost planes hold raw neighbour data, so the
+        // exchange is parity-agnostic
+        if ((rc = comm_exchange(s, u, 3, R))) return rc;
+    }
+    if (launch_rot(s->st, s->g, u[0], u[1], u[2], s->cx, s->cy, s->cz, r[0], r[1], r[2]))
+        return O3D_ERR_CUDA;
+    return O3D_OK;
+}
+
+int o3d_s_q_criterion(o3d_session* s, int dst) {
+    if (!s) return O3D_ERR_INVALID;
+    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
+    double* q = field(s, phys_id(s, dst));
+    if (!u[0] || !u[1] || !u[2] || !q) return O3D_ERR_CUDA;
+    int rc;
+    if (s->cfg.nranks > 1 && (rc = comm_exchange(s, u, 3, R))) return rc;
+    if (launch_qcrit(s->st, s->g, u[0], u[1], u[2], s->cx, s->cy, s->cz, q)) return O3D_ERR_CUDA;
+    return O3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// poisson.cu -- host drivers of the pressure Poisson solvers.
+//   sor_solve : reference poisson_solver_{0000,0011,111111} (src/poisson.f90), red-black fast
+//               path or lexicographic-wavefront verification ordering; exit tests and dynamic
+//               omega (src/poisson.f90:110-122) evaluated on the device.
+#include <cmath>
+
+#include "session.h"
+
+namespace o3d {
+
+static SorArgs make_sor_args(o3d_session* s, double* pp, const double* rhs) {
+    SorArgs a;
+    a.pp = pp;
+    a.rhs = rhs;
+    // src/poisson.f90:42-51
+    const double dx2 = s->cfg.dx * s->cfg.dx, dy2 = s->cfg.dy * s->cfg.dy,
+                 dz2 = s->cfg.dz * s->cfg.dz;
+    a.oneondx2 = 1.0 / dx2;
+    a.oneondy2 = 1.0 / dy2;
+    a.oneondz2 = 1.0 / dz2;
+    const double twoondx2 = 2.0 * a.oneondx2, twoondy2 = 2.0 * a.oneondy2,
+                 twoondz2 = 2.0 * a.oneondz2;
+    a.A = -(twoondx2 + twoondy2 + twoondz2);
+    a.invA = 1.0 / a.A;
+    // neighbour rule per variant: _0000 (periodic x3), _0011 (y mirrored), _111111 (all mirrored)
+    const int v = s->sor_variant;
+    a.mx = (v == 2) ? BM_MIRROR : BM_WRAP;
+    a.my = (v >= 1) ? BM_MIRROR : BM_WRAP;
+    const int mz = (v == 2) ? BM_MIRROR : BM_WRAP;
+    const int nr = s->cfg.nranks > 1 ? s->cfg.nranks : 1;
+    a.mz_lo = (nr > 1 && (s->cfg.rank > 0 || mz == BM_WRAP)) ? BM_HALO : mz;
+    a.mz_hi = (nr > 1 && (s->cfg.rank < nr - 1 || mz == BM_WRAP)) ? BM_HALO : mz;
+    a.nx = s->g.nx, a.ny = s->g.ny, a.nz = s->g.nz;
+    a.gz0 = s->z0;
+    a.gnz = s->cfg.nz;
+    a.seam_x = (a.mx == BM_WRAP) && (a.nx & 1);
+    a.seam_y = (a.my == BM_WRAP) && (a.ny & 1);
+    a.seam_z = (mz == BM_WRAP) && (a.gnz & 1);
+    return a;
+}
+
+static double sor_factor(const o3d_session* s) {
+    return s->sor_variant == 1 ? 1.01 : 1.05;  // src/poisson.f90:35,:162,:287
+}
+
+int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double* dmax) {
+    const o3d_config& c = s->cfg;
+    SorArgs a = make_sor_args(s, pp, rhs);
+    const bool multi = c.nranks > 1;
+    if (multi && c.sor_order == O3D_SOR_LEXI_WAVEFRONT) {
+        set_error("LEXI_WAVEFRONT ordering is a single-GPU verification mode");
+        return O3D_ERR_UNSUPPORTED;
+    }
+    // reset control block: dmax_old = 1609, src/poisson.f90:52
+    SorCtrl* h = s->ctrl_h;
+    h->dmax_bits = 0ull;
+    h->omega = s->omega;
+    h->dmax_old = 1609.0;
+    h->dmax_last = 0.0;
+    h->iter = 0;
+    h->done = (c.kmax < 1) ? 3 : 0;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(s->ctrl_d, h, sizeof(SorCtrl), cudaMemcpyHostToDevice, s->st));
+    const bool seams = a.seam_x || a.seam_y || a.seam_z;
+    const double factor = sor_factor(s);
+    int launched = 0;
+    int batch = s->last_iters > 0 ? s->last_iters : 8;
+    if (batch > 64) batch = 64;
+    if (c.sor_check_every > 0) batch = c.sor_check_every;
+    if (c.sor_order == O3D_SOR_LEXI_WAVEFRONT) batch = 1;
+    double* ppf[1] = {pp};
+    while (true) {
+        if (launched + batch > c.kmax) batch = c.kmax - launched;
+        if (batch < 1) batch = 1;
+        span_begin(s, ST_SOR);
+        for (int b = 0; b < batch; ++b) {
+            if (c.sor_order == O3D_SOR_LEXI_WAVEFRONT) {
+                const int nh = a.nx + a.ny + a.nz - 2;
+                for (int hpl = 0; hpl < nh; ++hpl)
+                    if (launch_sor_wavefront(s->st, a, hpl, s->ctrl_d)) return O3D_ERR_CUDA;
+            } else {
+                for (int colour = 0; colour < 2; ++colour) {
+                    if (multi && comm_exchange(s, ppf, 1, 1)) return O3D_ERR_COMM;
+                    if (launch_sor_rb(s->st, a, colour, 0, s->ctrl_d)) return O3D_ERR_CUDA;
+                }
+                if (seams) {
+                    for (int colour = 0; colour < 2; ++colour) {
+                        if (multi && comm_exchange(s, ppf, 1, 1)) return O3D_ERR_COMM;
+                        if (launch_sor_rb(s->st, a, colour, 1, s->ctrl_d)) return O3D_ERR_CUDA;
+                    }
+                }
+                if (multi &&
+                    comm_allreduce(s, reinterpret_cast<double*>(&s->ctrl_d->dmax_bits), 1,
+                                   RED_MAXBITS))
+                    return O3D_ERR_COMM;
+            }
+            if (launch_sor_control(s->st, s->ctrl_d, c.eps, c.kmax, c.idyn, factor))
+                return O3D_ERR_CUDA;
+        }
+        span_end(s, ST_SOR, 0);
+        launched += batch;
+        O3D_CUDA_CHECK(
+            cudaMemcpyAsync(h, s->ctrl_d, sizeof(SorCtrl), cudaMemcpyDeviceToHost, s->st));
+        O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+        if (h->done || launched >= c.kmax) break;
+        batch = 4;
+        if (c.sor_check_every > 0) batch = c.sor_check_every;
+        if (c.sor_order == O3D_SOR_LEXI_WAVEFRONT) batch = 1;
+    }
+    s->t_cnt[ST_SOR] += h->iter;
+    s->omega = h->omega;  // omega is intent(inout) and persists, src/integration.f90:222,247
+    s->last_iters = h->iter;
+    // Fortran `iter` after the loop: sweeps done, or kmax+1 when the loop ran out
+    if (iters) *iters = (h->done == 3 || h->done == 0) ? c.kmax + 1 : h->iter;
+    if (dmax) *dmax = h->dmax_last;
+    return O3D_OK;
+}
+
+int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npre, int npost,
+             double tol, int* cycles, double* dmax) {
+    (void)s, (void)pp, (void)rhs, (void)nlevels, (void)npre, (void)npost, (void)tol;
+    (void)cycles, (void)dmax;
+    set_error("multigrid V-cycle not built yet");
+    return O3D_ERR_UNSUPPORTED;
+}
+
+}  // namespace o3d

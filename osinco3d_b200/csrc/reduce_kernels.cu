@@ -1,0 +1,213 @@
+// reduce_kernels.cu -- device reductions for the per-step diagnostics the reference driver
+// runs on full fields (function_stats src/functions.f90:27, minval/maxval prints
+// src/IOfunctions.f90:322, compute_cfl src/utils.f90:178) and small utilities.
+// Two-stage, fixed-shape reductions: results are deterministic run to run (no FP atomics).
+#include "kernels.h"
+
+namespace o3d {
+namespace {
+
+constexpr int RB = 256;       // threads per block
+constexpr int RMAXB = 1184;   // 148 SMs x 8
+
+__device__ __forceinline__ double red_op(double a, double b, int op) {
+    if (op == RED_MIN) return fmin(a, b);
+    if (op == RED_SUM) return a + b;
+    return fmax(a, b);
+}
+__device__ __forceinline__ double red_init(int op) {
+    if (op == RED_MIN) return 1.7976931348623157e308;
+    if (op == RED_MAX) return -1.7976931348623157e308;
+    return 0.0;
+}
+
+__device__ __forceinline__ double block_reduce(double v, int op, double* red) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = red_op(v, __shfl_xor_sync(0xffffffffu, v, o), op);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double r = red_init(op);
+    if (tid < 32) {
+        r = (tid < RB / 32) ? red[tid] : red_init(op);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = red_op(r, __shfl_xor_sync(0xffffffffu, r, o), op);
+    }
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(RB) reduce_stage1(const double* __restrict__ f, long long n,
+                                                     int op, double* partial) {
+    __shared__ double red[32];
+    double v = red_init(op);
+    for (long long m = (long long)blockIdx.x * RB + threadIdx.x; m < n;
+         m += (long long)gridDim.x * RB) {
+        double x = __ldg(f + m);
+        if (op == RED_ABSMAX) x = fabs(x);
+        v = red_op(v, x, op);
+    }
+    v = block_reduce(v, op, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(RB) reduce_stage2(const double* partial, int nparts, int op,
+                                                     double* out) {
+    __shared__ double red[32];
+    double v = red_init(op);
+    for (int m = threadIdx.x; m < nparts; m += RB) v = red_op(v, partial[m], op);
+    v = block_reduce(v, op, red);
+    if (threadIdx.x == 0) *out = v;
+}
+
+// ncomp independent sums over partial[c*nparts + b]
+__global__ void __launch_bounds__(RB) sum_partials_kernel(const double* partial, int nparts,
+                                                           double* out) {
+    __shared__ double red[32];
+    const double* p = partial + (long long)blockIdx.x * nparts;
+    double v = 0.0;
+    for (int m = threadIdx.x; m < nparts; m += RB) v += p[m];
+    v = block_reduce(v, RED_SUM, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+}
+
+// function_stats: min, max (first occurrence in i-fastest order), sum
+struct StatAcc {
+    double mn, mx, sum;
+    long long imx;
+};
+__device__ __forceinline__ void stat_merge(StatAcc& a, const StatAcc& b) {
+    a.mn = fmin(a.mn, b.mn);
+    a.sum += b.sum;
+    if (b.mx > a.mx || (b.mx == a.mx && b.imx < a.imx)) {
+        a.mx = b.mx;
+        a.imx = b.imx;
+    }
+}
+__device__ __forceinline__ StatAcc stat_shfl(const StatAcc& a, int o) {
+    StatAcc b;
+    b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
+    b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
+    b.sum = __shfl_xor_sync(0xffffffffu, a.sum, o);
+    b.imx = __shfl_xor_sync(0xffffffffu, a.imx, o);
+    return b;
+}
+__device__ __forceinline__ StatAcc stat_block(StatAcc v, StatAcc* red) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const StatAcc b = stat_shfl(v, o);
+        stat_merge(v, b);
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0)
+        for (int q = 1; q < RB / 32; ++q) stat_merge(v, red[q]);
+    __syncthreads();
+    return v;
+}
+__device__ __forceinline__ StatAcc stat_init() {
+    StatAcc a;
+    a.mn = 1.7976931348623157e308;   // huge(), src/functions.f90:36
+    a.mx = -1.7976931348623157e308;  // -huge(), :37
+    a.sum = 0.0;
+    a.imx = 0x7fffffffffffffffLL;
+    return a;
+}
+
+__global__ void __launch_bounds__(RB) fstats_stage1(const double* __restrict__ f, long long n,
+                                                     double* partial) {
+    __shared__ StatAcc red[RB / 32];
+    StatAcc v = stat_init();
+    for (long long m = (long long)blockIdx.x * RB + threadIdx.x; m < n;
+         m += (long long)gridDim.x * RB) {
+        const double x = __ldg(f + m);
+        v.mn = fmin(v.mn, x);
+        v.sum += x;
+        if (x > v.mx) {  // strict: first occurrence wins within a thread (m ascending)
+            v.mx = x;
+            v.imx = m;
+        }
+    }
+    v = stat_block(v, red);
+    if (threadIdx.x == 0) {
+        double* p = partial + 4ll * blockIdx.x;
+        p[0] = v.mn, p[1] = v.mx, p[2] = v.sum, p[3] = __longlong_as_double(v.imx);
+    }
+}
+
+__global__ void __launch_bounds__(RB) fstats_stage2(const double* partial, int nparts, int nx,
+                                                     int ny, int nz, double* out6) {
+    __shared__ StatAcc red[RB / 32];
+    StatAcc v = stat_init();
+    for (int b = threadIdx.x; b < nparts; b += RB) {
+        StatAcc t;
+        t.mn = partial[4ll * b], t.mx = partial[4ll * b + 1], t.sum = partial[4ll * b + 2];
+        t.imx = __double_as_longlong(partial[4ll * b + 3]);
+        stat_merge(v, t);
+    }
+    v = stat_block(v, red);
+    if (threadIdx.x == 0) {
+        out6[0] = v.mn;
+        out6[1] = v.mx;
+        out6[2] = v.sum / (double)((long long)nx * ny * nz);  // src/functions.f90:61
+        long long m = v.imx;
+        if (m == 0x7fffffffffffffffLL) m = 0;  // all values <= -huge: reference keeps (1,1,1)
+        out6[3] = (double)(m % nx + 1);
+        out6[4] = (double)((m / nx) % ny + 1);
+        out6[5] = (double)(m / ((long long)nx * ny) + 1);
+    }
+}
+
+__global__ void fill_kernel(double* p, long long n, double v) {
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < n;
+         m += (long long)gridDim.x * blockDim.x)
+        p[m] = v;
+}
+
+}  // namespace
+
+int reduce_blocks(long long n) {
+    long long b = (n + RB - 1) / RB;
+    if (b > RMAXB) b = RMAXB;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int launch_reduce(cudaStream_t st, const double* f, long long n, int op, double* partial,
+                  double* out) {
+    const int nb = reduce_blocks(n);
+    reduce_stage1<<<nb, RB, 0, st>>>(f, n, op, partial);
+    reduce_stage2<<<1, RB, 0, st>>>(partial, nb, op == RED_ABSMAX ? RED_MAX : op, out);
+    count_launch(2);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_function_stats(cudaStream_t st, const double* f, int nx, int ny, int nz,
+                          double* partial, double* out6) {
+    const long long n = (long long)nx * ny * nz;
+    int nb = reduce_blocks(n);
+    if (nb > RMAXB / 4) nb = RMAXB / 4;  // partial holds 4 doubles per block
+    fstats_stage1<<<nb, RB, 0, st>>>(f, n, partial);
+    fstats_stage2<<<1, RB, 0, st>>>(partial, nb, nx, ny, nz, out6);
+    count_launch(2);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_sum_partials(cudaStream_t st, const double* partial, int nparts, int ncomp,
+                        double* out) {
+    sum_partials_kernel<<<ncomp, RB, 0, st>>>(partial, nparts, out);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_fill(cudaStream_t st, double* p, long long n, double v) {
+    long long b = (n + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    fill_kernel<<<(unsigned)b, 256, 0, st>>>(p, n, v);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace o3d

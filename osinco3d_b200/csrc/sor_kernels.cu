@@ -1,0 +1,220 @@
+// sor_kernels.cu -- pressure Poisson SOR (src/poisson.f90:6-381).
+//
+// The reference sweeps lexicographically (loop-carried dependence in i, j and k).  Two
+// orderings are provided:
+//   * RED_BLACK  (fast path): colour = (i+j+k) mod 2 with the GLOBAL k.  On an odd periodic
+//     extent planes 0 and n-1 are same-colour neighbours, so the last plane of such an axis is a
+//     "seam": points are further split by the parity of the number of seam planes they lie on.
+//     Neighbouring points always differ in colour or in seam parity, so each of the (up to) four
+//     classes is an independent set and the sweep is race-free and deterministic.
+//   * LEXI_WAVEFRONT (verification): hyperplanes i+j+k = h in ascending h; all points of a
+//     hyperplane are independent and their neighbours are exactly as "old"/"new" as in the
+//     lexicographic sweep, so the iterates are bit-identical to the reference's.
+// Exit tests and the dynamic-omega rule (src/poisson.f90:110-122) run on the device in
+// sor_control_kernel so the host only polls a flag every few iterations.
+#include "kernels.h"
+
+namespace o3d {
+namespace {
+
+constexpr int SBX = 64, SBY = 4;
+
+__device__ __forceinline__ void nbr_idx(int p, int n, int mlo, int mhi, int& m1, int& p1) {
+    // src/poisson.f90:57-66 (periodic) / :197-206 (mirrored); BM_HALO: stored ghost plane
+    m1 = p - 1;
+    p1 = p + 1;
+    if (p == 0) {
+        if (mlo == BM_WRAP) m1 = n - 1;
+        else if (mlo == BM_MIRROR) m1 = 1;
+    }
+    if (p == n - 1) {
+        if (mhi == BM_WRAP) p1 = 0;
+        else if (mhi == BM_MIRROR) p1 = n - 2;
+    }
+}
+
+__device__ __forceinline__ int seam_pop(const SorArgs& a, int i, int j, int gk) {
+    return (a.seam_x && i == a.nx - 1) + (a.seam_y && j == a.ny - 1) +
+           (a.seam_z && gk == a.gnz - 1);
+}
+
+__device__ __forceinline__ double sor_point(const SorArgs& a, int i, int j, int k,
+                                            double omega) {
+    const long long sy = a.nx, sz = (long long)a.nx * a.ny;
+    int im1, ip1, jm1, jp1, km1, kp1;
+    nbr_idx(i, a.nx, a.mx, a.mx, im1, ip1);
+    nbr_idx(j, a.ny, a.my, a.my, jm1, jp1);
+    nbr_idx(k, a.nz, a.mz_lo, a.mz_hi, km1, kp1);
+    const long long row = (long long)k * sz + (long long)j * sy;
+    const long long m = row + i;
+    const double pw = a.pp[row + im1], pe = a.pp[row + ip1];
+    const double ps = a.pp[(long long)k * sz + (long long)jm1 * sy + i];
+    const double pn = a.pp[(long long)k * sz + (long long)jp1 * sy + i];
+    const double pb = a.pp[(long long)km1 * sz + (long long)j * sy + i];
+    const double pt = a.pp[(long long)kp1 * sz + (long long)j * sy + i];
+    const double pc = a.pp[m];
+    // src/poisson.f90:95-98 with "/ A" replaced by "* (1/A)" (this ordering is not bit-parity)
+    const double p_new = (-(a.oneondx2 * (pw + pe)) - a.oneondy2 * (ps + pn) -
+                          a.oneondz2 * (pb + pt) + __ldg(a.rhs + m)) *
+                         a.invA;
+    a.pp[m] = (1.0 - omega) * pc + omega * p_new;  // :102
+    return fabs(p_new - pc);                       // :100
+}
+
+// bulk classes (seam parity 0)
+__global__ void __launch_bounds__(SBX* SBY) sor_rb_kernel(const SorArgs a, int colour,
+                                                          SorCtrl* ctrl, int zchunk) {
+    __shared__ double red[32];
+    if (*((volatile int*)&ctrl->done)) return;
+    const double omega = *((volatile double*)&ctrl->omega);
+    const int ii = blockIdx.x * SBX + threadIdx.x;
+    const int j = blockIdx.y * SBY + threadIdx.y;
+    const int kb = blockIdx.z * zchunk, ke = min(a.nz, kb + zchunk);
+    double dmax = 0.0;
+    if (j < a.ny) {
+        for (int k = kb; k < ke; ++k) {
+            const int gk = a.gz0 + k;
+            const int i = 2 * ii + ((j + gk + colour) & 1);
+            if (i < a.nx && !(seam_pop(a, i, j, gk) & 1))
+                dmax = fmax(dmax, sor_point(a, i, j, k, omega));
+        }
+    }
+    const double bm = block_max(dmax, red);
+    if (threadIdx.x == 0 && threadIdx.y == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+}
+
+// seam classes (seam parity 1): the union of the seam planes, flattened
+__global__ void __launch_bounds__(256) sor_seam_kernel(const SorArgs a, int colour,
+                                                       SorCtrl* ctrl, long long nxf,
+                                                       long long nyf, long long nzf) {
+    __shared__ double red[32];
+    if (*((volatile int*)&ctrl->done)) return;
+    const double omega = *((volatile double*)&ctrl->omega);
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double dmax = 0.0;
+    int i = -1, j = -1, k = -1;
+    bool ok = false;
+    if (t < nxf) {  // x seam plane: (nx-1, j, k)
+        i = a.nx - 1;
+        j = (int)(t % a.ny);
+        k = (int)(t / a.ny);
+        ok = true;
+    } else if ((t -= nxf) < nyf) {  // y seam plane, excluding points on the x seam
+        j = a.ny - 1;
+        i = (int)(t % a.nx);
+        k = (int)(t / a.nx);
+        ok = !(a.seam_x && i == a.nx - 1);
+    } else if ((t -= nyf) < nzf) {  // z seam plane (owned by the last rank)
+        k = a.nz - 1;
+        i = (int)(t % a.nx);
+        j = (int)(t / a.nx);
+        ok = !(a.seam_x && i == a.nx - 1) && !(a.seam_y && j == a.ny - 1);
+    }
+    if (ok) {
+        const int gk = a.gz0 + k;
+        if (((i + j + gk) & 1) == colour && (seam_pop(a, i, j, gk) & 1))
+            dmax = sor_point(a, i, j, k, omega);
+    }
+    const double bm = block_max(dmax, red);
+    if (threadIdx.x == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+}
+
+// one hyperplane of the lexicographic sweep, reference arithmetic (division by A)
+__global__ void __launch_bounds__(256) sor_wavefront_kernel(const SorArgs a, int h,
+                                                            SorCtrl* ctrl) {
+    __shared__ double red[32];
+    if (*((volatile int*)&ctrl->done)) return;
+    const double omega = *((volatile double*)&ctrl->omega);
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int k = blockIdx.y * 8 + threadIdx.y;
+    double d = 0.0;
+    const int i = h - j - k;
+    if (j < a.ny && k < a.nz && i >= 0 && i < a.nx) {
+        const long long sy = a.nx, sz = (long long)a.nx * a.ny;
+        int im1, ip1, jm1, jp1, km1, kp1;
+        nbr_idx(i, a.nx, a.mx, a.mx, im1, ip1);
+        nbr_idx(j, a.ny, a.my, a.my, jm1, jp1);
+        nbr_idx(k, a.nz, a.mz_lo, a.mz_hi, km1, kp1);
+        const long long m = (long long)k * sz + (long long)j * sy + i;
+        const double pw = a.pp[(long long)k * sz + (long long)j * sy + im1];
+        const double pe = a.pp[(long long)k * sz + (long long)j * sy + ip1];
+        const double ps = a.pp[(long long)k * sz + (long long)jm1 * sy + i];
+        const double pn = a.pp[(long long)k * sz + (long long)jp1 * sy + i];
+        const double pb = a.pp[(long long)km1 * sz + (long long)j * sy + i];
+        const double pt = a.pp[(long long)kp1 * sz + (long long)j * sy + i];
+        const double pc = a.pp[m];
+        const double p_new = (-(a.oneondx2 * (pw + pe)) - a.oneondy2 * (ps + pn) -
+                              a.oneondz2 * (pb + pt) + a.rhs[m]) /
+                             a.A;  // src/poisson.f90:95-98
+        d = fabs(p_new - pc);
+        a.pp[m] = (1.0 - omega) * pc + omega * p_new;
+    }
+    const double bm = block_max(d, red);
+    if (threadIdx.x == 0 && threadIdx.y == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+}
+
+// src/poisson.f90:110-122, evaluated once per completed sweep
+__global__ void sor_control_kernel(SorCtrl* c, double eps, int kmax, int idyn, double factor) {
+    if (c->done) return;
+    const double dmax = __longlong_as_double((long long)c->dmax_bits);
+    c->dmax_bits = 0ull;
+    const int iter = c->iter + 1;
+    c->iter = iter;
+    c->dmax_last = dmax;
+    if (dmax < eps) {  // :110
+        c->done = 1;
+        return;
+    }
+    if (fabs(c->dmax_old - dmax) < eps / 1000.0) {  // :111-114
+        c->done = 2;
+        return;
+    }
+    if (iter > 1 && idyn == 1) {  // :115-121
+        if (dmax > c->dmax_old)
+            c->omega = c->omega * (2.0 - factor);
+        else if (dmax < 0.1 * c->dmax_old)
+            c->omega = fmin(c->omega * factor, 2.0);
+    }
+    c->dmax_old = dmax;
+    if (iter >= kmax) c->done = 3;  // loop exhausted
+}
+
+}  // namespace
+
+int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl) {
+    if (seam_class == 0) {
+        const int half = (a.nx + 1) / 2;
+        const int gx = (half + SBX - 1) / SBX, gy = (a.ny + SBY - 1) / SBY;
+        const int zchunk = pick_zchunk(gx * gy, a.nz);
+        sor_rb_kernel<<<dim3(gx, gy, (a.nz + zchunk - 1) / zchunk), dim3(SBX, SBY, 1), 0, st>>>(
+            a, colour, ctrl, zchunk);
+    } else {
+        const long long nxf = a.seam_x ? (long long)a.ny * a.nz : 0;
+        const long long nyf = a.seam_y ? (long long)a.nx * a.nz : 0;
+        // the z seam is the last GLOBAL plane: only the rank that owns it sweeps it
+        const bool own_z = a.seam_z && (a.gz0 + a.nz == a.gnz);
+        const long long nzf = own_z ? (long long)a.nx * a.ny : 0;
+        const long long tot = nxf + nyf + nzf;
+        if (tot == 0) return 0;
+        sor_seam_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, colour, ctrl, nxf, nyf,
+                                                                       nzf);
+    }
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_sor_control(cudaStream_t st, SorCtrl* ctrl, double eps, int kmax, int idyn,
+                       double factor) {
+    sor_control_kernel<<<1, 1, 0, st>>>(ctrl, eps, kmax, idyn, factor);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_sor_wavefront(cudaStream_t st, const SorArgs& a, int h, SorCtrl* ctrl) {
+    sor_wavefront_kernel<<<dim3((a.ny + 31) / 32, (a.nz + 7) / 8), dim3(32, 8, 1), 0, st>>>(a, h,
+                                                                                          ctrl);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace o3d
