@@ -70,6 +70,8 @@ enum {
 
 const char* o3d_last_error(void);
 int o3d_abi_version(void);
+/* sizeof(o3d_config) as compiled (binding self-check for FFI mirrors of the struct) */
+int o3d_config_size(void);
 /* number of CUDA devices visible (0 if none / no driver) */
 int o3d_device_count(void);
 /* select the device used by this process (default 0; multi-GPU: LOCAL_RANK) */
@@ -273,6 +275,10 @@ int o3d_set_omega(o3d_session* s, double omega);
  * out[4]=transeq out[5]=halo exchange; counts[] = launches per stage */
 int o3d_s_timers(o3d_session* s, double* ms6, long long* counts6, int reset);
 int o3d_s_enable_timers(o3d_session* s, int on);
+/* stopwatch on the session stream (CUDA events): bench.py brackets its timed region with these
+ * because torch.cuda.Event only sees torch's current stream.  stop synchronises the stream. */
+int o3d_s_stopwatch_start(o3d_session* s);
+int o3d_s_stopwatch_stop(o3d_session* s, double* ms);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ from ._lib import (CLOSURE_00, CLOSURE_2DSIM, CLOSURE_I11, CLOSURE_P11, FREE_SLI
                    PERIODIC, RED_ABSMAX, RED_MAX, RED_MIN, RED_SUM, SOR_LEXI_WAVEFRONT,
                    SOR_RED_BLACK, O3DError, lib)
 from . import modules  # noqa: F401
-from .session import Session, make_config, nccl_unique_id  # noqa: F401
+from .session import PinnedPool, Session, make_config, nccl_unique_id  # noqa: F401
 
 
 def device_count():

@@ -90,6 +90,11 @@ def lib():
         _lib.o3d_set_omega.argtypes = [C.c_void_p, C.c_double]
         _lib.o3d_s_timers.argtypes = [C.c_void_p, dp, C.POINTER(C.c_longlong), C.c_int]
         _lib.o3d_s_enable_timers.argtypes = [C.c_void_p, C.c_int]
+        _lib.o3d_s_stopwatch_start.argtypes = [C.c_void_p]
+        _lib.o3d_s_stopwatch_stop.argtypes = [C.c_void_p, dp]
+        _lib.o3d_host_register.argtypes = [C.c_void_p, C.c_ulonglong]
+        _lib.o3d_host_unregister.argtypes = [C.c_void_p]
+        _lib.o3d_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     return _lib
 
 

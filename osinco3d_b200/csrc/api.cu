@@ -181,6 +181,7 @@ extern "C" {
 
 const char* o3d_last_error(void) { return g_err; }
 int o3d_abi_version(void) { return O3D_ABI_VERSION; }
+int o3d_config_size(void) { return (int)sizeof(o3d_config); }
 long long o3d_kernel_launches(void) { return g_launches.load(); }
 
 int o3d_device_count(void) {
@@ -282,6 +283,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->use_src = 0;
     for (int q2 = 0; q2 < 6; ++q2) s->t_ms[q2] = 0.0, s->t_cnt[q2] = 0;
     s->st = nullptr;
+    s->sw_a = nullptr, s->sw_b = nullptr;
     s->ctrl_d = nullptr, s->ctrl_h = nullptr, s->flag_d = nullptr, s->flag_h = nullptr;
     s->scal_d = nullptr, s->scal_h = nullptr;
     fill_dims(s);
@@ -324,6 +326,8 @@ int o3d_session_destroy(o3d_session* s) {
         if (sp.b) cudaEventDestroy(sp.b);
     }
     for (auto e : s->free_events) cudaEventDestroy(e);
+    if (s->sw_a) cudaEventDestroy(s->sw_a);
+    if (s->sw_b) cudaEventDestroy(s->sw_b);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return O3D_OK;
@@ -397,6 +401,24 @@ int o3d_s_timers(o3d_session* s, double* ms6, long long* counts6, int reset) {
         if (counts6) counts6[q] = s->t_cnt[q];
         if (reset) s->t_ms[q] = 0.0, s->t_cnt[q] = 0;
     }
+    return O3D_OK;
+}
+
+int o3d_s_stopwatch_start(o3d_session* s) {
+    if (!s) return O3D_ERR_INVALID;
+    if (!s->sw_a) O3D_CUDA_CHECK(cudaEventCreate(&s->sw_a));
+    if (!s->sw_b) O3D_CUDA_CHECK(cudaEventCreate(&s->sw_b));
+    O3D_CUDA_CHECK(cudaEventRecord(s->sw_a, s->st));
+    return O3D_OK;
+}
+
+int o3d_s_stopwatch_stop(o3d_session* s, double* ms) {
+    if (!s || !ms || !s->sw_a) return O3D_ERR_INVALID;
+    O3D_CUDA_CHECK(cudaEventRecord(s->sw_b, s->st));
+    O3D_CUDA_CHECK(cudaEventSynchronize(s->sw_b));
+    float t = 0.f;
+    O3D_CUDA_CHECK(cudaEventElapsedTime(&t, s->sw_a, s->sw_b));
+    *ms = t;
     return O3D_OK;
 }
 

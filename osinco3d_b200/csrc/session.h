@@ -45,6 +45,7 @@ struct o3d_session {
     std::vector<Span> pending;
     std::vector<cudaEvent_t> free_events;
     double t_ms[6];
+    cudaEvent_t sw_a, sw_b;  // stopwatch
     long long t_cnt[6];
 };
 

@@ -158,6 +158,14 @@ class Session:
         names = ["rhs", "div", "sor", "corr", "transeq", "halo"]
         return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
+    def stopwatch_start(self):
+        check(lib().o3d_s_stopwatch_start(self._h))
+
+    def stopwatch_stop(self):
+        ms = C.c_double(0.0)
+        check(lib().o3d_s_stopwatch_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def close(self):
         if self._h:
             lib().o3d_session_destroy(self._h)
@@ -168,3 +176,30 @@ class Session:
             self.close()
         except Exception:
             pass
+
+
+class PinnedPool:
+    """Page-locked host arrays (cudaHostAlloc through o3d_host_alloc) so that the host-pointer
+    module procedures and upload/download run at full PCIe speed."""
+
+    def __init__(self):
+        self._ptrs = []
+
+    def empty(self, shape):
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        check(lib().o3d_host_alloc(C.byref(p), C.c_ulonglong(8 * n)))
+        self._ptrs.append(p)
+        buf = (C.c_double * n).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.float64).reshape(shape, order="F")
+        return a
+
+    def array(self, src):
+        a = self.empty(src.shape)
+        a[...] = src
+        return a
+
+    def close(self):
+        for p in self._ptrs:
+            lib().o3d_host_free(p)
+        self._ptrs = []
