@@ -279,8 +279,9 @@ def test_tgv_golden_row1_through_cuda_statistics(gpu, O):
     M.schemes(1, 1, 1, 1, 1, 1)
     st = M.statistics_calc(ux, uy, uz, d, d, d, 1600.0, 0.0)
     ref = np.array(gold["tgv_re1600_dns"]["rows"][0])
+    # 13 printed digits; eps2 (col 3) is a cancelling sum whose association differs on the GPU
     for c in range(17):
-        assert abs(st[c] - ref[c]) <= 6e-13 * max(abs(ref[c]), 1e-30) + 1e-300, (c, st[c], ref[c])
+        assert abs(st[c] - ref[c]) <= 1e-12 * max(abs(ref[c]), 1e-30) + 1e-300, (c, st[c], ref[c])
 
 
 def test_invalid_arguments(gpu):
