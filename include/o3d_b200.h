@@ -245,8 +245,13 @@ int o3d_session_slab(const o3d_session* s, int* z0, int* nz_local);
 /* host <-> device copies of this rank's slab of one field (nx*ny*nz_local doubles) */
 int o3d_upload(o3d_session* s, int field, const double* host);
 int o3d_download(o3d_session* s, int field, double* host);
-/* raw device pointer of a field's first owned plane (for zero-copy callers, e.g. torch) */
+/* Device fields are PADDED (ghost cells hold the boundary closure, DESIGN.md "Data layout"):
+ * element (i,j,k) of a field lives at dptr[i + stride_j*j + stride_k*k].  o3d_device_ptr returns
+ * the interior origin (0,0,0) for zero-copy callers; after writing through it call
+ * o3d_mark_modified so that the ghost cells are refreshed before the next stencil. */
 int o3d_device_ptr(o3d_session* s, int field, double** dptr);
+int o3d_session_layout(const o3d_session* s, long long* stride_j, long long* stride_k);
+int o3d_mark_modified(o3d_session* s, int field);
 
 /* hot-path stages; same order and meaning as src/osinco3d_main.f90:105-115 */
 int o3d_s_predict_velocity(o3d_session* s, int itime);

@@ -75,6 +75,9 @@ def lib():
         _lib.o3d_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.o3d_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         _lib.o3d_session_slab.argtypes = [C.c_void_p, ip, ip]
+        _lib.o3d_session_layout.argtypes = [C.c_void_p, C.POINTER(C.c_longlong),
+                                            C.POINTER(C.c_longlong)]
+        _lib.o3d_mark_modified.argtypes = [C.c_void_p, C.c_int]
         _lib.o3d_s_predict_velocity.argtypes = [C.c_void_p, C.c_int]
         _lib.o3d_s_correct_pression.argtypes = [C.c_void_p, ip, dp]
         _lib.o3d_s_correct_velocity.argtypes = [C.c_void_p]

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 
+#include "march.cuh"
 #include "session.h"
 
 // ------------------------------------------------------------------------------------------
@@ -71,7 +72,7 @@ int axis_bc(int b1, int bn, int* out) {
 double* field(o3d_session* s, int id) {
     if (id < 0 || id >= O3D_F_COUNT) return nullptr;
     if (!s->base[id]) {
-        const size_t n = (size_t)s->plane * (size_t)(s->nzl + 2 * R);
+        const size_t n = (size_t)s->felems;
         double* p = nullptr;
         if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) {
             (void)cudaGetLastError();
@@ -79,9 +80,80 @@ double* field(o3d_session* s, int id) {
             return nullptr;
         }
         cudaMemsetAsync(p, 0, n * sizeof(double), s->st);
+        if (make_field_tmap(&s->tmap[id], p, s->g.px, s->g.py, s->g.nz + 2 * GH, MBX, MBY)) {
+            cudaFree(p);
+            return nullptr;
+        }
         s->base[id] = p;
+        // an all-zero field has valid ghosts for any closure
+        s->gaxes[id] = 0x7u;
+        s->gpar[id] = natural_parity(id);
     }
-    return s->base[id] + (size_t)R * s->plane;
+    return s->base[id] + interior_offset(s->g);
+}
+
+FieldRef fref(o3d_session* s, int id) {
+    FieldRef r;
+    r.p = field(s, id);
+    r.tm = &s->tmap[id];
+    return r;
+}
+
+unsigned natural_parity(int id) {
+    switch (id) {
+        case O3D_F_UX: case O3D_F_UX_PRED: return 0x1u;
+        case O3D_F_UY: case O3D_F_UY_PRED: return 0x2u;
+        case O3D_F_UZ: case O3D_F_UZ_PRED: return 0x4u;
+        default: return 0u;
+    }
+}
+
+void touch(o3d_session* s, int id) {
+    if (id >= 0 && id < O3D_F_COUNT) s->gaxes[id] = 0u;
+}
+
+int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, unsigned axes) {
+    GhostArgs a;
+    a.njobs = 0;
+    double* xbase[6];
+    int nx = 0;
+    const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO) && (axes & 0x4u);
+    for (int q = 0; q < n; ++q) {
+        const int id = ids[q];
+        double* p = field(s, id);
+        if (!p) return O3D_ERR_CUDA;
+        // axes that are missing, or present with the wrong parity
+        unsigned need = 0;
+        for (int ax = 0; ax < 3; ++ax) {
+            const unsigned bit = 1u << ax;
+            if (!(axes & bit)) continue;
+            const bool have = (s->gaxes[id] & bit) && ((s->gpar[id] & bit) == (par[q] & bit));
+            if (!have) need |= bit;
+        }
+        if (!need) continue;
+        GhostJob& jb = a.job[a.njobs++];
+        jb.p = p, jb.par = par[q], jb.axes = need;
+        if (zhalo && (need & 0x4u)) xbase[nx++] = s->base[id];
+        s->gaxes[id] |= need;
+        s->gpar[id] = (s->gpar[id] & ~need) | (par[q] & need);
+        if (a.njobs == 6 || q == n - 1) {
+            if (launch_fill_ghosts(s->st, s->g, a)) {
+                set_error("ghost fill launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return O3D_ERR_CUDA;
+            }
+            a.njobs = 0;
+        }
+    }
+    if (a.njobs && launch_fill_ghosts(s->st, s->g, a)) return O3D_ERR_CUDA;
+    if (nx) {
+        const int rc = comm_exchange(s, xbase, nx, R, s->cfg.nbcz1 == O3D_PERIODIC);
+        if (rc) return rc;
+    }
+    return O3D_OK;
+}
+
+int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes) {
+    return ensure_ghosts(s, &id, 1, &par, axes);
 }
 
 static const int HIST_BASE[4] = {O3D_F_FUX1, O3D_F_FUY1, O3D_F_FUZ1, O3D_F_FPHI1};
@@ -89,7 +161,7 @@ static const int HIST_BASE[4] = {O3D_F_FUX1, O3D_F_FUY1, O3D_F_FUZ1, O3D_F_FPHI1
 int hist_id(const o3d_session* s, int c, int level) { return HIST_BASE[c] + s->lv[c][level - 1]; }
 
 // translate a public field id (logical history levels) to a physical one
-static int phys_id(const o3d_session* s, int id) {
+int phys_id(const o3d_session* s, int id) {
     for (int c = 0; c < 4; ++c)
         if (id >= HIST_BASE[c] && id < HIST_BASE[c] + 3) return hist_id(s, c, id - HIST_BASE[c] + 1);
     return id;
@@ -152,10 +224,14 @@ static void resolve_spans(o3d_session* s) {
     s->pending.clear();
 }
 
-void fill_dims(o3d_session* s) {
+void fill_geom(o3d_session* s) {
     const o3d_config& c = s->cfg;
-    Dims& g = s->g;
+    Geom& g = s->g;
     g.nx = c.nx, g.ny = c.ny, g.nz = s->nzl;
+    g.px = pitch_for(c.nx);
+    g.py = c.ny + 2 * GH;
+    g.sy = g.px;
+    g.sz = (long long)g.px * g.py;
     g.bx = (c.nbcx1 == O3D_PERIODIC) ? BM_WRAP : BM_MIRROR;
     g.by = (c.nbcy1 == O3D_PERIODIC) ? BM_WRAP : BM_MIRROR;
     const int mz = (c.nbcz1 == O3D_PERIODIC) ? BM_WRAP : BM_MIRROR;
@@ -165,6 +241,7 @@ void fill_dims(o3d_session* s) {
     g.sim2d = c.sim2d;
     g.gz0 = s->z0;
     g.gnz = c.nz;
+    s->felems = field_elems(g);
     s->cx = make_coef(c.dx);
     s->cy = make_coef(c.dy);
     s->cz = make_coef(c.dz);
@@ -268,9 +345,9 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
         delete s;
         return O3D_ERR_INVALID;
     }
-    s->plane = (long long)cfg->nx * cfg->ny;
-    s->nloc = s->plane * s->nzl;
-    for (int f = 0; f < O3D_F_COUNT; ++f) s->base[f] = nullptr;
+    s->nloc = (long long)cfg->nx * cfg->ny * s->nzl;
+    for (int f = 0; f < O3D_F_COUNT; ++f) s->base[f] = nullptr, s->gaxes[f] = 0, s->gpar[f] = 0;
+    s->stage_d = nullptr;
     for (int c = 0; c < 4; ++c)
         for (int l = 0; l < 3; ++l) s->lv[c][l] = l;
     s->sor_variant = poisson_variant_of(cfg->nbcx1, cfg->nbcxn, cfg->nbcy1, cfg->nbcyn);
@@ -286,7 +363,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->sw_a = nullptr, s->sw_b = nullptr;
     s->ctrl_d = nullptr, s->ctrl_h = nullptr, s->flag_d = nullptr, s->flag_h = nullptr;
     s->scal_d = nullptr, s->scal_h = nullptr;
-    fill_dims(s);
+    fill_geom(s);
     cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&s->ctrl_d, sizeof(SorCtrl));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_h, sizeof(SorCtrl), cudaHostAllocDefault);
@@ -315,6 +392,7 @@ int o3d_session_destroy(o3d_session* s) {
     for (int f = 0; f < O3D_F_COUNT; ++f)
         if (s->base[f]) cudaFree(s->base[f]);
     if (s->partial) cudaFree(s->partial);
+    if (s->stage_d) cudaFree(s->stage_d);
     if (s->ctrl_d) cudaFree(s->ctrl_d);
     if (s->ctrl_h) cudaFreeHost(s->ctrl_h);
     if (s->flag_d) cudaFree(s->flag_d);
@@ -340,12 +418,26 @@ int o3d_session_slab(const o3d_session* s, int* z0, int* nz_local) {
     return O3D_OK;
 }
 
+static int ensure_stage(o3d_session* s) {
+    if (s->stage_d) return O3D_OK;
+    O3D_CUDA_CHECK(cudaMalloc(&s->stage_d, (size_t)s->nloc * sizeof(double)));
+    return O3D_OK;
+}
+
+// Host arrays are the reference's contiguous (nx,ny,nz) allocatables; device fields are padded.
+// A copy goes through one contiguous staging buffer so that the PCIe transfer is a single
+// full-speed DMA, followed / preceded by a pack kernel (HBM traffic, negligible next to PCIe).
 int o3d_upload(o3d_session* s, int fid, const double* host) {
     if (!s || !host) return O3D_ERR_INVALID;
-    double* d = field(s, phys_id(s, fid));
+    const int id = phys_id(s, fid);
+    double* d = field(s, id);
     if (!d) return O3D_ERR_CUDA;
-    O3D_CUDA_CHECK(cudaMemcpyAsync(d, host, (size_t)s->nloc * sizeof(double),
+    int rc = ensure_stage(s);
+    if (rc) return rc;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(s->stage_d, host, (size_t)s->nloc * sizeof(double),
                                    cudaMemcpyHostToDevice, s->st));
+    if (launch_pack(s->st, s->g, s->stage_d, d)) return O3D_ERR_CUDA;
+    touch(s, id);
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
     return O3D_OK;
 }
@@ -354,7 +446,10 @@ int o3d_download(o3d_session* s, int fid, double* host) {
     if (!s || !host) return O3D_ERR_INVALID;
     double* d = field(s, phys_id(s, fid));
     if (!d) return O3D_ERR_CUDA;
-    O3D_CUDA_CHECK(cudaMemcpyAsync(host, d, (size_t)s->nloc * sizeof(double),
+    int rc = ensure_stage(s);
+    if (rc) return rc;
+    if (launch_unpack(s->st, s->g, d, s->stage_d)) return O3D_ERR_CUDA;
+    O3D_CUDA_CHECK(cudaMemcpyAsync(host, s->stage_d, (size_t)s->nloc * sizeof(double),
                                    cudaMemcpyDeviceToHost, s->st));
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
     return O3D_OK;
@@ -366,6 +461,19 @@ int o3d_device_ptr(o3d_session* s, int fid, double** dptr) {
     if (!*dptr) return O3D_ERR_CUDA;
     // make the lazy zero-fill visible to other streams
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    return O3D_OK;
+}
+
+int o3d_session_layout(const o3d_session* s, long long* stride_j, long long* stride_k) {
+    if (!s) return O3D_ERR_INVALID;
+    if (stride_j) *stride_j = s->g.sy;
+    if (stride_k) *stride_k = s->g.sz;
+    return O3D_OK;
+}
+
+int o3d_mark_modified(o3d_session* s, int fid) {
+    if (!s) return O3D_ERR_INVALID;
+    touch(s, phys_id(s, fid));
     return O3D_OK;
 }
 
@@ -459,6 +567,11 @@ static void hist_rotate(o3d_session* s, int c, int target) {
     }
 }
 
+static const int VEL_IDS[3] = {O3D_F_UX, O3D_F_UY, O3D_F_UZ};
+static const int PRED_IDS[3] = {O3D_F_UX_PRED, O3D_F_UY_PRED, O3D_F_UZ_PRED};
+static const unsigned NAT3[3] = {0x1u, 0x2u, 0x4u};
+static const unsigned EVEN3[3] = {0u, 0u, 0u};
+
 int o3d_s_predict_velocity(o3d_session* s, int itime) {
     if (!s) return O3D_ERR_INVALID;
     const o3d_config& c = s->cfg;
@@ -466,16 +579,15 @@ int o3d_s_predict_velocity(o3d_session* s, int itime) {
     int rc = ab_select(c, itime, &adu, &bdu, &cdu);
     if (rc) return rc;
     RhsArgs a;
-    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
     int tgt[3];
     for (int k = 0; k < 3; ++k) {
-        a.u[k] = u[k];
+        a.u[k] = fref(s, VEL_IDS[k]);
         tgt[k] = hist_target(s, k);
         a.f2[k] = field(s, HIST_BASE[k] + s->lv[k][1]);
         a.f3[k] = field(s, HIST_BASE[k] + s->lv[k][2]);
         a.f1[k] = field(s, HIST_BASE[k] + tgt[k]);
-        a.up[k] = field(s, O3D_F_UX_PRED + k);
-        if (!a.u[k] || !a.f2[k] || !a.f3[k] || !a.f1[k] || !a.up[k]) return O3D_ERR_CUDA;
+        a.up[k] = field(s, PRED_IDS[k]);
+        if (!a.u[k].p || !a.f2[k] || !a.f3[k] || !a.f1[k] || !a.up[k]) return O3D_ERR_CUDA;
     }
     a.nu_t = field(s, O3D_F_NU_T);
     if (!a.nu_t) return O3D_ERR_CUDA;
@@ -485,15 +597,19 @@ int o3d_s_predict_velocity(o3d_session* s, int itime) {
     const double csd = c.cs * c.delta;
     a.csd2 = csd * csd;  // (cs*delta)**2, src/les_turbulence.f90:87
     a.iles = (c.iles == 1);
-    a.zchunk = 0;
-    if (c.nranks > 1 && (rc = comm_exchange(s, u, 3, R))) return rc;
+    // parity table of src/integration.f90:118-165 = natural-parity ghosts of ux, uy, uz
+    if ((rc = ensure_ghosts(s, VEL_IDS, 3, NAT3, 0x7u))) return rc;
     span_begin(s, ST_RHS);
     if (launch_rhs(s->st, s->g, a)) {
         set_error("rhs kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return O3D_ERR_CUDA;
     }
     span_end(s, ST_RHS, 1);
-    for (int k = 0; k < 3; ++k) hist_rotate(s, k, tgt[k]);
+    for (int k = 0; k < 3; ++k) {
+        hist_rotate(s, k, tgt[k]);
+        touch(s, PRED_IDS[k]);
+    }
+    if (a.iles) touch(s, O3D_F_NU_T);
     return O3D_OK;
 }
 
@@ -505,23 +621,28 @@ int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
                   "(src/initialization.f90:283-301)");
         return O3D_ERR_BC;
     }
-    double* up[3] = {field(s, O3D_F_UX_PRED), field(s, O3D_F_UY_PRED), field(s, O3D_F_UZ_PRED)};
+    FieldRef up[3] = {fref(s, O3D_F_UX_PRED), fref(s, O3D_F_UY_PRED), fref(s, O3D_F_UZ_PRED)};
     double* rhs = field(s, O3D_F_RHS);
     double* pp = field(s, O3D_F_PP);
-    if (!up[0] || !up[1] || !up[2] || !rhs || !pp) return O3D_ERR_CUDA;
+    if (!up[0].p || !up[1].p || !up[2].p || !rhs || !pp) return O3D_ERR_CUDA;
     int rc;
-    if (c.nranks > 1 && (rc = comm_exchange(s, up + 2, 1, R))) return rc;  // only d/dz needs ghosts
+    // divergence(..., odd = 1): derxi(ux*), deryi(uy*), derzi(uz*); each field only needs the
+    // ghosts of its own axis (src/differential_operators.f90:30-32)
+    for (int k = 0; k < 3; ++k)
+        if ((rc = ensure_ghosts1(s, PRED_IDS[k], NAT3[k], 1u << k))) return rc;
     span_begin(s, ST_DIV);
-    if (launch_div(s->st, s->g, up[0], up[1], up[2], s->cx, s->cy, s->cz, 1, 1, c.dt, rhs))
-        return O3D_ERR_CUDA;
+    if (launch_div(s->st, s->g, up, s->cx, s->cy, s->cz, 1, c.dt, rhs)) return O3D_ERR_CUDA;
     span_end(s, ST_DIV, 1);
+    touch(s, O3D_F_RHS);
     if (c.multigrid == 1) {
         int cycles = 0;
         rc = mg_solve(s, pp, rhs, c.kmax, 5, 4, c.eps, &cycles, dmax);  // src/integration.f90:244
         if (iters) *iters = cycles;
-        return rc;
+    } else {
+        rc = sor_solve(s, pp, rhs, iters, dmax);
     }
-    return sor_solve(s, pp, rhs, iters, dmax);
+    touch(s, O3D_F_PP);
+    return rc;
 }
 
 int o3d_s_correct_velocity(o3d_session* s) {
@@ -529,17 +650,18 @@ int o3d_s_correct_velocity(o3d_session* s) {
     const o3d_config& c = s->cfg;
     double* up[3] = {field(s, O3D_F_UX_PRED), field(s, O3D_F_UY_PRED), field(s, O3D_F_UZ_PRED)};
     double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
-    double* pp = field(s, O3D_F_PP);
+    FieldRef pp = fref(s, O3D_F_PP);
     for (int k = 0; k < 3; ++k)
         if (!up[k] || !u[k]) return O3D_ERR_CUDA;
-    if (!pp) return O3D_ERR_CUDA;
+    if (!pp.p) return O3D_ERR_CUDA;
     int rc;
-    if (c.nranks > 1 && (rc = comm_exchange(s, &pp, 1, R))) return rc;
+    if ((rc = ensure_ghosts1(s, O3D_F_PP, 0u, 0x7u))) return rc;  // derxp/deryp/derzp
     O3D_CUDA_CHECK(cudaMemsetAsync(s->flag_d, 0, sizeof(int), s->st));
     span_begin(s, ST_CORR);
     if (launch_corr(s->st, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d))
         return O3D_ERR_CUDA;
     span_end(s, ST_CORR, 1);
+    for (int k = 0; k < 3; ++k) touch(s, VEL_IDS[k]);
     O3D_CUDA_CHECK(
         cudaMemcpyAsync(s->flag_h, s->flag_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
@@ -560,7 +682,7 @@ int o3d_s_transeq(o3d_session* s, int itime) {
     double* phi = field(s, O3D_F_PHI);
     double* phi_new = field(s, O3D_F_SCRATCH0);
     const int tgt = hist_target(s, 3);
-    a.phi = phi;
+    a.phi = fref(s, O3D_F_PHI);
     a.phi_new = phi_new;
     for (int k = 0; k < 3; ++k) a.u[k] = field(s, O3D_F_UX + k);
     a.nu_t = field(s, O3D_F_NU_T);
@@ -579,16 +701,17 @@ int o3d_s_transeq(o3d_session* s, int itime) {
     a.sc = c.sc;
     a.adu = adu, a.bdu = bdu, a.cdu = cdu;
     a.iles = (c.iles == 1);
-    a.zchunk = 0;
-    if (c.nranks > 1 && (rc = comm_exchange(s, &phi, 1, R))) return rc;
+    if ((rc = ensure_ghosts1(s, O3D_F_PHI, 0u, 0x7u))) return rc;  // all "p" closures, :412-419
     span_begin(s, ST_TRANSEQ);
     if (launch_transeq_rhs(s->st, s->g, a)) return O3D_ERR_CUDA;
     if (launch_sum_partials(s->st, s->partial, nb, 3, s->scal_d)) return O3D_ERR_CUDA;
     if (c.nranks > 1 && (rc = comm_allreduce(s, s->scal_d, 3, RED_SUM))) return rc;
     const double count = (double)((long long)c.nx * c.ny * c.nz);
-    if (launch_transeq_clip(s->st, s->nloc, phi_new, phi, s->scal_d, count)) return O3D_ERR_CUDA;
+    if (launch_transeq_clip(s->st, s->g, phi_new, phi, s->scal_d, count)) return O3D_ERR_CUDA;
     span_end(s, ST_TRANSEQ, 1);
     hist_rotate(s, 3, tgt);
+    touch(s, O3D_F_PHI);
+    touch(s, O3D_F_SCRATCH0);
     return O3D_OK;
 }
 
@@ -605,13 +728,17 @@ int o3d_step(o3d_session* s, int itime, int* iters, double* dmax) {
 // ---- diagnostics -------------------------------------------------------------------------
 int o3d_s_divergence(o3d_session* s, int fx, int fy, int fz, int dst, int odd) {
     if (!s) return O3D_ERR_INVALID;
-    double* f[3] = {field(s, phys_id(s, fx)), field(s, phys_id(s, fy)), field(s, phys_id(s, fz))};
-    double* out = field(s, phys_id(s, dst));
-    if (!f[0] || !f[1] || !f[2] || !out) return O3D_ERR_CUDA;
+    const int ids[3] = {phys_id(s, fx), phys_id(s, fy), phys_id(s, fz)};
+    const int out_id = phys_id(s, dst);
+    FieldRef f[3] = {fref(s, ids[0]), fref(s, ids[1]), fref(s, ids[2])};
+    double* out = field(s, out_id);
+    if (!f[0].p || !f[1].p || !f[2].p || !out) return O3D_ERR_CUDA;
     int rc;
-    if (s->cfg.nranks > 1 && (rc = comm_exchange(s, f + 2, 1, R))) return rc;
-    if (launch_div(s->st, s->g, f[0], f[1], f[2], s->cx, s->cy, s->cz, odd, 0, 1.0, out))
-        return O3D_ERR_CUDA;
+    // src/differential_operators.f90:25-33: odd -> derxi/deryi/derzi, else derxp/deryp/derzp
+    for (int k = 0; k < 3; ++k)
+        if ((rc = ensure_ghosts1(s, ids[k], odd ? (1u << k) : 0u, 1u << k))) return rc;
+    if (launch_div(s->st, s->g, f, s->cx, s->cy, s->cz, 0, 1.0, out)) return O3D_ERR_CUDA;
+    touch(s, out_id);
     return O3D_OK;
 }
 
@@ -620,8 +747,8 @@ int o3d_s_reduce(o3d_session* s, int fid, int op, double* out) {
     double* f = field(s, phys_id(s, fid));
     if (!f) return O3D_ERR_CUDA;
     int rc;
-    if ((rc = ensure_partial(s, reduce_blocks(s->nloc)))) return rc;
-    if (launch_reduce(s->st, f, s->nloc, op, s->partial, s->scal_d + 8)) return O3D_ERR_CUDA;
+    if ((rc = ensure_partial(s, reduce_blocks(s->g)))) return rc;
+    if (launch_reduce(s->st, s->g, f, op, s->partial, s->scal_d + 8)) return O3D_ERR_CUDA;
     if (s->cfg.nranks > 1 && (rc = comm_allreduce(s, s->scal_d + 8, 1, op))) return rc;
     O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h + 8, s->scal_d + 8, sizeof(double),
                                    cudaMemcpyDeviceToHost, s->st));
@@ -640,8 +767,7 @@ int o3d_s_function_stats(o3d_session* s, int fid, double* stats6) {
     if (!f) return O3D_ERR_CUDA;
     int rc;
     if ((rc = ensure_partial(s, 4096))) return rc;
-    if (launch_function_stats(s->st, f, s->g.nx, s->g.ny, s->g.nz, s->partial, s->scal_d + 16))
-        return O3D_ERR_CUDA;
+    if (launch_function_stats(s->st, s->g, f, s->partial, s->scal_d + 16)) return O3D_ERR_CUDA;
     O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h + 16, s->scal_d + 16, 6 * sizeof(double),
                                    cudaMemcpyDeviceToHost, s->st));
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
@@ -651,14 +777,14 @@ int o3d_s_function_stats(o3d_session* s, int fid, double* stats6) {
 
 int o3d_s_statistics(o3d_session* s, double t, double* out17) {
     if (!s || !out17) return O3D_ERR_INVALID;
-    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
-    if (!u[0] || !u[1] || !u[2]) return O3D_ERR_CUDA;
+    FieldRef u[3] = {fref(s, O3D_F_UX), fref(s, O3D_F_UY), fref(s, O3D_F_UZ)};
+    if (!u[0].p || !u[1].p || !u[2].p) return O3D_ERR_CUDA;
     const int nb = stats_blocks(s->g);
     int rc;
     if ((rc = ensure_partial(s, 16ll * nb))) return rc;
-    if (s->cfg.nranks > 1 && (rc = comm_exchange(s, u, 3, R))) return rc;
-    if (launch_stats(s->st, s->g, u[0], u[1], u[2], s->cx, s->cy, s->cz, 1.0 / s->cfg.re,
-                     s->partial))
+    // same parity table as calculate_nu_t (src/utils.f90:283-291,339-347)
+    if ((rc = ensure_ghosts(s, VEL_IDS, 3, NAT3, 0x7u))) return rc;
+    if (launch_stats(s->st, s->g, u, s->cx, s->cy, s->cz, 1.0 / s->cfg.re, s->partial))
         return O3D_ERR_CUDA;
     if (launch_sum_partials(s->st, s->partial, nb, 16, s->scal_d + 32)) return O3D_ERR_CUDA;
     if (s->cfg.nranks > 1 && (rc = comm_allreduce(s, s->scal_d + 32, 16, RED_SUM))) return rc;
@@ -679,30 +805,31 @@ int o3d_s_statistics(o3d_session* s, double t, double* out17) {
 
 int o3d_s_rotational(o3d_session* s, int rotx, int roty, int rotz) {
     if (!s) return O3D_ERR_INVALID;
-    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
-    double* r[3] = {field(s, phys_id(s, rotx)), field(s, phys_id(s, roty)),
-                    field(s, phys_id(s, rotz))};
+    FieldRef u[3] = {fref(s, O3D_F_UX), fref(s, O3D_F_UY), fref(s, O3D_F_UZ)};
+    const int rid[3] = {phys_id(s, rotx), phys_id(s, roty), phys_id(s, rotz)};
+    double* r[3] = {field(s, rid[0]), field(s, rid[1]), field(s, rid[2])};
     for (int k = 0; k < 3; ++k)
-        if (!u[k] || !r[k]) return O3D_ERR_CUDA;
+        if (!u[k].p || !r[k]) return O3D_ERR_CUDA;
     int rc;
-    if (s->cfg.nranks > 1) {
-        // curl uses the even closure for every term; ghost planes hold raw neighbour data, so the
-        // exchange is parity-agnostic
-        if ((rc = comm_exchange(s, u, 3, R))) return rc;
-    }
-    if (launch_rot(s->st, s->g, u[0], u[1], u[2], s->cx, s->cy, s->cz, r[0], r[1], r[2]))
-        return O3D_ERR_CUDA;
+    // every curl term uses the even closure (src/differential_operators.f90:64-74): refill the
+    // velocity ghosts with even parity for this launch; the next consumer restores its own
+    if ((rc = ensure_ghosts(s, VEL_IDS, 3, EVEN3, 0x7u))) return rc;
+    if (launch_rot(s->st, s->g, u, s->cx, s->cy, s->cz, r[0], r[1], r[2])) return O3D_ERR_CUDA;
+    for (int k = 0; k < 3; ++k) touch(s, rid[k]);
     return O3D_OK;
 }
 
 int o3d_s_q_criterion(o3d_session* s, int dst) {
     if (!s) return O3D_ERR_INVALID;
-    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
-    double* q = field(s, phys_id(s, dst));
-    if (!u[0] || !u[1] || !u[2] || !q) return O3D_ERR_CUDA;
+    FieldRef u[3] = {fref(s, O3D_F_UX), fref(s, O3D_F_UY), fref(s, O3D_F_UZ)};
+    const int qid = phys_id(s, dst);
+    double* q = field(s, qid);
+    if (!u[0].p || !u[1].p || !u[2].p || !q) return O3D_ERR_CUDA;
     int rc;
-    if (s->cfg.nranks > 1 && (rc = comm_exchange(s, u, 3, R))) return rc;
-    if (launch_qcrit(s->st, s->g, u[0], u[1], u[2], s->cx, s->cy, s->cz, q)) return O3D_ERR_CUDA;
+    // derxi/deryi/derzi on the diagonal, p closures elsewhere (:90-100) = natural parity
+    if ((rc = ensure_ghosts(s, VEL_IDS, 3, NAT3, 0x7u))) return rc;
+    if (launch_qcrit(s->st, s->g, u, s->cx, s->cy, s->cz, q)) return O3D_ERR_CUDA;
+    touch(s, qid);
     return O3D_OK;
 }
 

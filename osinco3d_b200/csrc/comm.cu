@@ -126,37 +126,32 @@ void comm_destroy(o3d_session* s) {
     s->comm = nullptr;
 }
 
-// Ghost-plane exchange of `width` planes per side.  wrap != 0: the slab ring is periodic in z.
-int comm_exchange_w(o3d_session* s, double* const* fields, int nf, int width, int wrap) {
+// Ghost-plane exchange of `width` planes per side.  Planes are whole padded planes (px * py
+// doubles, contiguous); `bases` are field allocation starts.  wrap != 0: the slab ring is
+// periodic in z.
+int comm_exchange(o3d_session* s, double* const* bases, int nf, int width, int wrap) {
     Comm* c = s->comm;
     if (!c) return O3D_OK;
     const int up = (c->rank + 1 < c->nranks) ? c->rank + 1 : (wrap ? 0 : -1);
     const int dn = (c->rank > 0) ? c->rank - 1 : (wrap ? c->nranks - 1 : -1);
-    const size_t cnt = (size_t)width * (size_t)s->plane;
+    const long long sz = s->g.sz;
+    const size_t cnt = (size_t)width * (size_t)sz;
     span_begin(s, ST_HALO);
     O3D_NCCL_CHECK(g_api.GroupStart());
     for (int f = 0; f < nf; ++f) {
-        double* p = fields[f];
-        if (up >= 0)
-            O3D_NCCL_CHECK(g_api.Send(p + (long long)(s->nzl - width) * s->plane, cnt, ncclFloat64_,
-                                      up, c->nccl, s->st));
-        if (dn >= 0)
-            O3D_NCCL_CHECK(g_api.Recv(p - (long long)width * s->plane, cnt, ncclFloat64_, dn,
-                                      c->nccl, s->st));
-        if (dn >= 0) O3D_NCCL_CHECK(g_api.Send(p, cnt, ncclFloat64_, dn, c->nccl, s->st));
-        if (up >= 0)
-            O3D_NCCL_CHECK(g_api.Recv(p + (long long)s->nzl * s->plane, cnt, ncclFloat64_, up,
-                                      c->nccl, s->st));
+        double* b = bases[f];
+        double* top_owned = b + sz * (long long)(GH + s->nzl - width);  // last `width` planes
+        double* bot_owned = b + sz * (long long)GH;                     // first `width` planes
+        double* ghost_lo = b + sz * (long long)(GH - width);
+        double* ghost_hi = b + sz * (long long)(GH + s->nzl);
+        if (up >= 0) O3D_NCCL_CHECK(g_api.Send(top_owned, cnt, ncclFloat64_, up, c->nccl, s->st));
+        if (dn >= 0) O3D_NCCL_CHECK(g_api.Recv(ghost_lo, cnt, ncclFloat64_, dn, c->nccl, s->st));
+        if (dn >= 0) O3D_NCCL_CHECK(g_api.Send(bot_owned, cnt, ncclFloat64_, dn, c->nccl, s->st));
+        if (up >= 0) O3D_NCCL_CHECK(g_api.Recv(ghost_hi, cnt, ncclFloat64_, up, c->nccl, s->st));
     }
     O3D_NCCL_CHECK(g_api.GroupEnd());
     span_end(s, ST_HALO, 1);
     return O3D_OK;
-}
-
-int comm_exchange(o3d_session* s, double* const* fields, int nf, int width) {
-    // pressure follows the SOR variant's z rule (src/initialization.f90:283-301), everything
-    // else the nbcz flags; for every configuration the reference accepts they coincide
-    return comm_exchange_w(s, fields, nf, width, s->cfg.nbcz1 == O3D_PERIODIC);
 }
 
 int comm_allreduce(o3d_session* s, double* dev, int n, int op) {

@@ -1,0 +1,96 @@
+// ghost_kernels.cu -- maintenance of the padded field layout (o3d_common.cuh):
+//   fill_ghosts : write the boundary closure of src/derivation.f90 (periodic wrap, even / odd
+//                 mirror) into the 3 ghost layers of up to 6 fields in one launch.  Only the
+//                 face ghosts are filled: no stencil of the reference has mixed derivatives.
+//   pack/unpack : contiguous Fortran array (nx,ny,nz) <-> padded interior (H2D / D2H staging).
+// Surface work only: ~6 * 3 * n^2 cells per field against n^3 for a stencil pass.
+#include "kernels.h"
+
+namespace o3d {
+namespace {
+
+__global__ void __launch_bounds__(256) fill_ghosts_kernel(const Geom g, const GhostArgs a) {
+    const int job = blockIdx.z / 3, axis = blockIdx.z % 3;
+    if (job >= a.njobs) return;
+    const GhostJob jb = a.job[job];
+    if (!((jb.axes >> axis) & 1u)) return;
+    const bool odd = (jb.par >> axis) & 1u;
+    double* __restrict__ p = jb.p;
+    const int n = (axis == 0) ? g.nx : (axis == 1) ? g.ny : g.nz;
+    const long long s = (axis == 0) ? 1 : (axis == 1) ? g.sy : g.sz;
+    const int mlo = (axis == 0) ? g.bx : (axis == 1) ? g.by : g.bz_lo;
+    const int mhi = (axis == 0) ? g.bx : (axis == 1) ? g.by : g.bz_hi;
+    // the two other extents (a = fast, b = slow)
+    const int na = (axis == 0) ? g.ny : g.nx;
+    const int nb = (axis == 2) ? g.ny : g.nz;
+    const long long sa = (axis == 0) ? g.sy : 1;
+    const long long sb = (axis == 2) ? g.sy : g.sz;
+    const long long total = (long long)na * nb * 6;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int ia, ib, g6;
+        if (axis == 0) {  // 6 ghost cells of one row are handled by 6 neighbouring threads
+            g6 = (int)(t % 6);
+            const long long row = t / 6;
+            ia = (int)(row % na), ib = (int)(row / na);
+        } else {  // i fastest: coalesced rows
+            ia = (int)(t % na);
+            const long long rest = t / na;
+            g6 = (int)(rest % 6), ib = (int)(rest / 6);
+        }
+        const int side = g6 / 3, gg = g6 % 3 + 1;
+        const int mode = side ? mhi : mlo;
+        if (mode == BM_HALO) continue;  // filled by the z-slab halo exchange
+        const int q = side ? (n - 1 + gg) : -gg;
+        bool refl;
+        const int src = map_index(q, n, mlo, mhi, refl);
+        const long long base = (long long)ia * sa + (long long)ib * sb;
+        const double v = p[base + (long long)src * s];
+        p[base + (long long)q * s] = (refl && odd) ? -v : v;
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const Geom g, const double* __restrict__ src,
+                                                    double* __restrict__ dst, int to_padded) {
+    const long long rows = (long long)g.ny * g.nz;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int j = (int)(row % g.ny), k = (int)(row / g.ny);
+        const long long mp = (long long)k * g.sz + (long long)j * g.sy;
+        const long long mc = row * g.nx;
+        if (to_padded)
+            for (int i = threadIdx.x; i < g.nx; i += blockDim.x) dst[mp + i] = src[mc + i];
+        else
+            for (int i = threadIdx.x; i < g.nx; i += blockDim.x) dst[mc + i] = src[mp + i];
+    }
+}
+
+}  // namespace
+
+int launch_fill_ghosts(cudaStream_t st, const Geom& g, const GhostArgs& a) {
+    if (a.njobs <= 0) return 0;
+    const long long face = (long long)((g.nx > g.ny) ? g.nx : g.ny) * ((g.ny > g.nz) ? g.ny : g.nz) * 6;
+    long long b = (face + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    fill_ghosts_kernel<<<dim3((unsigned)b, 1, 3 * a.njobs), 256, 0, st>>>(g, a);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_pack(cudaStream_t st, const Geom& g, const double* contiguous, double* padded) {
+    long long b = (long long)g.ny * g.nz;
+    if (b > 148 * 16) b = 148 * 16;
+    pack_kernel<<<(unsigned)b, 256, 0, st>>>(g, contiguous, padded, 1);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_unpack(cudaStream_t st, const Geom& g, const double* padded, double* contiguous) {
+    long long b = (long long)g.ny * g.nz;
+    if (b > 148 * 16) b = 148 * 16;
+    pack_kernel<<<(unsigned)b, 256, 0, st>>>(g, padded, contiguous, 0);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace o3d

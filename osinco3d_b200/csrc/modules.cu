@@ -54,7 +54,7 @@ int scratch(int nx, int ny, int nz, double dx, double dy, double dz, o3d_session
     s->cfg.dx = dx, s->cfg.dy = dy, s->cfg.dz = dz;
     s->cfg.nranks = 1, s->cfg.rank = 0;
     s->use_src = 0;
-    fill_dims(s);
+    fill_geom(s);
     *out = s;
     return O3D_OK;
 }
@@ -79,7 +79,8 @@ int der_impl(int axis, int order, int closure, double* df, const double* f, doub
     o3d_session* s;
     int rc = scratch(nx, ny, nz, d, d, d, &s);
     if (rc) return rc;
-    Dims g = s->g;
+    // the routine's own closure, whatever schemes() bound: put it into the ghost cells
+    Geom g = s->g;
     const int mode = (closure == O3D_CLOSURE_00) ? BM_WRAP : BM_MIRROR;
     if (axis == 0) g.bx = mode;
     if (axis == 1) g.by = mode;
@@ -88,11 +89,21 @@ int der_impl(int axis, int order, int closure, double* df, const double* f, doub
     double* src = field(s, O3D_F_SCRATCH0);
     double* dst = field(s, O3D_F_SCRATCH1);
     if (!src || !dst) return O3D_ERR_CUDA;
-    if (launch_der(s->st, g, axis, order, closure == O3D_CLOSURE_I11, closure == O3D_CLOSURE_2DSIM,
-                   d, src, dst)) {
+    const int zero = (closure == O3D_CLOSURE_2DSIM);
+    if (!zero) {
+        GhostArgs ga;
+        ga.njobs = 1;
+        ga.job[0].p = src;
+        ga.job[0].par = (closure == O3D_CLOSURE_I11) ? (1u << axis) : 0u;
+        ga.job[0].axes = 1u << axis;
+        if (launch_fill_ghosts(s->st, g, ga)) return O3D_ERR_CUDA;
+    }
+    touch(s, O3D_F_SCRATCH0);
+    if (launch_der(s->st, g, axis, order, zero, d, src, dst)) {
         set_error("derivative kernel launch failed");
         return O3D_ERR_CUDA;
     }
+    touch(s, O3D_F_SCRATCH1);
     return down(s, O3D_F_SCRATCH1, df);
 }
 
@@ -261,9 +272,12 @@ int o3d_calculate_nu_t(double* nu_t, const double* ux, const double* uy, const d
     const double csd = cs * delta;
     double* out = field(s, O3D_F_NU_T);
     if (!out) return O3D_ERR_CUDA;
-    if (launch_nu_t(s->st, s->g, field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ), s->cx,
-                    s->cy, s->cz, csd * csd, out))
-        return O3D_ERR_CUDA;
+    const int ids[3] = {O3D_F_UX, O3D_F_UY, O3D_F_UZ};
+    const unsigned par[3] = {0x1u, 0x2u, 0x4u};  // src/les_turbulence.f90:55-67
+    if ((rc = ensure_ghosts(s, ids, 3, par, 0x7u))) return rc;
+    FieldRef u[3] = {fref(s, O3D_F_UX), fref(s, O3D_F_UY), fref(s, O3D_F_UZ)};
+    if (launch_nu_t(s->st, s->g, u, s->cx, s->cy, s->cz, csd * csd, out)) return O3D_ERR_CUDA;
+    touch(s, O3D_F_NU_T);
     if (stats6 && (rc = o3d_s_function_stats(s, O3D_F_NU_T, stats6))) return rc;
     return down(s, O3D_F_NU_T, nu_t);
 }
@@ -296,7 +310,8 @@ int o3d_predict_velocity(double* ux_pred, double* uy_pred, double* uz_pred, cons
     if (iles != 1) {  // nu_t = 0.0d0, src/integration.f90:112
         double* nt = field(s, O3D_F_NU_T);
         if (!nt) return O3D_ERR_CUDA;
-        O3D_CUDA_CHECK(cudaMemsetAsync(nt, 0, N * sizeof(double), s->st));
+        O3D_CUDA_CHECK(cudaMemsetAsync(nt - interior_offset(s->g), 0,
+                                       (size_t)s->felems * sizeof(double), s->st));
     }
     if ((rc = o3d_s_predict_velocity(s, itime))) return rc;
     if ((rc = down(s, O3D_F_UX_PRED, ux_pred)) || (rc = down(s, O3D_F_UY_PRED, uy_pred)) ||

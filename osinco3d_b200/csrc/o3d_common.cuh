@@ -3,8 +3,20 @@
 // Arithmetic contract: every kernel evaluates the reference's expressions in the reference's
 // order, in FP64, with FMA contraction disabled (nvcc -fmad=false), so stencil-only outputs
 // are bit-identical to a gfortran -O3 x86-64 build of jojoledemago/osinco3d
-// (src/derivation.f90, src/integration.f90 ...).  Ghost values carry their sign
-// (x-(-y) == x+y bitwise), see DESIGN.md "Closures".
+// (src/derivation.f90, src/integration.f90 ...).
+//
+// Memory layout (DESIGN.md "Data layout in HBM"): every field lives in a PADDED, PITCHED box
+//     (px, py, nz + 6)   px = pitch (multiple of 16 doubles = 128 B), py = ny + 6
+// with the interior point (0,0,0) at element (GX, GH, GH).  Ghost cells (3 layers per side,
+// the widest stencil radius) hold the boundary closure of src/derivation.f90 as DATA:
+//     periodic  *_00  : f(-g) = f(n-g),   f(n-1+g) = f(g-1)
+//     even      *p_11 : f(-g) = +f(g),    f(n-1+g) = +f(n-1-g)
+//     odd       *i_11 : f(-g) = -f(g),    f(n-1+g) = -f(n-1-g)
+// so every stencil kernel is the reference's INTERIOR formula (src/derivation.f90:43-47,
+// :529-533) at every point, branch-free.  x - (-y) == x + y bitwise, so this reproduces the
+// explicitly written boundary planes (e.g. :137-159) exactly; the even first derivative on a
+// wall plane evaluates to a*(x-x) - b*(y-y) + c*(z-z) = +0.0, the literal the reference
+// assigns (:87,:105).  z ghost planes at a rank boundary are filled by the NCCL halo exchange.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -13,26 +25,33 @@
 
 namespace o3d {
 
-// ---- boundary handling of one axis side -------------------------------------------------
 enum : int {
-    BM_WRAP = 0,    // periodic: f(p) = f(p -+ n)                 (der?_00)
+    BM_WRAP = 0,    // periodic                                   (der?_00)
     BM_MIRROR = 1,  // free-slip: f(1-k) = +-f(1+k)               (der?p_11 / der?i_11)
-    BM_HALO = 2     // z only: planes -3..-1 / nz..nz+2 are stored ghost planes filled by the
-                    // z-slab halo exchange (multi-GPU)
+    BM_HALO = 2     // z only: ghost planes come from the neighbouring rank (multi-GPU)
 };
 
-constexpr int R = 3;  // widest stencil radius (6th-order first derivative)
+constexpr int R = 3;    // ghost width = widest stencil radius (6th-order first derivative)
+constexpr int GH = R;   // ghost rows / planes before the interior in y and z
+constexpr int GX = 16;  // doubles before the interior in x: interior rows start 128 B aligned
 
-struct Dims {
-    int nx, ny, nz;      // local extents (nz = planes owned by this rank)
+struct Geom {
+    int nx, ny, nz;      // interior extents of this rank's slab
+    int px, py;          // pitch in doubles (multiple of 16), padded rows per plane (ny + 6)
+    long long sy, sz;    // element strides of j and k: px, px * py
     int bx, by;          // BM_WRAP | BM_MIRROR
     int bz_lo, bz_hi;    // BM_WRAP | BM_MIRROR | BM_HALO
     int sim2d;           // derz_2dsim / derzz_2dsim: z derivatives are zero
     int gz0, gnz;        // first owned global plane, global nz (red-black colouring)
 };
 
-// Map a line index q (may lie up to R outside [0,n)) to a stored index.
-// `refl` reports a mirror reflection (sign flips for odd parity).
+inline int pitch_for(int nx) { return ((GX + nx + R + 15) / 16) * 16; }
+// doubles in one field allocation / offset of interior (0,0,0) from the allocation start
+inline long long field_elems(const Geom& g) { return g.sz * (long long)(g.nz + 2 * GH); }
+inline long long interior_offset(const Geom& g) { return GX + g.sy * GH + g.sz * GH; }
+
+// Map a line index q (may lie up to n-1 outside [0,n)) to a stored interior index under a
+// closure; `refl` reports a mirror reflection (sign flips for odd parity).
 __host__ __device__ __forceinline__ int map_index(int q, int n, int mode_lo, int mode_hi,
                                                   bool& refl) {
     refl = false;
@@ -88,11 +107,6 @@ __device__ __forceinline__ double d2_expr(double a, double b, double c, double m
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 __device__ __forceinline__ double warp_sum(double v) {

@@ -31,6 +31,7 @@ static SorArgs make_sor_args(o3d_session* s, double* pp, const double* rhs) {
     a.mz_lo = (nr > 1 && (s->cfg.rank > 0 || mz == BM_WRAP)) ? BM_HALO : mz;
     a.mz_hi = (nr > 1 && (s->cfg.rank < nr - 1 || mz == BM_WRAP)) ? BM_HALO : mz;
     a.nx = s->g.nx, a.ny = s->g.ny, a.nz = s->g.nz;
+    a.sy = s->g.sy, a.sz = s->g.sz;
     a.gz0 = s->z0;
     a.gnz = s->cfg.nz;
     a.seam_x = (a.mx == BM_WRAP) && (a.nx & 1);
@@ -67,7 +68,8 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     if (batch > 64) batch = 64;
     if (c.sor_check_every > 0) batch = c.sor_check_every;
     if (c.sor_order == O3D_SOR_LEXI_WAVEFRONT) batch = 1;
-    double* ppf[1] = {pp};
+    double* ppf[1] = {pp - interior_offset(s->g)};  // allocation base of pp
+    const int zwrap = (s->sor_variant != 2);  // _0000 / _0011 wrap in z, _111111 mirrors
     while (true) {
         if (launched + batch > c.kmax) batch = c.kmax - launched;
         if (batch < 1) batch = 1;
@@ -79,12 +81,12 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                     if (launch_sor_wavefront(s->st, a, hpl, s->ctrl_d)) return O3D_ERR_CUDA;
             } else {
                 for (int colour = 0; colour < 2; ++colour) {
-                    if (multi && comm_exchange(s, ppf, 1, 1)) return O3D_ERR_COMM;
+                    if (multi && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
                     if (launch_sor_rb(s->st, a, colour, 0, s->ctrl_d)) return O3D_ERR_CUDA;
                 }
                 if (seams) {
                     for (int colour = 0; colour < 2; ++colour) {
-                        if (multi && comm_exchange(s, ppf, 1, 1)) return O3D_ERR_COMM;
+                        if (multi && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
                         if (launch_sor_rb(s->st, a, colour, 1, s->ctrl_d)) return O3D_ERR_CUDA;
                     }
                 }

@@ -1,14 +1,14 @@
-// reduce_kernels.cu -- device reductions for the per-step diagnostics the reference driver
-// runs on full fields (function_stats src/functions.f90:27, minval/maxval prints
-// src/IOfunctions.f90:322, compute_cfl src/utils.f90:178) and small utilities.
+// reduce_kernels.cu -- device reductions over the interior of a padded field, for the per-step
+// diagnostics the reference driver runs on full fields (function_stats src/functions.f90:27,
+// minval/maxval prints src/IOfunctions.f90:322, compute_cfl src/utils.f90:178).
 // Two-stage, fixed-shape reductions: results are deterministic run to run (no FP atomics).
 #include "kernels.h"
 
 namespace o3d {
 namespace {
 
-constexpr int RB = 256;       // threads per block
-constexpr int RMAXB = 1184;   // 148 SMs x 8
+constexpr int RB = 256;      // threads per block
+constexpr int RMAXB = 1184;  // 148 SMs x 8
 
 __device__ __forceinline__ double red_op(double a, double b, int op) {
     if (op == RED_MIN) return fmin(a, b);
@@ -37,15 +37,19 @@ __device__ __forceinline__ double block_reduce(double v, int op, double* red) {
     return r;
 }
 
-__global__ void __launch_bounds__(RB) reduce_stage1(const double* __restrict__ f, long long n,
+__global__ void __launch_bounds__(RB) reduce_stage1(const Geom g, const double* __restrict__ f,
                                                      int op, double* partial) {
     __shared__ double red[32];
     double v = red_init(op);
-    for (long long m = (long long)blockIdx.x * RB + threadIdx.x; m < n;
-         m += (long long)gridDim.x * RB) {
-        double x = __ldg(f + m);
-        if (op == RED_ABSMAX) x = fabs(x);
-        v = red_op(v, x, op);
+    const long long rows = (long long)g.ny * g.nz;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int j = (int)(row % g.ny), k = (int)(row / g.ny);
+        const long long base = (long long)k * g.sz + (long long)j * g.sy;
+        for (int i = threadIdx.x; i < g.nx; i += RB) {
+            double x = __ldg(f + base + i);
+            if (op == RED_ABSMAX) x = fabs(x);
+            v = red_op(v, x, op);
+        }
     }
     v = block_reduce(v, op, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = v;
@@ -115,18 +119,23 @@ __device__ __forceinline__ StatAcc stat_init() {
     return a;
 }
 
-__global__ void __launch_bounds__(RB) fstats_stage1(const double* __restrict__ f, long long n,
+__global__ void __launch_bounds__(RB) fstats_stage1(const Geom g, const double* __restrict__ f,
                                                      double* partial) {
     __shared__ StatAcc red[RB / 32];
     StatAcc v = stat_init();
-    for (long long m = (long long)blockIdx.x * RB + threadIdx.x; m < n;
-         m += (long long)gridDim.x * RB) {
-        const double x = __ldg(f + m);
-        v.mn = fmin(v.mn, x);
-        v.sum += x;
-        if (x > v.mx) {  // strict: first occurrence wins within a thread (m ascending)
-            v.mx = x;
-            v.imx = m;
+    const long long rows = (long long)g.ny * g.nz;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int j = (int)(row % g.ny), k = (int)(row / g.ny);
+        const long long base = (long long)k * g.sz + (long long)j * g.sy;
+        for (int i = threadIdx.x; i < g.nx; i += RB) {
+            const double x = __ldg(f + base + i);
+            const long long lin = row * g.nx + i;  // position in the reference's array order
+            v.mn = fmin(v.mn, x);
+            v.sum += x;
+            if (x > v.mx) {  // strict: first occurrence wins within a thread (lin ascending)
+                v.mx = x;
+                v.imx = lin;
+            }
         }
     }
     v = stat_block(v, red);
@@ -159,37 +168,30 @@ __global__ void __launch_bounds__(RB) fstats_stage2(const double* partial, int n
     }
 }
 
-__global__ void fill_kernel(double* p, long long n, double v) {
-    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < n;
-         m += (long long)gridDim.x * blockDim.x)
-        p[m] = v;
-}
-
 }  // namespace
 
-int reduce_blocks(long long n) {
-    long long b = (n + RB - 1) / RB;
+int reduce_blocks(const Geom& g) {
+    long long b = (long long)g.ny * g.nz;
     if (b > RMAXB) b = RMAXB;
     if (b < 1) b = 1;
     return (int)b;
 }
 
-int launch_reduce(cudaStream_t st, const double* f, long long n, int op, double* partial,
+int launch_reduce(cudaStream_t st, const Geom& g, const double* f, int op, double* partial,
                   double* out) {
-    const int nb = reduce_blocks(n);
-    reduce_stage1<<<nb, RB, 0, st>>>(f, n, op, partial);
+    const int nb = reduce_blocks(g);
+    reduce_stage1<<<nb, RB, 0, st>>>(g, f, op, partial);
     reduce_stage2<<<1, RB, 0, st>>>(partial, nb, op == RED_ABSMAX ? RED_MAX : op, out);
     count_launch(2);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-int launch_function_stats(cudaStream_t st, const double* f, int nx, int ny, int nz,
-                          double* partial, double* out6) {
-    const long long n = (long long)nx * ny * nz;
-    int nb = reduce_blocks(n);
+int launch_function_stats(cudaStream_t st, const Geom& g, const double* f, double* partial,
+                          double* out6) {
+    int nb = reduce_blocks(g);
     if (nb > RMAXB / 4) nb = RMAXB / 4;  // partial holds 4 doubles per block
-    fstats_stage1<<<nb, RB, 0, st>>>(f, n, partial);
-    fstats_stage2<<<1, RB, 0, st>>>(partial, nb, nx, ny, nz, out6);
+    fstats_stage1<<<nb, RB, 0, st>>>(g, f, partial);
+    fstats_stage2<<<1, RB, 0, st>>>(partial, nb, g.nx, g.ny, g.nz, out6);
     count_launch(2);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -197,15 +199,6 @@ int launch_function_stats(cudaStream_t st, const double* f, int nx, int ny, int 
 int launch_sum_partials(cudaStream_t st, const double* partial, int nparts, int ncomp,
                         double* out) {
     sum_partials_kernel<<<ncomp, RB, 0, st>>>(partial, nparts, out);
-    count_launch();
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
-}
-
-int launch_fill(cudaStream_t st, double* p, long long n, double v) {
-    long long b = (n + 255) / 256;
-    if (b > 148 * 16) b = 148 * 16;
-    if (b < 1) b = 1;
-    fill_kernel<<<(unsigned)b, 256, 0, st>>>(p, n, v);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -11,16 +11,22 @@ struct Comm;  // z-slab halo exchange + reductions over NCCL (comm.cu)
 
 struct o3d_session {
     o3d_config cfg;
-    o3d::Dims g;           // local slab
+    o3d::Geom g;           // local slab, padded layout
     int z0, nzl;           // owned global planes [z0, z0+nzl)
-    long long plane, nloc; // nx*ny, nx*ny*nzl
+    long long nloc;        // interior points of this rank: nx*ny*nzl
+    long long felems;      // doubles per padded field allocation
     cudaStream_t st;
     o3d::Coef cx, cy, cz;
 
-    // physical buffers: [0, O3D_F_COUNT) for plain fields; history levels are logical views
-    double* base[O3D_F_COUNT];  // allocation start (3 ghost planes below plane 0)
-    // history: physical buffer ids per component (0..2 = fux,fuy,fuz; 3 = fphi), logical level
-    int lv[4][3];
+    // padded fields; history levels are logical views onto three physical buffers
+    double* base[O3D_F_COUNT];       // allocation start (ghosts included)
+    CUtensorMap tmap[O3D_F_COUNT];   // 40 x 14 x 1 boxes for the march engine
+    // ghost-cell state per field: which axes currently hold a valid closure and with which
+    // parity bits (bit a: odd along axis a).  Producers / uploads reset gaxes to 0.
+    unsigned gaxes[O3D_F_COUNT], gpar[O3D_F_COUNT];
+    int lv[4][3];          // history: physical buffer per component (0..2 = fu?, 3 = fphi)
+
+    double* stage_d;       // contiguous nloc doubles: H2D / D2H staging of one field
 
     // SOR
     o3d::SorCtrl* ctrl_d;
@@ -45,8 +51,8 @@ struct o3d_session {
     std::vector<Span> pending;
     std::vector<cudaEvent_t> free_events;
     double t_ms[6];
-    cudaEvent_t sw_a, sw_b;  // stopwatch
     long long t_cnt[6];
+    cudaEvent_t sw_a, sw_b;  // stopwatch
 };
 
 namespace o3d {
@@ -67,12 +73,23 @@ int axis_bc(int b1, int bn, int* out);
 
 enum { ST_RHS = 0, ST_DIV = 1, ST_SOR = 2, ST_CORR = 3, ST_TRANSEQ = 4, ST_HALO = 5 };
 
-// lazily allocated, zero-initialised field; returns pointer to owned plane 0 (nullptr on OOM)
+// lazily allocated, zero-initialised padded field; returns the interior origin (nullptr on OOM)
 double* field(o3d_session* s, int id);
+FieldRef fref(o3d_session* s, int id);
 // logical history level (1..3) of component c (0..2 velocity, 3 scalar) -> field id
 int hist_id(const o3d_session* s, int c, int level);
+int phys_id(const o3d_session* s, int id);
+// parity bits the reference's tables give a field (src/integration.f90:118-165): the velocity
+// component normal to an axis is odd along it, everything else even
+unsigned natural_parity(int id);
+// mark the interior of a field as modified: its ghost cells are stale
+void touch(o3d_session* s, int id);
+// make the ghost cells of `n` fields valid on the axes in `axes` with parity `par[q]`
+// (one fused launch + z-slab halo exchange where the z neighbour is another rank)
+int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, unsigned axes);
+int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes);
 int ensure_partial(o3d_session* s, long long n);
-void fill_dims(o3d_session* s);
+void fill_geom(o3d_session* s);
 
 void span_begin(o3d_session* s, int stage);
 void span_end(o3d_session* s, int stage, long long count);
@@ -85,10 +102,10 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
 // comm.cu
 int comm_create(o3d_session* s);
 void comm_destroy(o3d_session* s);
-// exchange the 3 ghost planes per side of `nf` fields (no-op when nranks == 1)
-int comm_exchange(o3d_session* s, double* const* fields, int nf, int width);
+// exchange `width` ghost planes per side of `nf` fields given by their ALLOCATION BASE
+// (no-op when nranks == 1); wrap: the slab ring is periodic in z
+int comm_exchange(o3d_session* s, double* const* bases, int nf, int width, int wrap);
 int comm_allreduce(o3d_session* s, double* dev, int n, int op /* RED_* */);
-int comm_exchange_w(o3d_session* s, double* const* fields, int nf, int width, int wrap);
 int nccl_unique_id(unsigned char* out128);
 
 }  // namespace o3d

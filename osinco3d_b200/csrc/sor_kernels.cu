@@ -7,6 +7,9 @@
 //     "seam": points are further split by the parity of the number of seam planes they lie on.
 //     Neighbouring points always differ in colour or in seam parity, so each of the (up to) four
 //     classes is an independent set and the sweep is race-free and deterministic.
+//   (pp lives in the padded layout of o3d_common.cuh, but the sweeps use the reference's
+//   neighbour-index rule directly -- src/poisson.f90:57-92 -- because in-place updates would
+//   otherwise have to keep ghost copies coherent between half-sweeps.)
 //   * LEXI_WAVEFRONT (verification): hyperplanes i+j+k = h in ascending h; all points of a
 //     hyperplane are independent and their neighbours are exactly as "old"/"new" as in the
 //     lexicographic sweep, so the iterates are bit-identical to the reference's.
@@ -40,7 +43,7 @@ __device__ __forceinline__ int seam_pop(const SorArgs& a, int i, int j, int gk) 
 
 __device__ __forceinline__ double sor_point(const SorArgs& a, int i, int j, int k,
                                             double omega) {
-    const long long sy = a.nx, sz = (long long)a.nx * a.ny;
+    const long long sy = a.sy, sz = a.sz;
     int im1, ip1, jm1, jp1, km1, kp1;
     nbr_idx(i, a.nx, a.mx, a.mx, im1, ip1);
     nbr_idx(j, a.ny, a.my, a.my, jm1, jp1);
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256) sor_wavefront_kernel(const SorArgs a, int
     double d = 0.0;
     const int i = h - j - k;
     if (j < a.ny && k < a.nz && i >= 0 && i < a.nx) {
-        const long long sy = a.nx, sz = (long long)a.nx * a.ny;
+        const long long sy = a.sy, sz = a.sz;
         int im1, ip1, jm1, jp1, km1, kp1;
         nbr_idx(i, a.nx, a.mx, a.mx, im1, ip1);
         nbr_idx(j, a.ny, a.my, a.my, jm1, jp1);
