@@ -232,6 +232,7 @@ enum {
     O3D_F_FUX1, O3D_F_FUX2, O3D_F_FUX3, O3D_F_FUY1, O3D_F_FUY2, O3D_F_FUY3,
     O3D_F_FUZ1, O3D_F_FUZ2, O3D_F_FUZ3, O3D_F_FPHI1, O3D_F_FPHI2, O3D_F_FPHI3,
     O3D_F_DIVU, O3D_F_SCRATCH0, O3D_F_SCRATCH1, O3D_F_SCRATCH2,
+    O3D_F_PP2, /* ping-pong partner of pp inside the fused red-black SOR (internal) */
     O3D_F_COUNT
 };
 

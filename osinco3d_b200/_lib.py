@@ -25,7 +25,7 @@ RED_MIN, RED_MAX, RED_SUM, RED_ABSMAX = 0, 1, 2, 3
 
 FIELDS = ["ux", "uy", "uz", "pp", "phi", "ux_pred", "uy_pred", "uz_pred", "nu_t", "rhs",
           "fux1", "fux2", "fux3", "fuy1", "fuy2", "fuy3", "fuz1", "fuz2", "fuz3",
-          "fphi1", "fphi2", "fphi3", "divu", "scratch0", "scratch1", "scratch2"]
+          "fphi1", "fphi2", "fphi3", "divu", "scratch0", "scratch1", "scratch2", "pp2"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 
 

@@ -152,6 +152,29 @@ int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, un
     return O3D_OK;
 }
 
+// three fields, field q only along axis q (divergence operands): one fused launch
+int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par) {
+    GhostArgs a;
+    a.njobs = 0;
+    double* xbase[1];
+    int nxch = 0;
+    for (int q = 0; q < 3; ++q) {
+        const int id = ids[q];
+        double* p = field(s, id);
+        if (!p) return O3D_ERR_CUDA;
+        const unsigned bit = 1u << q;
+        if ((s->gaxes[id] & bit) && ((s->gpar[id] & bit) == (par[q] & bit))) continue;
+        GhostJob& jb = a.job[a.njobs++];
+        jb.p = p, jb.par = par[q], jb.axes = bit;
+        s->gaxes[id] |= bit;
+        s->gpar[id] = (s->gpar[id] & ~bit) | (par[q] & bit);
+        if (q == 2 && (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO)) xbase[nxch++] = s->base[id];
+    }
+    if (a.njobs && launch_fill_ghosts(s->st, s->g, a)) return O3D_ERR_CUDA;
+    if (nxch) return comm_exchange(s, xbase, nxch, R, s->cfg.nbcz1 == O3D_PERIODIC);
+    return O3D_OK;
+}
+
 int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes) {
     return ensure_ghosts(s, &id, 1, &par, axes);
 }
@@ -628,8 +651,7 @@ int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
     int rc;
     // divergence(..., odd = 1): derxi(ux*), deryi(uy*), derzi(uz*); each field only needs the
     // ghosts of its own axis (src/differential_operators.f90:30-32)
-    for (int k = 0; k < 3; ++k)
-        if ((rc = ensure_ghosts1(s, PRED_IDS[k], NAT3[k], 1u << k))) return rc;
+    if ((rc = ensure_ghosts_own_axis(s, PRED_IDS, NAT3))) return rc;
     span_begin(s, ST_DIV);
     if (launch_div(s->st, s->g, up, s->cx, s->cy, s->cz, 1, c.dt, rhs)) return O3D_ERR_CUDA;
     span_end(s, ST_DIV, 1);
@@ -735,8 +757,8 @@ int o3d_s_divergence(o3d_session* s, int fx, int fy, int fz, int dst, int odd) {
     if (!f[0].p || !f[1].p || !f[2].p || !out) return O3D_ERR_CUDA;
     int rc;
     // src/differential_operators.f90:25-33: odd -> derxi/deryi/derzi, else derxp/deryp/derzp
-    for (int k = 0; k < 3; ++k)
-        if ((rc = ensure_ghosts1(s, ids[k], odd ? (1u << k) : 0u, 1u << k))) return rc;
+    const unsigned dpar[3] = {odd ? 0x1u : 0u, odd ? 0x2u : 0u, odd ? 0x4u : 0u};
+    if ((rc = ensure_ghosts_own_axis(s, ids, dpar))) return rc;
     if (launch_div(s->st, s->g, f, s->cx, s->cy, s->cz, 0, 1.0, out)) return O3D_ERR_CUDA;
     touch(s, out_id);
     return O3D_OK;

@@ -125,6 +125,9 @@ struct SorArgs {
 };
 // one colour class: colour in {0,1}, seam_class in {0,1} (popcount parity of the seam mask)
 int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl);
+// fused red+black iteration (one pass, ping-pong p_old -> p_new); needs a 2-colourable grid
+int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,
+                     SorCtrl* ctrl);
 // end-of-iteration control: exits and dynamic omega, src/poisson.f90:110-122
 int launch_sor_control(cudaStream_t st, SorCtrl* ctrl, double eps, int kmax, int idyn,
                        double factor);

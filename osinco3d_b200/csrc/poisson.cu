@@ -3,6 +3,7 @@
 //               path or lexicographic-wavefront verification ordering; exit tests and dynamic
 //               omega (src/poisson.f90:110-122) evaluated on the device.
 #include <cmath>
+#include <utility>
 
 #include "session.h"
 
@@ -62,39 +63,54 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     h->done = (c.kmax < 1) ? 3 : 0;
     O3D_CUDA_CHECK(cudaMemcpyAsync(s->ctrl_d, h, sizeof(SorCtrl), cudaMemcpyHostToDevice, s->st));
     const bool seams = a.seam_x || a.seam_y || a.seam_z;
+    const bool wavefront = (c.sor_order == O3D_SOR_LEXI_WAVEFRONT);
+    // fast path: fused red+black pass with ping-pong buffers (needs a 2-colourable grid)
+    const bool fused = !wavefront && !seams;
+    double* alt = nullptr;
+    if (fused) {
+        alt = field(s, O3D_F_PP2);
+        if (!alt) return O3D_ERR_CUDA;
+    }
     const double factor = sor_factor(s);
     int launched = 0;
     int batch = s->last_iters > 0 ? s->last_iters : 8;
     if (batch > 64) batch = 64;
     if (c.sor_check_every > 0) batch = c.sor_check_every;
-    if (c.sor_order == O3D_SOR_LEXI_WAVEFRONT) batch = 1;
-    double* ppf[1] = {pp - interior_offset(s->g)};  // allocation base of pp
+    if (wavefront) batch = 1;
+    const long long ioff = interior_offset(s->g);
     const int zwrap = (s->sor_variant != 2);  // _0000 / _0011 wrap in z, _111111 mirrors
     while (true) {
         if (launched + batch > c.kmax) batch = c.kmax - launched;
         if (batch < 1) batch = 1;
         span_begin(s, ST_SOR);
         for (int b = 0; b < batch; ++b) {
-            if (c.sor_order == O3D_SOR_LEXI_WAVEFRONT) {
+            if (wavefront) {
                 const int nh = a.nx + a.ny + a.nz - 2;
                 for (int hpl = 0; hpl < nh; ++hpl)
                     if (launch_sor_wavefront(s->st, a, hpl, s->ctrl_d)) return O3D_ERR_CUDA;
+            } else if (fused) {
+                const int t = launched + b;  // iteration t reads src, writes dst
+                double* src = (t & 1) ? alt : pp;
+                double* dst = (t & 1) ? pp : alt;
+                if (multi) {
+                    double* bases[1] = {src - ioff};
+                    if (comm_exchange(s, bases, 1, 2, zwrap)) return O3D_ERR_COMM;
+                }
+                if (launch_sor_fused(s->st, a, src, dst, s->ctrl_d)) return O3D_ERR_CUDA;
             } else {
+                double* ppf[1] = {pp - ioff};
                 for (int colour = 0; colour < 2; ++colour) {
                     if (multi && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
                     if (launch_sor_rb(s->st, a, colour, 0, s->ctrl_d)) return O3D_ERR_CUDA;
                 }
-                if (seams) {
-                    for (int colour = 0; colour < 2; ++colour) {
-                        if (multi && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
-                        if (launch_sor_rb(s->st, a, colour, 1, s->ctrl_d)) return O3D_ERR_CUDA;
-                    }
+                for (int colour = 0; colour < 2; ++colour) {
+                    if (multi && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
+                    if (launch_sor_rb(s->st, a, colour, 1, s->ctrl_d)) return O3D_ERR_CUDA;
                 }
-                if (multi &&
-                    comm_allreduce(s, reinterpret_cast<double*>(&s->ctrl_d->dmax_bits), 1,
-                                   RED_MAXBITS))
-                    return O3D_ERR_COMM;
             }
+            if (multi && !wavefront &&
+                comm_allreduce(s, reinterpret_cast<double*>(&s->ctrl_d->dmax_bits), 1, RED_MAXBITS))
+                return O3D_ERR_COMM;
             if (launch_sor_control(s->st, s->ctrl_d, c.eps, c.kmax, c.idyn, factor))
                 return O3D_ERR_CUDA;
         }
@@ -106,8 +122,16 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         if (h->done || launched >= c.kmax) break;
         batch = 4;
         if (c.sor_check_every > 0) batch = c.sor_check_every;
-        if (c.sor_order == O3D_SOR_LEXI_WAVEFRONT) batch = 1;
+        if (wavefront) batch = 1;
     }
+    if (fused && (h->iter & 1)) {
+        // an odd number of ping-pong passes left the iterate in the alternate buffer: swap the
+        // two physical fields (O(1), no copy)
+        std::swap(s->base[O3D_F_PP], s->base[O3D_F_PP2]);
+        std::swap(s->tmap[O3D_F_PP], s->tmap[O3D_F_PP2]);
+    }
+    touch(s, O3D_F_PP);
+    touch(s, O3D_F_PP2);
     s->t_cnt[ST_SOR] += h->iter;
     s->omega = h->omega;  // omega is intent(inout) and persists, src/integration.f90:222,247
     s->last_iters = h->iter;

@@ -88,6 +88,7 @@ void touch(o3d_session* s, int id);
 // (one fused launch + z-slab halo exchange where the z neighbour is another rank)
 int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, unsigned axes);
 int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes);
+int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par);
 int ensure_partial(o3d_session* s, long long n);
 void fill_geom(o3d_session* s);
 

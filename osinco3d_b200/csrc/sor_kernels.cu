@@ -122,6 +122,184 @@ __global__ void __launch_bounds__(256) sor_seam_kernel(const SorArgs a, int colo
     if (threadIdx.x == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused red+black iteration: ONE pass over the grid per SOR iteration.
+//
+// A CTA owns a 32 x 8 column and marches in z.  Planes of the previous iterate live in a small
+// shared-memory ring (36 x 12 cells: the tile plus a 2-cell halo).  At march step k the CTA
+//   (1) red-updates plane k+1 over the tile plus a 1-cell ring (the ring cells are recomputed
+//       redundantly instead of waiting for the neighbouring CTA -- same inputs, same arithmetic,
+//       so bit-identical values), using only OLD black values of planes k, k+1, k+2;
+//   (2) black-updates plane k over the tile, using only NEW red values of planes k-1, k, k+1;
+//   (3) writes plane k of the new iterate.
+// The iterate is ping-ponged between two buffers (read pp_old, write pp_new), so no CTA can
+// observe a half-updated neighbour.  Result = exactly a red half-sweep followed by a black
+// half-sweep, i.e. bit-identical to launching sor_rb_kernel twice, at
+//   read pp (8) + read rhs (8) + write pp (8) = 24 B/pt per ITERATION
+// instead of 48 B/pt for two in-place half-sweeps of colour-interleaved storage.
+// Domain boundaries use the reference's neighbour rule as an index map when the halo cells are
+// loaded (src/poisson.f90:57-92); requires 2-colourability (no odd periodic extent).
+constexpr int FTX = 32, FTY = 8, FNT = FTX * FTY;
+constexpr int FPX = FTX + 4, FPY = FTY + 4, FPL = FPX * FPY;  // staged pp plane, halo 2
+constexpr int FRX = FTX + 2, FRY = FTY + 2, FRL = FRX * FRY;  // staged rhs plane, halo 1
+constexpr int FNP = 5, FNR = 3;                                // ring slots
+constexpr int FRING = FRL - FNT;                               // 84 ring-1 cells
+
+struct FusedArgs {
+    const double* p_old;
+    double* p_new;
+    const double* rhs;
+    double ox, oy, oz, invA;
+    int mx, my, mz_lo, mz_hi;
+    int nx, ny, nz;
+    long long sy, sz;
+    int gz0;
+    int zchunk;
+};
+
+__device__ __forceinline__ int fmap(int q, int n, int mlo, int mhi) {
+    bool refl;
+    return map_index(q, n, mlo, mhi, refl);
+}
+
+__global__ void __launch_bounds__(FNT) sor_fused_kernel(const FusedArgs a, SorCtrl* ctrl) {
+    __shared__ double sp[FNP][FPL];
+    __shared__ double sr[FNR][FRL];
+    __shared__ double red[32];
+    if (*((volatile int*)&ctrl->done)) return;
+    const double omega = *((volatile double*)&ctrl->omega);
+    const double one_m_omega = 1.0 - omega;
+    const int tid = threadIdx.x;
+    const int tx = tid & (FTX - 1), ty = tid >> 5;
+    const int i0 = blockIdx.x * FTX, j0 = blockIdx.y * FTY;
+    const int kb = blockIdx.z * a.zchunk, ke = min(a.nz, kb + a.zchunk);
+
+    // loader slots: global offsets (inside a plane) of the staged cells this thread fetches
+    long long poff[2], roff[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int c = tid + q * FNT;
+        poff[q] = -1;
+        if (c < FPL) {
+            const int gi = i0 - 2 + c % FPX, gj = j0 - 2 + c / FPX;
+            if (gi < a.nx + 2 && gj < a.ny + 2)
+                poff[q] = fmap(gi, a.nx, a.mx, a.mx) + a.sy * fmap(gj, a.ny, a.my, a.my);
+        }
+        roff[q] = -1;
+        if (c < FRL) {
+            const int gi = i0 - 1 + c % FRX, gj = j0 - 1 + c / FRX;
+            if (gi < a.nx + 1 && gj < a.ny + 1)
+                roff[q] = fmap(gi, a.nx, a.mx, a.mx) + a.sy * fmap(gj, a.ny, a.my, a.my);
+        }
+    }
+    auto zoff = [&](int plane) { return a.sz * (long long)fmap(plane, a.nz, a.mz_lo, a.mz_hi); };
+    auto pslot = [&](int plane) { return (plane - (kb - 2)) % FNP; };
+    auto rslot = [&](int plane) { return (plane - (kb - 1)) % FNR; };
+    auto load_p = [&](int plane, double* v) {
+        const long long z = zoff(plane);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) v[q] = (poff[q] >= 0) ? __ldg(a.p_old + z + poff[q]) : 0.0;
+    };
+    auto load_r = [&](int plane, double* v) {
+        const long long z = zoff(plane);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) v[q] = (roff[q] >= 0) ? __ldg(a.rhs + z + roff[q]) : 0.0;
+    };
+    auto store_p = [&](int plane, const double* v) {
+        double* d = sp[pslot(plane)];
+        d[tid] = v[0];
+        if (tid + FNT < FPL) d[tid + FNT] = v[1];
+    };
+    auto store_r = [&](int plane, const double* v) {
+        double* d = sr[rslot(plane)];
+        d[tid] = v[0];
+        if (tid + FNT < FRL) d[tid + FNT] = v[1];
+    };
+
+    // own cell and (for the first 84 threads) one ring-1 cell, in staged-pp coordinates
+    const int own = (ty + 2) * FPX + tx + 2;
+    int ring = -1;
+    if (tid < FRING) {
+        int lx, ly;
+        if (tid < FRX) lx = 1 + tid, ly = 1;
+        else if (tid < 2 * FRX) lx = 1 + tid - FRX, ly = FPY - 2;
+        else if (tid < 2 * FRX + FTY) lx = 1, ly = 2 + tid - 2 * FRX;
+        else lx = FPX - 2, ly = 2 + tid - 2 * FRX - FTY;
+        ring = ly * FPX + lx;
+    }
+    const int gi = i0 + tx, gj = j0 + ty;
+    const bool in_dom = gi < a.nx && gj < a.ny;
+    const int cpar = (gi + gj + a.gz0) & 1;  // colour of the own cell in plane 0
+
+    double dmax = 0.0;
+    // red update of staged cell `cell` in plane q (all its neighbours are black = old)
+    auto red_update = [&](int cell, int q, bool count) {
+        double* S = sp[pslot(q)];
+        const double* Sm = sp[pslot(q - 1)];
+        const double* Sp = sp[pslot(q + 1)];
+        const int lx = cell % FPX, ly = cell / FPX;
+        const double pc = S[cell];
+        const double r = sr[rslot(q)][(ly - 1) * FRX + lx - 1];
+        // src/poisson.f90:95-98 with "/ A" as "* (1/A)" (see sor_point)
+        const double p_new = (-(a.ox * (S[cell - 1] + S[cell + 1])) -
+                              a.oy * (S[cell - FPX] + S[cell + FPX]) -
+                              a.oz * (Sm[cell] + Sp[cell]) + r) * a.invA;
+        S[cell] = one_m_omega * pc + omega * p_new;  // :102
+        if (count) dmax = fmax(dmax, fabs(p_new - pc));  // :100
+    };
+    auto red_plane = [&](int q, bool owned_plane) {
+        // colour 0 ("red") = (i + j + global k) even
+        if (((cpar + q) & 1) == 0) red_update(own, q, owned_plane && in_dom);
+        if (ring >= 0) {
+            const int lx = ring % FPX, ly = ring / FPX;
+            if (((i0 - 2 + lx + j0 - 2 + ly + a.gz0 + q) & 1) == 0) red_update(ring, q, false);
+        }
+    };
+
+    double pv[2], rv[2];
+    // prologue: planes kb-2 .. kb+1 of pp, kb-1 .. kb of rhs; then red(kb-1), red(kb)
+    for (int q = kb - 2; q <= kb + 1; ++q) {
+        load_p(q, pv);
+        store_p(q, pv);
+    }
+    for (int q = kb - 1; q <= kb; ++q) {
+        load_r(q, rv);
+        store_r(q, rv);
+    }
+    load_p(kb + 2, pv);
+    load_r(kb + 1, rv);
+    __syncthreads();
+    red_plane(kb - 1, false);
+    red_plane(kb, true);
+
+    for (int k = kb; k < ke; ++k) {
+        store_p(k + 2, pv);
+        store_r(k + 1, rv);
+        if (k + 3 <= ke + 1) load_p(k + 3, pv);
+        if (k + 2 <= ke) load_r(k + 2, rv);
+        __syncthreads();
+        red_plane(k + 1, k + 1 < ke);
+        __syncthreads();
+        if (in_dom) {
+            const double* S = sp[pslot(k)];
+            double v = S[own];
+            if (((cpar + k) & 1) == 1) {  // black: neighbours are all new red
+                const double* Sm = sp[pslot(k - 1)];
+                const double* Sp = sp[pslot(k + 1)];
+                const double r = sr[rslot(k)][(ty + 1) * FRX + tx + 1];
+                const double p_new = (-(a.ox * (S[own - 1] + S[own + 1])) -
+                                      a.oy * (S[own - FPX] + S[own + FPX]) -
+                                      a.oz * (Sm[own] + Sp[own]) + r) * a.invA;
+                dmax = fmax(dmax, fabs(p_new - v));
+                v = one_m_omega * v + omega * p_new;
+            }
+            a.p_new[(long long)k * a.sz + (long long)gj * a.sy + gi] = v;
+        }
+    }
+    const double bm = block_max(dmax, red);
+    if (tid == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+}
+
 // one hyperplane of the lexicographic sweep, reference arithmetic (division by A)
 __global__ void __launch_bounds__(256) sor_wavefront_kernel(const SorArgs a, int h,
                                                             SorCtrl* ctrl) {
@@ -202,6 +380,29 @@ int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class,
         sor_seam_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, colour, ctrl, nxf, nyf,
                                                                        nzf);
     }
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,
+                     SorCtrl* ctrl) {
+    FusedArgs f;
+    f.p_old = p_old, f.p_new = p_new, f.rhs = a.rhs;
+    f.ox = a.oneondx2, f.oy = a.oneondy2, f.oz = a.oneondz2, f.invA = a.invA;
+    f.mx = a.mx, f.my = a.my, f.mz_lo = a.mz_lo, f.mz_hi = a.mz_hi;
+    f.nx = a.nx, f.ny = a.ny, f.nz = a.nz;
+    f.sy = a.sy, f.sz = a.sz;
+    f.gz0 = a.gz0;
+    const int gx = (a.nx + FTX - 1) / FTX, gy = (a.ny + FTY - 1) / FTY;
+    // 4 extra planes per chunk: keep chunks long
+    const int target = 148 * 6;
+    int nch = (target + gx * gy - 1) / (gx * gy);
+    int maxch = a.nz / 48;
+    if (maxch < 1) maxch = 1;
+    if (nch > maxch) nch = maxch;
+    if (nch < 1) nch = 1;
+    f.zchunk = (a.nz + nch - 1) / nch;
+    sor_fused_kernel<<<dim3(gx, gy, (a.nz + f.zchunk - 1) / f.zchunk), FNT, 0, st>>>(f, ctrl);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
