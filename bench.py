@@ -42,7 +42,8 @@ PI = 3.141592653589793
 # algorithmic bytes per grid point and launch (SURVEY.md 8d / DESIGN.md "Kernels")
 B_RHS = {1: 72.0, 2: 96.0, 3: 120.0}     # Euler / AB2 / AB3 (+8 with LES nu_t)
 B_DIV = 32.0
-B_SOR_HALF = 16.0                        # one colour half-sweep = half of 32 B/pt per iteration
+B_SOR_HALF = 16.0     # in-place colour half-sweep (odd periodic grids): half of 32 B/pt/iteration
+B_SOR_FUSED = 24.0    # fused red+black pass with ping-pong: read pp + read rhs + write pp
 B_CORR = 56.0
 B_TRANSEQ = 88.0
 
@@ -394,17 +395,21 @@ def main():
             stages[k] = {"launches": int(cnt), "ms_per_launch": ms / cnt, "bytes_per_pt": b,
                          "gbs": b * nloc / (ms / cnt * 1e-3) / 1e9}
     ms_sor, sweeps = tm["sor"]
+    # fused single-pass red+black kernel unless an odd periodic extent forces the 4-class sweep
+    fused = not (bc[0] == 0 and (n % 2 or nz % 2))
     if sweeps:
-        half = 2 * sweeps
-        stages["sor"] = {"launches": int(half), "ms_per_launch": ms_sor / half,
-                         "bytes_per_pt": B_SOR_HALF,
-                         "gbs": B_SOR_HALF * nloc / (ms_sor / half * 1e-3) / 1e9,
-                         "iterations_per_step": sweeps / K}
+        nl = sweeps if fused else 2 * sweeps
+        bpp = B_SOR_FUSED if fused else B_SOR_HALF
+        stages["sor"] = {"launches": int(nl), "ms_per_launch": ms_sor / nl, "bytes_per_pt": bpp,
+                         "gbs": bpp * nloc / (ms_sor / nl * 1e-3) / 1e9,
+                         "iterations_per_step": sweeps / K,
+                         "kernel": "sor_fused_kernel" if fused else "sor_rb_kernel"}
     for k in stages:
         stages[k]["frac"] = stages[k]["gbs"] / peak
         stages[k]["share_of_step"] = stages[k]["ms_per_launch"] * stages[k]["launches"] / ms_dev
-    kernel_of = {"rhs": "vel_kernel<RhsEpi>", "div": "div_kernel", "sor": "sor_rb_kernel",
-                 "corr": "corr_kernel"}
+    kernel_of = {"rhs": "march_kernel<3,0,1,RhsEpi>", "div": "march_kernel<1,2,2,DivEpi>",
+                 "sor": "sor_fused_kernel" if fused else "sor_rb_kernel",
+                 "corr": "march_kernel<1,0,4,CorrEpi>"}
     dom = max(stages, key=lambda k: stages[k]["share_of_step"]) if stages else None
     roofline = None
     if dom:
@@ -415,7 +420,7 @@ def main():
                     "ms_per_launch": s["ms_per_launch"], "share_of_step": s["share_of_step"],
                     "stages": stages}
     k_mean = float(np.mean(iters))
-    b_step = b_rhs + B_DIV + B_CORR + 32.0 * k_mean
+    b_step = b_rhs + B_DIV + B_CORR + (B_SOR_FUSED if fused else 32.0) * k_mean
     whole = {"bytes_per_pt_step": b_step, "gbs": b_step * nloc / (ms_dev / K * 1e-3) / 1e9}
     whole["frac"] = whole["gbs"] / peak
 

@@ -39,54 +39,71 @@ struct MarchGeom {
     int sim2d;
 };
 
-template <int NF>
+// NFZ fields need the 7-plane z window (ring of 7+P stages), NFC fields only the plane being
+// computed (ring of 1+P stages); P = prefetch distance in planes.  Fields are ordered z-fields
+// first in MarchMaps.
+template <int NFZ, int NFC, int P>
 constexpr int march_smem_bytes() {
-    return MNST * NF * MFIELD * 8 + MNST * 8;
+    return (NFZ * (7 + P) + NFC * (1 + P)) * MFIELD * 8 + (P + 1) * 8;
 }
 
-// The staged window seen by one thread: p[m] points at this thread's cell of field 0 in plane
-// k-3+m; field f is MFIELD doubles further.
-template <int NF>
+// The staged data seen by one thread: p[m] points at this thread's cell of z-field 0 in plane
+// k-3+m (z-field f is MFIELD doubles further); q points at its cell of c-field 0 in plane k.
+template <int NFZ, int NFC = 0>
 struct Ring {
     const double* p[7];
+    const double* q;
     __device__ __forceinline__ double c(int f) const { return p[3][f * MFIELD]; }
     __device__ __forceinline__ double x(int f, int d) const { return p[3][f * MFIELD + d]; }
     __device__ __forceinline__ double y(int f, int d) const { return p[3][f * MFIELD + d * MBX]; }
     __device__ __forceinline__ double z(int f, int d) const { return p[3 + d][f * MFIELD]; }
+    __device__ __forceinline__ double cx(int f, int d) const { return q[f * MFIELD + d]; }
+    __device__ __forceinline__ double cy(int f, int d) const { return q[f * MFIELD + d * MBX]; }
     // src/derivation.f90:43-47 / :529-533 along each axis
-    __device__ __forceinline__ double d1x(int f, const Coef& q) const {
-        return d1_expr(q.a1, q.b1, q.c1, x(f, -3), x(f, -2), x(f, -1), x(f, 1), x(f, 2), x(f, 3));
+    __device__ __forceinline__ double d1x(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, x(f, -3), x(f, -2), x(f, -1), x(f, 1), x(f, 2), x(f, 3));
     }
-    __device__ __forceinline__ double d1y(int f, const Coef& q) const {
-        return d1_expr(q.a1, q.b1, q.c1, y(f, -3), y(f, -2), y(f, -1), y(f, 1), y(f, 2), y(f, 3));
+    __device__ __forceinline__ double d1y(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, y(f, -3), y(f, -2), y(f, -1), y(f, 1), y(f, 2), y(f, 3));
     }
-    __device__ __forceinline__ double d1z(int f, const Coef& q) const {
-        return d1_expr(q.a1, q.b1, q.c1, z(f, -3), z(f, -2), z(f, -1), z(f, 1), z(f, 2), z(f, 3));
+    __device__ __forceinline__ double d1z(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, z(f, -3), z(f, -2), z(f, -1), z(f, 1), z(f, 2), z(f, 3));
     }
-    __device__ __forceinline__ double d2x(int f, const Coef& q) const {
-        return d2_expr(q.a2, q.b2, q.c2, x(f, -2), x(f, -1), c(f), x(f, 1), x(f, 2));
+    __device__ __forceinline__ double d2x(int f, const Coef& k) const {
+        return d2_expr(k.a2, k.b2, k.c2, x(f, -2), x(f, -1), c(f), x(f, 1), x(f, 2));
     }
-    __device__ __forceinline__ double d2y(int f, const Coef& q) const {
-        return d2_expr(q.a2, q.b2, q.c2, y(f, -2), y(f, -1), c(f), y(f, 1), y(f, 2));
+    __device__ __forceinline__ double d2y(int f, const Coef& k) const {
+        return d2_expr(k.a2, k.b2, k.c2, y(f, -2), y(f, -1), c(f), y(f, 1), y(f, 2));
     }
-    __device__ __forceinline__ double d2z(int f, const Coef& q) const {
-        return d2_expr(q.a2, q.b2, q.c2, z(f, -2), z(f, -1), c(f), z(f, 1), z(f, 2));
+    __device__ __forceinline__ double d2z(int f, const Coef& k) const {
+        return d2_expr(k.a2, k.b2, k.c2, z(f, -2), z(f, -1), c(f), z(f, 1), z(f, 2));
+    }
+    // centre-only fields
+    __device__ __forceinline__ double c_d1x(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, cx(f, -3), cx(f, -2), cx(f, -1), cx(f, 1), cx(f, 2),
+                       cx(f, 3));
+    }
+    __device__ __forceinline__ double c_d1y(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, cy(f, -3), cy(f, -2), cy(f, -1), cy(f, 1), cy(f, 2),
+                       cy(f, 3));
     }
 };
 
 // Epilogue concept:
 //   struct Pre;                                   streamed operands of one point
 //   Pre  prefetch(long long m, bool ok) const;    issue their loads (m = element offset)
-//   void apply(const Ring<NF>&, long long m, int i, int j, int k, const Pre&);
+//   void apply(const Ring<NFZ,NFC>&, long long m, int i, int j, int k, const Pre&);
 //   void finish(int tid, double* smem);           after the march (block reductions)
-template <int NF, class Epi, int MINB>
+template <int NFZ, int NFC, int P, class Epi, int MINB>
 __global__ void __launch_bounds__(MNT, MINB)
-    march_kernel(const __grid_constant__ MarchMaps<NF> maps, const MarchGeom g, Epi epi) {
+    march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC> maps, const MarchGeom g, Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* ring = reinterpret_cast<double*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + MNST * NF * MFIELD * 8);
-    constexpr int STAGE = NF * MFIELD;                 // doubles
-    constexpr uint32_t STAGE_BYTES = STAGE * 8;
+    constexpr int NZS = 7 + P, NCS = 1 + P, NB = P + 1;
+    constexpr int ZSTAGE = NFZ * MFIELD, CSTAGE = NFC * MFIELD;  // doubles
+    double* zring = reinterpret_cast<double*>(smem_raw);
+    double* cring = zring + NZS * ZSTAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cring + NCS * CSTAGE);
+    constexpr uint32_t PLANE_BYTES = MFIELD * 8;
 
     const int tid = threadIdx.x;
     const int tx = tid & (MTX - 1), ty = tid >> 5;
@@ -96,62 +113,81 @@ __global__ void __launch_bounds__(MNT, MINB)
     const int ke = min(g.nz, kb + g.zchunk);
     const bool in_dom = (i < g.nx) && (j < g.ny);
 
-    const uint32_t ring_s = smem_u32(ring);
+    const uint32_t zring_s = smem_u32(zring), cring_s = smem_u32(cring);
     const uint32_t bars_s = smem_u32(bars);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < MNST; ++s) mbar_init(bars_s + 8 * s, 1);
+        for (int s = 0; s < NB; ++s) mbar_init(bars_s + 8 * s, 1);
         fence_barrier_init();
     }
     __syncthreads();
 
     // box origin in tensor coordinates: element (GX + i0 - MXO, GH + j0 - R, GH + plane)
     const int cx = GX + i0 - MXO, cy = GH + j0 - R;
-    auto issue = [&](int plane, int stage) {
-        const uint32_t bar = bars_s + 8 * stage;
-        mbar_expect_tx(bar, STAGE_BYTES);
+    // z-plane `plane` lives in z-stage (plane - (kb-3)) mod NZS, c-plane in (plane - kb) mod NCS
+    auto issue_z = [&](int plane, uint32_t bar) {
+        const int st = (plane - (kb - R)) % NZS;
 #pragma unroll
-        for (int f = 0; f < NF; ++f)
-            tma_load_3d(ring_s + (uint32_t)(stage * STAGE + f * MFIELD) * 8, &maps.m[f], bar, cx,
-                        cy, GH + plane);
+        for (int f = 0; f < NFZ; ++f)
+            tma_load_3d(zring_s + (uint32_t)(st * ZSTAGE + f * MFIELD) * 8, &maps.m[f], bar, cx, cy,
+                        GH + plane);
+    };
+    auto issue_c = [&](int plane, uint32_t bar) {
+        const int st = (plane - kb) % NCS;
+#pragma unroll
+        for (int f = 0; f < NFC; ++f)
+            tma_load_3d(cring_s + (uint32_t)(st * CSTAGE + f * MFIELD) * 8, &maps.m[NFZ + f], bar,
+                        cx, cy, GH + plane);
+    };
+    // "need group" n = what iteration n waits for: z-plane kb+n+3 and c-plane kb+n (group 0 also
+    // carries z-planes kb-3 .. kb+2); its barrier is n mod NB
+    const int niter = ke - kb;
+    auto issue_group = [&](int n) {
+        const uint32_t bar = bars_s + 8 * (n % NB);
+        const int nz_planes = (n == 0) ? 7 : 1;
+        mbar_expect_tx(bar, (uint32_t)(nz_planes * NFZ + NFC) * PLANE_BYTES);
+        if (n == 0) {
+#pragma unroll
+            for (int s = 0; s < 6; ++s) issue_z(kb - R + s, bar);
+        }
+        issue_z(kb + n + R, bar);
+        issue_c(kb + n, bar);
     };
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < 7; ++s) issue(kb - R + s, s);
+        for (int n = 0; n < P && n < niter; ++n) issue_group(n);
     }
 
     const long long m0 = (long long)j * g.sy + i;
     typename Epi::Pre cur = epi.prefetch(m0 + (long long)kb * g.sz, in_dom);
     const int cell = (ty + R) * MBX + tx + MXO;
-#pragma unroll
-    for (int s = 0; s < 6; ++s) mbar_wait(bars_s + 8 * s, 0);
 
     for (int k = kb; k < ke; ++k) {
         const int it = k - kb;
         // streamed operands of the next plane
         typename Epi::Pre nxt = epi.prefetch(m0 + (long long)(k + 1) * g.sz, in_dom && (k + 1 < ke));
-        // plane k+3 has landed?
-        mbar_wait(bars_s + 8 * ((it + 6) & 7), ((it + 6) >> 3) & 1);
-        // every thread is done with plane k-1, so the stage of plane k-4 can be refilled
+        // every thread is done with plane k-1: its stages can be refilled with group it+P
         __syncthreads();
-        if (tid == 0 && k + 4 <= ke + 2) issue(k + 4, (it + 7) & 7);
+        if (tid == 0 && it + P < niter) issue_group(it + P);
+        // group `it` has landed?
+        mbar_wait(bars_s + 8 * (it % NB), (it / NB) & 1);
         if (in_dom) {
-            Ring<NF> r;
+            Ring<NFZ, NFC> r;
 #pragma unroll
-            for (int m = 0; m < 7; ++m) r.p[m] = ring + ((it + m) & 7) * STAGE + cell;
+            for (int m = 0; m < 7; ++m) r.p[m] = zring + ((it + m) % NZS) * ZSTAGE + cell;
+            r.q = cring + (it % NCS) * CSTAGE + cell;
             epi.apply(r, m0 + (long long)k * g.sz, i, j, k, cur);
         }
         cur = nxt;
     }
     __syncthreads();
-    epi.finish(tid, ring);
+    epi.finish(tid, zring);
 }
 
-template <int NF, class Epi, int MINB>
-int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NF>& maps, const Epi& epi) {
+template <int NFZ, int NFC, int P, class Epi, int MINB>
+int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC>& maps, const Epi& epi) {
     static bool attr_set = false;
-    auto kern = march_kernel<NF, Epi, MINB>;
-    constexpr int smem = march_smem_bytes<NF>();
+    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB>;
+    constexpr int smem = march_smem_bytes<NFZ, NFC, P>();
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
             cudaSuccess)

@@ -139,11 +139,15 @@ __global__ void __launch_bounds__(256) sor_seam_kernel(const SorArgs a, int colo
 // instead of 48 B/pt for two in-place half-sweeps of colour-interleaved storage.
 // Domain boundaries use the reference's neighbour rule as an index map when the halo cells are
 // loaded (src/poisson.f90:57-92); requires 2-colourability (no odd periodic extent).
-constexpr int FTX = 32, FTY = 8, FNT = FTX * FTY;
-constexpr int FPX = FTX + 4, FPY = FTY + 4, FPL = FPX * FPY;  // staged pp plane, halo 2
-constexpr int FRX = FTX + 2, FRY = FTY + 2, FRL = FRX * FRY;  // staged rhs plane, halo 1
-constexpr int FNP = 5, FNR = 3;                                // ring slots
-constexpr int FRING = FRL - FNT;                               // 84 ring-1 cells
+// Shared-memory planes are stored colour-split: cell (lx, ly) of the 36 x 20 staged plane sits
+// at ly*36 + (lx&1)*18 + (lx>>1), so the cells of one colour in a row are contiguous (no bank
+// conflicts) and a thread that owns the x-pair (2p, 2p+1) is active in both half-sweeps.
+constexpr int FTX = 32, FTY = 16, FNT = 256;                  // tile; 16 x 16 threads own x-pairs
+constexpr int FPX = FTX + 4, FPY = FTY + 4, FPL = FPX * FPY;  // staged plane, halo 2 (720 cells)
+constexpr int FHALF = FPX / 2;                                // 18
+constexpr int FNP = 5, FNR = 3;                               // ring slots: pp planes, rhs planes
+constexpr int FNL = (FPL + FNT - 1) / FNT;                    // loader slots per thread (3)
+constexpr int FRING = 2 * (FTX + 2) + 2 * FTY;                // 100 ring-1 cells
 
 struct FusedArgs {
     const double* p_old;
@@ -161,140 +165,159 @@ __device__ __forceinline__ int fmap(int q, int n, int mlo, int mhi) {
     bool refl;
     return map_index(q, n, mlo, mhi, refl);
 }
+__device__ __forceinline__ int fcell(int lx, int ly) {
+    return ly * FPX + (lx & 1) * FHALF + (lx >> 1);
+}
 
-__global__ void __launch_bounds__(FNT) sor_fused_kernel(const FusedArgs a, SorCtrl* ctrl) {
-    __shared__ double sp[FNP][FPL];
-    __shared__ double sr[FNR][FRL];
+__global__ void __launch_bounds__(FNT, 3) sor_fused_kernel(const FusedArgs a, SorCtrl* ctrl) {
+    __shared__ __align__(16) double sp[FNP][FPL];
+    __shared__ __align__(16) double sr[FNR][FPL];
     __shared__ double red[32];
     if (*((volatile int*)&ctrl->done)) return;
     const double omega = *((volatile double*)&ctrl->omega);
     const double one_m_omega = 1.0 - omega;
     const int tid = threadIdx.x;
-    const int tx = tid & (FTX - 1), ty = tid >> 5;
+    const int px = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.x * FTX, j0 = blockIdx.y * FTY;
     const int kb = blockIdx.z * a.zchunk, ke = min(a.nz, kb + a.zchunk);
 
-    // loader slots: global offsets (inside a plane) of the staged cells this thread fetches
-    long long poff[2], roff[2];
+    // loader slots: global in-plane offset and shared index of the staged cells this thread
+    // fetches (index map of src/poisson.f90:57-92 applied once, outside the march)
+    long long poff[FNL];
+    int pidx[FNL];
+    bool rok[FNL];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < FNL; ++q) {
         const int c = tid + q * FNT;
         poff[q] = -1;
+        pidx[q] = 0;
+        rok[q] = false;
         if (c < FPL) {
-            const int gi = i0 - 2 + c % FPX, gj = j0 - 2 + c / FPX;
-            if (gi < a.nx + 2 && gj < a.ny + 2)
+            const int lx = c % FPX, ly = c / FPX;
+            const int gi = i0 - 2 + lx, gj = j0 - 2 + ly;
+            pidx[q] = fcell(lx, ly);
+            if (gi < a.nx + 2 && gj < a.ny + 2) {
                 poff[q] = fmap(gi, a.nx, a.mx, a.mx) + a.sy * fmap(gj, a.ny, a.my, a.my);
-        }
-        roff[q] = -1;
-        if (c < FRL) {
-            const int gi = i0 - 1 + c % FRX, gj = j0 - 1 + c / FRX;
-            if (gi < a.nx + 1 && gj < a.ny + 1)
-                roff[q] = fmap(gi, a.nx, a.mx, a.mx) + a.sy * fmap(gj, a.ny, a.my, a.my);
+                rok[q] = lx >= 1 && lx <= FPX - 2 && ly >= 1 && ly <= FPY - 2;  // ring-1 region
+            }
         }
     }
-    auto zoff = [&](int plane) { return a.sz * (long long)fmap(plane, a.nz, a.mz_lo, a.mz_hi); };
-    auto pslot = [&](int plane) { return (plane - (kb - 2)) % FNP; };
-    auto rslot = [&](int plane) { return (plane - (kb - 1)) % FNR; };
-    auto load_p = [&](int plane, double* v) {
-        const long long z = zoff(plane);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) v[q] = (poff[q] >= 0) ? __ldg(a.p_old + z + poff[q]) : 0.0;
-    };
-    auto load_r = [&](int plane, double* v) {
-        const long long z = zoff(plane);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) v[q] = (roff[q] >= 0) ? __ldg(a.rhs + z + roff[q]) : 0.0;
-    };
-    auto store_p = [&](int plane, const double* v) {
-        double* d = sp[pslot(plane)];
-        d[tid] = v[0];
-        if (tid + FNT < FPL) d[tid + FNT] = v[1];
-    };
-    auto store_r = [&](int plane, const double* v) {
-        double* d = sr[rslot(plane)];
-        d[tid] = v[0];
-        if (tid + FNT < FRL) d[tid + FNT] = v[1];
-    };
-
-    // own cell and (for the first 84 threads) one ring-1 cell, in staged-pp coordinates
-    const int own = (ty + 2) * FPX + tx + 2;
-    int ring = -1;
+    // own x-pair (lx = 2+2px, 3+2px; ly = 2+ty): shared index of the EVEN member; the odd member
+    // is FHALF further.  cpar: colour of the even member in local plane 0 (0 = red).
+    const int own = (ty + 2) * FPX + 1 + px;
+    const int gi = i0 + 2 * px, gj = j0 + ty;
+    const bool in0 = gi < a.nx && gj < a.ny, in1 = gi + 1 < a.nx && gj < a.ny;
+    const int cpar = (gi + gj + a.gz0) & 1;
+    // one ring-1 cell for the first 100 threads
+    int ring = -1, rpar = 0;
     if (tid < FRING) {
         int lx, ly;
-        if (tid < FRX) lx = 1 + tid, ly = 1;
-        else if (tid < 2 * FRX) lx = 1 + tid - FRX, ly = FPY - 2;
-        else if (tid < 2 * FRX + FTY) lx = 1, ly = 2 + tid - 2 * FRX;
-        else lx = FPX - 2, ly = 2 + tid - 2 * FRX - FTY;
-        ring = ly * FPX + lx;
+        if (tid < FTX + 2) lx = 1 + tid, ly = 1;
+        else if (tid < 2 * (FTX + 2)) lx = 1 + tid - (FTX + 2), ly = FPY - 2;
+        else if (tid < 2 * (FTX + 2) + FTY) lx = 1, ly = 2 + tid - 2 * (FTX + 2);
+        else lx = FPX - 2, ly = 2 + tid - 2 * (FTX + 2) - FTY;
+        ring = fcell(lx, ly);
+        rpar = (i0 - 2 + lx + j0 - 2 + ly + a.gz0) & 1;
+        // neighbour offsets of a cell depend on which half it is in
+        if (lx & 1) ring |= 0x10000;
     }
-    const int gi = i0 + tx, gj = j0 + ty;
-    const bool in_dom = gi < a.nx && gj < a.ny;
-    const int cpar = (gi + gj + a.gz0) & 1;  // colour of the own cell in plane 0
 
     double dmax = 0.0;
-    // red update of staged cell `cell` in plane q (all its neighbours are black = old)
-    auto red_update = [&](int cell, int q, bool count) {
-        double* S = sp[pslot(q)];
-        const double* Sm = sp[pslot(q - 1)];
-        const double* Sp = sp[pslot(q + 1)];
-        const int lx = cell % FPX, ly = cell / FPX;
+    // SOR update of the cell at shared index `cell` (odd: it sits in the odd half) of plane S
+    auto update = [&](double* S, const double* Sm, const double* Sp, const double* Rr, int cell,
+                      bool odd, bool store, bool count) -> double {
+        const int other = odd ? cell - FHALF : cell + FHALF;  // same (lx>>1) in the other half
+        const double west = odd ? S[other] : S[other - 1];
+        const double east = odd ? S[other + 1] : S[other];
         const double pc = S[cell];
-        const double r = sr[rslot(q)][(ly - 1) * FRX + lx - 1];
         // src/poisson.f90:95-98 with "/ A" as "* (1/A)" (see sor_point)
-        const double p_new = (-(a.ox * (S[cell - 1] + S[cell + 1])) -
-                              a.oy * (S[cell - FPX] + S[cell + FPX]) -
-                              a.oz * (Sm[cell] + Sp[cell]) + r) * a.invA;
-        S[cell] = one_m_omega * pc + omega * p_new;  // :102
+        const double p_new = (-(a.ox * (west + east)) - a.oy * (S[cell - FPX] + S[cell + FPX]) -
+                              a.oz * (Sm[cell] + Sp[cell]) + Rr[cell]) * a.invA;
+        const double v = one_m_omega * pc + omega * p_new;  // :102
+        if (store) S[cell] = v;
         if (count) dmax = fmax(dmax, fabs(p_new - pc));  // :100
-    };
-    auto red_plane = [&](int q, bool owned_plane) {
-        // colour 0 ("red") = (i + j + global k) even
-        if (((cpar + q) & 1) == 0) red_update(own, q, owned_plane && in_dom);
-        if (ring >= 0) {
-            const int lx = ring % FPX, ly = ring / FPX;
-            if (((i0 - 2 + lx + j0 - 2 + ly + a.gz0 + q) & 1) == 0) red_update(ring, q, false);
-        }
+        return v;
     };
 
-    double pv[2], rv[2];
-    // prologue: planes kb-2 .. kb+1 of pp, kb-1 .. kb of rhs; then red(kb-1), red(kb)
-    for (int q = kb - 2; q <= kb + 1; ++q) {
-        load_p(q, pv);
-        store_p(q, pv);
+    int s_m1 = 0, s_0 = 1, s_p1 = 2, s_p2 = 3, s_free = 4;  // pp slots of planes k-1 .. k+2, free
+    int r_0 = 0, r_p1 = 1, r_free = 2;                      // rhs slots of planes k, k+1, free
+    double pv[FNL], rv[FNL];
+    auto load = [&](int plane, bool want_p, bool want_r) {
+        const long long z = a.sz * (long long)fmap(plane, a.nz, a.mz_lo, a.mz_hi);
+#pragma unroll
+        for (int q = 0; q < FNL; ++q) {
+            if (want_p) pv[q] = (poff[q] >= 0) ? __ldg(a.p_old + z + poff[q]) : 0.0;
+            if (want_r) rv[q] = rok[q] ? __ldg(a.rhs + z + poff[q]) : 0.0;
+        }
+    };
+    auto stash = [&](double* d, const double* v) {
+#pragma unroll
+        for (int q = 0; q < FNL; ++q)
+            if (tid + q * FNT < FPL) d[pidx[q]] = v[q];
+    };
+    auto red_plane = [&](int q, int sm, int s0, int sp1, int rs, bool owned) {
+        // red = (i + j + global k) even.  Own pair: the even member is red iff cpar + q is even.
+        const bool odd = (cpar + q) & 1;
+        update(sp[s0], sp[sm], sp[sp1], sr[rs], own + (odd ? FHALF : 0), odd, true,
+               owned && (odd ? in1 : in0));
+        if (ring >= 0 && (((rpar + q) & 1) == 0))
+            update(sp[s0], sp[sm], sp[sp1], sr[rs], ring & 0xffff, (ring >> 16) & 1, true, false);
+    };
+
+    // prologue: pp planes kb-2 .. kb+1, rhs planes kb-1, kb; red(kb-1), red(kb)
+    load(kb - 2, true, false);
+    stash(sp[4], pv);  // temporarily: plane kb-2 in the free slot
+    load(kb - 1, true, true);
+    stash(sp[s_m1], pv);
+    stash(sr[r_free], rv);  // rhs(kb-1)
+    load(kb, true, true);
+    stash(sp[s_0], pv);
+    stash(sr[r_0], rv);
+    load(kb + 1, true, false);
+    stash(sp[s_p1], pv);
+    load(kb + 2, true, false);  // prefetch for the first march step
+    {
+        const long long z = a.sz * (long long)fmap(kb + 1, a.nz, a.mz_lo, a.mz_hi);
+#pragma unroll
+        for (int q = 0; q < FNL; ++q) rv[q] = rok[q] ? __ldg(a.rhs + z + poff[q]) : 0.0;
     }
-    for (int q = kb - 1; q <= kb; ++q) {
-        load_r(q, rv);
-        store_r(q, rv);
-    }
-    load_p(kb + 2, pv);
-    load_r(kb + 1, rv);
     __syncthreads();
-    red_plane(kb - 1, false);
-    red_plane(kb, true);
+    red_plane(kb - 1, 4, s_m1, s_0, r_free, false);
+    red_plane(kb, s_m1, s_0, s_p1, r_0, true);
+    __syncthreads();  // red(kb-1) read slot 4 (plane kb-2): done before it is overwritten
 
     for (int k = kb; k < ke; ++k) {
-        store_p(k + 2, pv);
-        store_r(k + 1, rv);
-        if (k + 3 <= ke + 1) load_p(k + 3, pv);
-        if (k + 2 <= ke) load_r(k + 2, rv);
-        __syncthreads();
-        red_plane(k + 1, k + 1 < ke);
-        __syncthreads();
-        if (in_dom) {
-            const double* S = sp[pslot(k)];
-            double v = S[own];
-            if (((cpar + k) & 1) == 1) {  // black: neighbours are all new red
-                const double* Sm = sp[pslot(k - 1)];
-                const double* Sp = sp[pslot(k + 1)];
-                const double r = sr[rslot(k)][(ty + 1) * FRX + tx + 1];
-                const double p_new = (-(a.ox * (S[own - 1] + S[own + 1])) -
-                                      a.oy * (S[own - FPX] + S[own + FPX]) -
-                                      a.oz * (Sm[own] + Sp[own]) + r) * a.invA;
-                dmax = fmax(dmax, fabs(p_new - v));
-                v = one_m_omega * v + omega * p_new;
-            }
-            a.p_new[(long long)k * a.sz + (long long)gj * a.sy + gi] = v;
+        stash(sp[s_p2], pv);   // plane k+2
+        stash(sr[r_p1], rv);   // rhs k+1
+        if (k + 3 <= ke + 1) load(k + 3, true, false);
+        if (k + 2 <= ke) {
+            const long long z = a.sz * (long long)fmap(k + 2, a.nz, a.mz_lo, a.mz_hi);
+#pragma unroll
+            for (int q = 0; q < FNL; ++q) rv[q] = rok[q] ? __ldg(a.rhs + z + poff[q]) : 0.0;
         }
+        __syncthreads();
+        red_plane(k + 1, s_0, s_p1, s_p2, r_p1, k + 1 < ke);
+        __syncthreads();
+        {
+            // black member of the own pair in plane k: all its neighbours are new red values
+            const bool odd = ((cpar + k) & 1) == 0;  // even member red -> odd member is black
+            const int bc = own + (odd ? FHALF : 0);
+            const double vb = update(sp[s_0], sp[s_m1], sp[s_p1], sr[r_0], bc, odd, false,
+                                     odd ? in1 : in0);
+            const double vr = sp[s_0][own + (odd ? 0 : FHALF)];
+            double* dst = a.p_new + (long long)k * a.sz + (long long)gj * a.sy + gi;
+            const double v0 = odd ? vr : vb, v1 = odd ? vb : vr;
+            if (in1) {
+                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            } else if (in0) {
+                dst[0] = v0;
+            }
+        }
+        // rotate the rings
+        const int t = s_m1;
+        s_m1 = s_0, s_0 = s_p1, s_p1 = s_p2, s_p2 = s_free, s_free = t;
+        const int u = r_0;
+        r_0 = r_p1, r_p1 = r_free, r_free = u;
     }
     const double bm = block_max(dmax, red);
     if (tid == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);

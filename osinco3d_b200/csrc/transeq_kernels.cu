@@ -121,7 +121,7 @@ int launch_transeq_rhs(cudaStream_t st, const Geom& g, const TranseqArgs& a) {
     e.s_old = e.s_clip = e.s_w = 0.0;
     MarchMaps<1> m;
     m.m[0] = *a.phi.tm;
-    return launch_march<1, TranseqEpi, 3>(st, g, m, e);
+    return launch_march<1, 0, 4, TranseqEpi, 3>(st, g, m, e);
 }
 
 int launch_transeq_clip(cudaStream_t st, const Geom& g, const double* phi_new, double* phi,

@@ -221,28 +221,28 @@ int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r) {
     e.q = coefs(r.cx, r.cy, r.cz);
     e.onere = r.onere, e.adu = r.adu, e.bdu = r.bdu, e.cdu = r.cdu, e.csd2 = r.csd2;
     e.iles = r.iles, e.sim2d = g.sim2d;
-    return launch_march<3, RhsEpi, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e);
+    return launch_march<3, 0, 1, RhsEpi, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e);
 }
 
 int launch_nu_t(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,
                 const Coef& cy, const Coef& cz, double csd2, double* nu_t) {
     NutEpi e;
     e.nu_t = nu_t, e.csd2 = csd2, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d;
-    return launch_march<3, NutEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
+    return launch_march<3, 0, 1, NutEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
 }
 
 int launch_rot(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx, const Coef& cy,
                const Coef& cz, double* rotx, double* roty, double* rotz) {
     RotEpi e;
     e.rx = rotx, e.ry = roty, e.rz = rotz, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d;
-    return launch_march<3, RotEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
+    return launch_march<3, 0, 1, RotEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
 }
 
 int launch_qcrit(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,
                  const Coef& cy, const Coef& cz, double* q) {
     QEpi e;
     e.qc = q, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d;
-    return launch_march<3, QEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
+    return launch_march<3, 0, 1, QEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
 }
 
 int stats_blocks(const Geom& g) {
@@ -256,7 +256,7 @@ int launch_stats(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& 
     StatsEpi e;
     e.partial = partial, e.xnu = xnu, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d;
     for (int s = 0; s < NSTAT; ++s) e.acc[s] = 0.0;
-    return launch_march<3, StatsEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
+    return launch_march<3, 0, 1, StatsEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
 }
 
 }  // namespace o3d
