@@ -628,9 +628,12 @@ int o3d_s_predict_velocity(o3d_session* s, int itime) {
         return O3D_ERR_CUDA;
     }
     span_end(s, ST_RHS, 1);
+    const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
     for (int k = 0; k < 3; ++k) {
         hist_rotate(s, k, tgt[k]);
-        touch(s, PRED_IDS[k]);
+        // the RHS kernel wrote the own-axis ghost images of u* (odd closure) with the interior
+        s->gaxes[PRED_IDS[k]] = (k == 2 && zhalo) ? 0u : (1u << k);
+        s->gpar[PRED_IDS[k]] = NAT3[k];
     }
     if (a.iles) touch(s, O3D_F_NU_T);
     return O3D_OK;
@@ -683,7 +686,13 @@ int o3d_s_correct_velocity(o3d_session* s) {
     if (launch_corr(s->st, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d))
         return O3D_ERR_CUDA;
     span_end(s, ST_CORR, 1);
-    for (int k = 0; k < 3; ++k) touch(s, VEL_IDS[k]);
+    {   // the correction kernel wrote the natural-parity ghost images of u with the interior
+        const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+        for (int k = 0; k < 3; ++k) {
+            s->gaxes[VEL_IDS[k]] = zhalo ? 0x3u : 0x7u;
+            s->gpar[VEL_IDS[k]] = NAT3[k];
+        }
+    }
     O3D_CUDA_CHECK(
         cudaMemcpyAsync(s->flag_h, s->flag_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));

@@ -37,6 +37,7 @@ struct MarchGeom {
     long long sy, sz;
     int zchunk;
     int sim2d;
+    int bx, by, bz_lo, bz_hi;  // closures, for epilogues that also write ghost images
 };
 
 // NFZ fields need the 7-plane z window (ring of 7+P stages), NFC fields only the plane being
@@ -90,6 +91,7 @@ struct Ring {
 };
 
 // Epilogue concept:
+//   void setup(const MarchGeom&, int i, int j);   per-thread constants, before the march
 //   struct Pre;                                   streamed operands of one point
 //   Pre  prefetch(long long m, bool ok) const;    issue their loads (m = element offset)
 //   void apply(const Ring<NFZ,NFC>&, long long m, int i, int j, int k, const Pre&);
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(MNT, MINB)
     }
 
     const long long m0 = (long long)j * g.sy + i;
+    epi.setup(g, i, j);
     typename Epi::Pre cur = epi.prefetch(m0 + (long long)kb * g.sz, in_dom);
     const int cell = (ty + R) * MBX + tx + MXO;
 
@@ -198,6 +201,7 @@ int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC>& map
     mg.nx = g.nx, mg.ny = g.ny, mg.nz = g.nz;
     mg.sy = g.sy, mg.sz = g.sz;
     mg.sim2d = g.sim2d;
+    mg.bx = g.bx, mg.by = g.by, mg.bz_lo = g.bz_lo, mg.bz_hi = g.bz_hi;
     const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
     mg.zchunk = pick_zchunk(gx * gy, g.nz);
     const int gz = (g.nz + mg.zchunk - 1) / mg.zchunk;

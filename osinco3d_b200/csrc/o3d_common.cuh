@@ -74,6 +74,29 @@ __host__ __device__ __forceinline__ int map_index(int q, int n, int mode_lo, int
     return q;
 }
 
+// Ghost images of an interior point: the element-index offsets (0 = none) of the up to two ghost
+// cells of its line that hold a copy of point p under the closure (low side / high side).
+// Producers use it to write the ghost cells together with the interior value, so that no
+// separate ghost-fill pass is needed after a fused kernel.
+struct Img2 {
+    int lo, hi;
+};
+__host__ __device__ __forceinline__ Img2 image_offsets(int p, int n, int mode_lo, int mode_hi) {
+    Img2 r;
+    r.lo = 0, r.hi = 0;
+    if (mode_lo == BM_MIRROR) {
+        if (p >= 1 && p <= R) r.lo = -2 * p;               // ghost -p = +-f(p)
+    } else if (mode_lo == BM_WRAP) {
+        if (p >= n - R) r.lo = -n;                         // ghost p-n = f(p)
+    }
+    if (mode_hi == BM_MIRROR) {
+        if (p >= n - 1 - R && p <= n - 2) r.hi = 2 * (n - 1 - p);  // ghost 2(n-1)-p = +-f(p)
+    } else if (mode_hi == BM_WRAP) {
+        if (p < R) r.hi = n;                               // ghost n+p = f(p)
+    }
+    return r;
+}
+
 // Coefficients exactly as the reference computes them.
 struct Coef {
     double a1, b1, c1;  // src/derivation.f90:26-30   1,9,45 / (60 d)

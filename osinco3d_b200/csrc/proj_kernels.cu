@@ -20,6 +20,7 @@ struct DivEpi {
     double dt;
     int divide, sim2d;
     typedef NoPre Pre;
+    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     __device__ __forceinline__ void apply(const Ring<1, 2>& r, long long m, int, int, int,
                                           const Pre&) {
@@ -41,6 +42,20 @@ struct CorrEpi {
     int* flag;
     int sim2d;
     int bad;
+    // ghost images of the corrected velocity, natural parity (component c is odd along axis c):
+    // the next RHS / statistics launch finds its closure already in the ghost cells
+    Img2 ix, iy;
+    int nz, bz_lo, bz_hi;
+    long long sy_, sz_;
+    bool mx, my, mz_lo, mz_hi;  // mirrored sides
+    __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j) {
+        ix = image_offsets(i, g.nx, g.bx, g.bx);
+        iy = image_offsets(j, g.ny, g.by, g.by);
+        nz = g.nz, bz_lo = g.bz_lo, bz_hi = g.bz_hi;
+        sy_ = g.sy, sz_ = g.sz;
+        mx = g.bx == BM_MIRROR, my = g.by == BM_MIRROR;
+        mz_lo = g.bz_lo == BM_MIRROR, mz_hi = g.bz_hi == BM_MIRROR;
+    }
     struct Pre {
         double v[3];
     };
@@ -50,7 +65,7 @@ struct CorrEpi {
         for (int c = 0; c < 3; ++c) p.v[c] = ok ? __ldg(up[c] + m) : 0.0;
         return p;
     }
-    __device__ __forceinline__ void apply(const Ring<1>& r, long long m, int, int, int,
+    __device__ __forceinline__ void apply(const Ring<1>& r, long long m, int, int, int k,
                                           const Pre& pre) {
         // src/integration.f90:298-300 (derxp, deryp, derzp)
         const double dpdx = r.d1x(0, cx);
@@ -63,6 +78,21 @@ struct CorrEpi {
         u[0][m] = u0;
         u[1][m] = u1;
         u[2][m] = u2;
+        const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
+        if (ix.lo | ix.hi | iy.lo | iy.hi | iz.lo | iz.hi) {  // boundary-adjacent threads only
+            const double v[3] = {u0, u1, u2};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double vx = (mx && c == 0) ? -v[c] : v[c];
+                if (ix.lo) u[c][m + ix.lo] = vx;
+                if (ix.hi) u[c][m + ix.hi] = vx;
+                const double vy = (my && c == 1) ? -v[c] : v[c];
+                if (iy.lo) u[c][m + iy.lo * sy_] = vy;
+                if (iy.hi) u[c][m + iy.hi * sy_] = vy;
+                if (iz.lo) u[c][m + iz.lo * sz_] = (mz_lo && c == 2) ? -v[c] : v[c];
+                if (iz.hi) u[c][m + iz.hi * sz_] = (mz_hi && c == 2) ? -v[c] : v[c];
+            }
+        }
         // src/integration.f90:309-325: contains_nan .or. maxval > 1000
         if (u0 != u0 || u1 != u1 || u2 != u2 || u0 > 1000. || u1 > 1000. || u2 > 1000.) bad = 1;
     }
@@ -96,7 +126,7 @@ int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const double
     e.dt = dt, e.flag = flag, e.sim2d = g.sim2d, e.bad = 0;
     MarchMaps<1> m;
     m.m[0] = *pp.tm;
-    return launch_march<1, 0, 4, CorrEpi, 4>(st, g, m, e);
+    return launch_march<1, 0, 1, CorrEpi, 3>(st, g, m, e);
 }
 
 }  // namespace o3d

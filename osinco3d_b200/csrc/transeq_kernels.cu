@@ -24,6 +24,7 @@ struct TranseqEpi {
     double resc, sc, adu, bdu, cdu;
     int iles, sim2d;
     double s_old, s_clip, s_w;
+    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
     struct Pre {
         double u[3], nut, f2v, f3v, srcv;
     };
@@ -121,7 +122,7 @@ int launch_transeq_rhs(cudaStream_t st, const Geom& g, const TranseqArgs& a) {
     e.s_old = e.s_clip = e.s_w = 0.0;
     MarchMaps<1> m;
     m.m[0] = *a.phi.tm;
-    return launch_march<1, 0, 4, TranseqEpi, 3>(st, g, m, e);
+    return launch_march<1, 0, 1, TranseqEpi, 3>(st, g, m, e);
 }
 
 int launch_transeq_clip(cudaStream_t st, const Geom& g, const double* phi_new, double* phi,

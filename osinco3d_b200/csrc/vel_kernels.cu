@@ -59,6 +59,22 @@ struct RhsEpi {
     Coefs3 q;
     double onere, adu, bdu, cdu, csd2;
     int iles, sim2d;
+    // ghost images of u* along each component's own axis (all that divergence(odd=1) needs,
+    // src/differential_operators.f90:30-32): odd closure -> mirrored copies change sign
+    Img2 ix, iy;
+    int nz, bz_lo, bz_hi;
+    long long sy_, sz_;
+    double sgx, sgy, sgz_lo, sgz_hi;
+    __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j) {
+        ix = image_offsets(i, g.nx, g.bx, g.bx);
+        iy = image_offsets(j, g.ny, g.by, g.by);
+        nz = g.nz, bz_lo = g.bz_lo, bz_hi = g.bz_hi;
+        sy_ = g.sy, sz_ = g.sz;
+        sgx = (g.bx == BM_MIRROR) ? -1.0 : 1.0;
+        sgy = (g.by == BM_MIRROR) ? -1.0 : 1.0;
+        sgz_lo = (g.bz_lo == BM_MIRROR) ? -1.0 : 1.0;
+        sgz_hi = (g.bz_hi == BM_MIRROR) ? -1.0 : 1.0;
+    }
     struct Pre {
         double f2v[3], f3v[3];
     };
@@ -71,7 +87,7 @@ struct RhsEpi {
         }
         return p;
     }
-    __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int,
+    __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int k,
                                           const Pre& pre) {
         const Grad G = gradient(r, q, sim2d);
         double nut = 0.0;
@@ -92,6 +108,17 @@ struct RhsEpi {
             const double upv = uc + adu * f + bdu * pre.f2v[c] + cdu * pre.f3v[c];
             f1[c][m] = f;
             up[c][m] = upv;
+            if (c == 0) {
+                if (ix.lo) up[0][m + ix.lo] = sgx * upv;
+                if (ix.hi) up[0][m + ix.hi] = sgx * upv;
+            } else if (c == 1) {
+                if (iy.lo) up[1][m + iy.lo * sy_] = sgy * upv;
+                if (iy.hi) up[1][m + iy.hi * sy_] = sgy * upv;
+            } else {
+                const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
+                if (iz.lo) up[2][m + iz.lo * sz_] = sgz_lo * upv;
+                if (iz.hi) up[2][m + iz.hi * sz_] = sgz_hi * upv;
+            }
         }
     }
     __device__ __forceinline__ void finish(int, double*) {}
@@ -105,6 +132,7 @@ struct NutEpi {
     double csd2;
     int sim2d;
     typedef NoPre Pre;
+    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int, const Pre&) {
         nu_t[m] = smagorinsky(gradient(r, q, sim2d), csd2);
@@ -119,6 +147,7 @@ struct RotEpi {
     Coefs3 q;
     int sim2d;
     typedef NoPre Pre;
+    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int, const Pre&) {
         const Grad G = gradient(r, q, sim2d);
@@ -134,6 +163,7 @@ struct QEpi {
     Coefs3 q;
     int sim2d;
     typedef NoPre Pre;
+    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int, const Pre&) {
         const Grad G = gradient(r, q, sim2d);
@@ -153,6 +183,7 @@ struct StatsEpi {
     int sim2d;
     double acc[NSTAT];
     typedef NoPre Pre;
+    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     __device__ __forceinline__ void apply(const Ring<3>& r, long long, int, int, int, const Pre&) {
         const Grad G = gradient(r, q, sim2d);
