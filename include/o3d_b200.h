@@ -224,6 +224,9 @@ typedef struct o3d_session o3d_session;
 /* multi-GPU bootstrap: rank 0 obtains 128 ncclUniqueId bytes, the launcher broadcasts them
  * (torch.distributed / MPI / a file) and every rank puts them in o3d_config.nccl_id */
 int o3d_nccl_unique_id(unsigned char* out128);
+/* the z-slab partition o3d_session_create applies: rank owns global planes [z0, z0+nz_local);
+ * contiguous slabs, remainder planes to the low ranks.  Pure host arithmetic (no device). */
+int o3d_slab_partition(int nz, int nranks, int rank, int* z0, int* nz_local);
 
 /* fields a session owns (module `initialization` globals) */
 enum {
@@ -276,6 +279,9 @@ int o3d_s_q_criterion(o3d_session* s, int dst);
 /* current SOR relaxation factor (inout across steps, src/integration.f90:222,247) */
 int o3d_get_omega(const o3d_session* s, double* omega);
 int o3d_set_omega(o3d_session* s, double omega);
+/* the Poisson controls are per-call arguments of correct_pression in the reference
+ * (src/integration.f90:199-200); a resident driver pushes them into the session with this */
+int o3d_session_set_poisson(o3d_session* s, double eps, int kmax, int idyn, int multigrid);
 /* accumulated per-stage device time in ms since the last reset (CUDA events on the
  * session stream): out[0]=rhs/predictor out[1]=divergence out[2]=sor out[3]=correction
  * out[4]=transeq out[5]=halo exchange; counts[] = launches per stage */

@@ -91,6 +91,8 @@ def lib():
         _lib.o3d_s_q_criterion.argtypes = [C.c_void_p, C.c_int]
         _lib.o3d_get_omega.argtypes = [C.c_void_p, dp]
         _lib.o3d_set_omega.argtypes = [C.c_void_p, C.c_double]
+        _lib.o3d_session_set_poisson.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                                 C.c_int]
         _lib.o3d_s_timers.argtypes = [C.c_void_p, dp, C.POINTER(C.c_longlong), C.c_int]
         _lib.o3d_s_enable_timers.argtypes = [C.c_void_p, C.c_int]
         _lib.o3d_s_stopwatch_start.argtypes = [C.c_void_p]

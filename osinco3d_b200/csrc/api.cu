@@ -326,6 +326,14 @@ int o3d_nccl_unique_id(unsigned char* out128) {
     return nccl_unique_id(out128);
 }
 
+int o3d_slab_partition(int nz, int nranks, int rank, int* z0, int* nz_local) {
+    if (nz < 1 || nranks < 1 || rank < 0 || rank >= nranks) return O3D_ERR_INVALID;
+    const int q = nz / nranks, r = nz % nranks;
+    if (nz_local) *nz_local = q + (rank < r ? 1 : 0);
+    if (z0) *z0 = rank * q + (rank < r ? rank : r);
+    return O3D_OK;
+}
+
 int o3d_set_sor_order(int order) {
     if (order != O3D_SOR_RED_BLACK && order != O3D_SOR_LEXI_WAVEFRONT) return O3D_ERR_INVALID;
     g_sor_order = order;
@@ -360,9 +368,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
         return O3D_ERR_INVALID;
     }
     // contiguous z slabs, remainder planes to the low ranks
-    const int q = cfg->nz / nr, r = cfg->nz % nr;
-    s->nzl = q + (s->cfg.rank < r ? 1 : 0);
-    s->z0 = s->cfg.rank * q + (s->cfg.rank < r ? s->cfg.rank : r);
+    o3d_slab_partition(cfg->nz, nr, s->cfg.rank, &s->z0, &s->nzl);
     if (nr > 1 && s->nzl < 2 * R) {
         set_error("z slab of %d planes is thinner than two stencil halos", s->nzl);
         delete s;
@@ -379,6 +385,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->partial = nullptr;
     s->partial_n = 0;
     s->comm = nullptr;
+    s->mg = nullptr;
     s->timers_on = 0;
     s->use_src = 0;
     for (int q2 = 0; q2 < 6; ++q2) s->t_ms[q2] = 0.0, s->t_cnt[q2] = 0;
@@ -412,6 +419,7 @@ int o3d_session_destroy(o3d_session* s) {
     if (!s) return O3D_OK;
     if (s->st) cudaStreamSynchronize(s->st);
     comm_destroy(s);
+    mg_destroy(s);
     for (int f = 0; f < O3D_F_COUNT; ++f)
         if (s->base[f]) cudaFree(s->base[f]);
     if (s->partial) cudaFree(s->partial);
@@ -514,6 +522,12 @@ int o3d_get_omega(const o3d_session* s, double* omega) {
 int o3d_set_omega(o3d_session* s, double omega) {
     if (!s) return O3D_ERR_INVALID;
     s->omega = omega;
+    return O3D_OK;
+}
+
+int o3d_session_set_poisson(o3d_session* s, double eps, int kmax, int idyn, int multigrid) {
+    if (!s) return O3D_ERR_INVALID;
+    s->cfg.eps = eps, s->cfg.kmax = kmax, s->cfg.idyn = idyn, s->cfg.multigrid = multigrid;
     return O3D_OK;
 }
 

@@ -134,6 +134,29 @@ int launch_sor_control(cudaStream_t st, SorCtrl* ctrl, double eps, int kmax, int
 // verification ordering: one hyperplane i+j+k = h of the lexicographic sweep
 int launch_sor_wavefront(cudaStream_t st, const SorArgs& a, int h, SorCtrl* ctrl);
 
+// ---- geometric multigrid (mg_kernels.cu; replaces src/poisson_multigrid.f90) ----
+struct MgGrid {
+    int nx, ny, nz;
+    long long sy, sz;     // element strides (level 0: padded field; coarser levels: compact)
+    int mx, my, mz;       // neighbour rule per axis: BM_WRAP | BM_MIRROR
+    double ox, oy, oz;    // 1/d^2 per axis, src/poisson.f90:42-47
+    double A, invA;       // -(2ox + 2oy + 2oz), :48-51
+};
+// 1-D transfer tables between a level and the next coarser one (device pointers, per axis)
+struct MgTables {
+    const int* c0[3];     // [n_fine]   prolongation: lower coarse index
+    const double* w[3];   // [n_fine]   weight of the upper coarse index
+    const int* ridx[3];   // [n_coarse][4] restriction: fine indices
+    const double* rw[3];  // [n_coarse][4] restriction: weights (row sum 1, may be 0)
+};
+int launch_mg_residual(cudaStream_t st, const MgGrid& g, const double* p, const double* rhs,
+                       double* res, unsigned long long* maxbits);
+int launch_mg_restrict(cudaStream_t st, const MgGrid& f, const MgGrid& c, const MgTables& t,
+                       const double* res, double* rhs_c, double* p_c);
+int launch_mg_prolong(cudaStream_t st, const MgGrid& f, const MgGrid& c, const MgTables& t,
+                      const double* e, double* p);
+int launch_mg_coarse(cudaStream_t st, const MgGrid& g, double* p, double* rhs, int sweeps);
+
 // ---- reductions over the interior ----
 enum { RED_MIN = 0, RED_MAX = 1, RED_SUM = 2, RED_ABSMAX = 3, RED_MAXBITS = 10 };
 int reduce_blocks(const Geom& g);

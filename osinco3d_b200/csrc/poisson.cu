@@ -9,7 +9,7 @@
 
 namespace o3d {
 
-static SorArgs make_sor_args(o3d_session* s, double* pp, const double* rhs) {
+SorArgs make_sor_args(o3d_session* s, double* pp, const double* rhs) {
     SorArgs a;
     a.pp = pp;
     a.rhs = rhs;
@@ -139,14 +139,6 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     if (iters) *iters = (h->done == 3 || h->done == 0) ? c.kmax + 1 : h->iter;
     if (dmax) *dmax = h->dmax_last;
     return O3D_OK;
-}
-
-int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npre, int npost,
-             double tol, int* cycles, double* dmax) {
-    (void)s, (void)pp, (void)rhs, (void)nlevels, (void)npre, (void)npost, (void)tol;
-    (void)cycles, (void)dmax;
-    set_error("multigrid V-cycle not built yet");
-    return O3D_ERR_UNSUPPORTED;
 }
 
 }  // namespace o3d

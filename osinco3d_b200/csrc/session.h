@@ -7,6 +7,7 @@
 
 namespace o3d {
 struct Comm;  // z-slab halo exchange + reductions over NCCL (comm.cu)
+struct MgHierarchy;  // level arrays + transfer tables of the V-cycle (multigrid.cu)
 }
 
 struct o3d_session {
@@ -43,6 +44,7 @@ struct o3d_session {
     double* scal_h;        // pinned mirror
 
     o3d::Comm* comm;
+    o3d::MgHierarchy* mg;  // built lazily by mg_solve, cached across steps
     int use_src;           // transeq source term uploaded to O3D_F_SCRATCH1
 
     // timers
@@ -99,6 +101,9 @@ void span_end(o3d_session* s, int stage, long long count);
 int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double* dmax);
 int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npre, int npost,
              double tol, int* cycles, double* dmax);
+void mg_destroy(o3d_session* s);
+// shared with poisson.cu
+SorArgs make_sor_args(o3d_session* s, double* pp, const double* rhs);
 
 // comm.cu
 int comm_create(o3d_session* s);

@@ -148,6 +148,9 @@ class Session:
     def omega(self, v):
         check(lib().o3d_set_omega(self._h, C.c_double(v)))
 
+    def set_poisson(self, eps, kmax, idyn=0, multigrid=0):
+        check(lib().o3d_session_set_poisson(self._h, C.c_double(eps), kmax, idyn, multigrid))
+
     def enable_timers(self, on=True):
         check(lib().o3d_s_enable_timers(self._h, 1 if on else 0))
 
