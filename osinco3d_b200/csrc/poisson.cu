@@ -79,6 +79,13 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     if (wavefront) batch = 1;
     const long long ioff = interior_offset(s->g);
     const int zwrap = (s->sor_variant != 2);  // _0000 / _0011 wrap in z, _111111 mirrors
+    if (fused && multi) {
+        // the fused pass recomputes the red points of the first ghost plane on each side
+        // (bit-identical to the neighbour rank's values), which needs rhs there: constant over
+        // the solve, so one exchange of one plane per side
+        double* rb[1] = {const_cast<double*>(rhs) - ioff};
+        if (comm_exchange(s, rb, 1, 1, zwrap)) return O3D_ERR_COMM;
+    }
     while (true) {
         if (launched + batch > c.kmax) batch = c.kmax - launched;
         if (batch < 1) batch = 1;
