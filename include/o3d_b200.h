@@ -262,7 +262,11 @@ int o3d_s_predict_velocity(o3d_session* s, int itime);
 int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax);
 int o3d_s_correct_velocity(o3d_session* s);
 int o3d_s_transeq(o3d_session* s, int itime);
-/* predict + pression + velocity [+ transeq]; returns O3D_ERR_DIVERGED like the reference */
+/* predict + pression + velocity [+ transeq].  The NaN / >1000 guard of correct_velocity
+ * (src/integration.f90:309-325) does not stall the pipeline here: its flag is examined at the
+ * next host synchronisation, so O3D_ERR_DIVERGED is returned by the FOLLOWING o3d_step (after
+ * its Poisson solve) or by o3d_sync(), whichever comes first.  o3d_s_correct_velocity and the
+ * stateless o3d_correct_velocity report it immediately. */
 int o3d_step(o3d_session* s, int itime, int* iters, double* dmax);
 /* asynchronous variant used by bench.py: enqueue only, no host synchronisation except the
  * SOR convergence polls; call o3d_sync() before reading results */

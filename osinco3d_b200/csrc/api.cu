@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 
 #include "march.cuh"
@@ -86,7 +87,7 @@ double* field(o3d_session* s, int id) {
         }
         s->base[id] = p;
         // an all-zero field has valid ghosts for any closure
-        s->gaxes[id] = 0x7u;
+        s->gaxes[id] = 0xFu;
         s->gpar[id] = natural_parity(id);
     }
     return s->base[id] + interior_offset(s->g);
@@ -112,7 +113,8 @@ void touch(o3d_session* s, int id) {
     if (id >= 0 && id < O3D_F_COUNT) s->gaxes[id] = 0u;
 }
 
-int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, unsigned axes) {
+int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, unsigned axes,
+                  bool defer) {
     GhostArgs a;
     a.njobs = 0;
     double* xbase[6];
@@ -131,12 +133,21 @@ int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, un
             if (!have) need |= bit;
         }
         if (!need) continue;
-        GhostJob& jb = a.job[a.njobs++];
-        jb.p = p, jb.par = par[q], jb.axes = need;
-        if (zhalo && (need & 0x4u)) xbase[nx++] = s->base[id];
-        s->gaxes[id] |= need;
+        unsigned fill = need;
+        if (zhalo && (need & 0x4u)) {
+            xbase[nx++] = s->base[id];
+            // z ghosts on the wall sides were already written by the producer (bit 0x8), or this
+            // rank has no wall side at all: nothing to fill locally along z
+            const bool wall_ok = (s->gaxes[id] & 0x8u) && ((s->gpar[id] & 0x4u) == (par[q] & 0x4u));
+            if (wall_ok || (s->g.bz_lo == BM_HALO && s->g.bz_hi == BM_HALO)) fill &= ~0x4u;
+        }
+        s->gaxes[id] |= need | ((need & 0x4u) ? 0x8u : 0u);
         s->gpar[id] = (s->gpar[id] & ~need) | (par[q] & need);
-        if (a.njobs == 6 || q == n - 1) {
+        if (fill) {
+            GhostJob& jb = a.job[a.njobs++];
+            jb.p = p, jb.par = par[q], jb.axes = fill;
+        }
+        if (a.njobs == 6) {
             if (launch_fill_ghosts(s->st, s->g, a)) {
                 set_error("ghost fill launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return O3D_ERR_CUDA;
@@ -146,14 +157,19 @@ int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, un
     }
     if (a.njobs && launch_fill_ghosts(s->st, s->g, a)) return O3D_ERR_CUDA;
     if (nx) {
-        const int rc = comm_exchange(s, xbase, nx, R, s->cfg.nbcz1 == O3D_PERIODIC);
+        const int wrap = s->cfg.nbcz1 == O3D_PERIODIC;
+        if (defer) {  // the caller overlaps the exchange with its interior launch
+            const int widths[6] = {R, R, R, R, R, R};
+            return comm_exchange_async(s, xbase, widths, nx, wrap);
+        }
+        const int rc = comm_exchange(s, xbase, nx, R, wrap);
         if (rc) return rc;
     }
     return O3D_OK;
 }
 
 // three fields, field q only along axis q (divergence operands): one fused launch
-int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par) {
+int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par, bool defer) {
     GhostArgs a;
     a.njobs = 0;
     double* xbase[1];
@@ -164,19 +180,57 @@ int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par) 
         if (!p) return O3D_ERR_CUDA;
         const unsigned bit = 1u << q;
         if ((s->gaxes[id] & bit) && ((s->gpar[id] & bit) == (par[q] & bit))) continue;
-        GhostJob& jb = a.job[a.njobs++];
-        jb.p = p, jb.par = par[q], jb.axes = bit;
-        s->gaxes[id] |= bit;
+        bool fill = true;
+        if (q == 2 && (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO)) {
+            xbase[nxch++] = s->base[id];
+            const bool wall_ok = (s->gaxes[id] & 0x8u) && ((s->gpar[id] & bit) == (par[q] & bit));
+            if (wall_ok || (s->g.bz_lo == BM_HALO && s->g.bz_hi == BM_HALO)) fill = false;
+        }
+        if (fill) {
+            GhostJob& jb = a.job[a.njobs++];
+            jb.p = p, jb.par = par[q], jb.axes = bit;
+        }
+        s->gaxes[id] |= bit | (q == 2 ? 0x8u : 0u);
         s->gpar[id] = (s->gpar[id] & ~bit) | (par[q] & bit);
-        if (q == 2 && (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO)) xbase[nxch++] = s->base[id];
     }
     if (a.njobs && launch_fill_ghosts(s->st, s->g, a)) return O3D_ERR_CUDA;
-    if (nxch) return comm_exchange(s, xbase, nxch, R, s->cfg.nbcz1 == O3D_PERIODIC);
+    if (nxch) {
+        const int wrap = s->cfg.nbcz1 == O3D_PERIODIC;
+        if (defer) {
+            const int widths[1] = {R};
+            return comm_exchange_async(s, xbase, widths, nxch, wrap);
+        }
+        return comm_exchange(s, xbase, nxch, R, wrap);
+    }
     return O3D_OK;
 }
 
-int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes) {
-    return ensure_ghosts(s, &id, 1, &par, axes);
+int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes, bool defer) {
+    return ensure_ghosts(s, &id, 1, &par, axes, defer);
+}
+
+// Launch a z-marching kernel so that a pending halo exchange overlaps it: the interior planes go
+// to the session stream at once; the two boundary chunks are queued on the COMMUNICATION stream
+// right behind the NCCL exchange, so they start the moment the ghosts have landed and run
+// concurrently with the interior launch; the session stream then joins.  Everything the
+// boundary chunks read must have been enqueued before the exchange was issued.
+// `launch(stream, zmode, zedge)`.
+int launch_overlapped(o3d_session* s, const std::function<int(cudaStream_t, int, int)>& launch) {
+    const int edge = split_edge(s);
+    if (!s->halo_pending || edge == 0) {
+        int rc = comm_wait(s);
+        if (rc) return rc;
+        return launch(s->st, ZFULL, 0) ? O3D_ERR_CUDA : O3D_OK;
+    }
+    trace_mark(s, 0, "interior begin");
+    if (launch(s->st, ZINTERIOR, edge)) return O3D_ERR_CUDA;
+    trace_mark(s, 0, "interior end");
+    if (launch(s->st_comm, ZBOUNDARY, edge)) return O3D_ERR_CUDA;
+    trace_mark(s, 1, "boundary end");
+    O3D_CUDA_CHECK(cudaEventRecord(s->ev_halo, s->st_comm));
+    const int rc = comm_wait(s);
+    trace_mark(s, 0, "joined");
+    return rc;
 }
 
 static const int HIST_BASE[4] = {O3D_F_FUX1, O3D_F_FUY1, O3D_F_FUZ1, O3D_F_FPHI1};
@@ -209,6 +263,30 @@ static cudaEvent_t get_event(o3d_session* s) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     return e;
+}
+
+void trace_mark(o3d_session* s, int comm, const char* name) {
+    if (!s->trace_on) return;
+    o3d_session::Mark m;
+    cudaEventCreate(&m.e);
+    m.name = name, m.comm = comm;
+    cudaEventRecord(m.e, comm ? s->st_comm : s->st);
+    s->marks.push_back(m);
+}
+
+static void trace_dump(o3d_session* s) {
+    cudaStreamSynchronize(s->st);
+    cudaStreamSynchronize(s->st_comm);
+    fprintf(stderr, "[o3d trace] rank %d step %d (us since first mark; C = communication stream)\n",
+            s->cfg.rank, s->step_count);
+    for (auto& m : s->marks) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->marks[0].e, m.e);
+        fprintf(stderr, "[o3d trace] r%d %9.1f %s %s\n", s->cfg.rank, 1e3 * ms, m.comm ? "C" : " ",
+                m.name);
+    }
+    for (auto& m : s->marks) cudaEventDestroy(m.e);
+    s->marks.clear();
 }
 
 void span_begin(o3d_session* s, int stage) {
@@ -245,6 +323,12 @@ static void resolve_spans(o3d_session* s) {
         s->free_events.push_back(sp.a);
     }
     s->pending.clear();
+}
+
+void poll_flag(o3d_session* s) {
+    if (!s->flag_pending) return;
+    s->flag_pending = 0;
+    if (*s->flag_h) s->diverged = 1;
 }
 
 void fill_geom(o3d_session* s) {
@@ -389,12 +473,26 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->timers_on = 0;
     s->use_src = 0;
     for (int q2 = 0; q2 < 6; ++q2) s->t_ms[q2] = 0.0, s->t_cnt[q2] = 0;
-    s->st = nullptr;
+    s->st = nullptr, s->st_comm = nullptr;
+    s->ev_ready = nullptr, s->ev_halo = nullptr;
+    s->halo_pending = 0;
+    s->flag_pending = 0, s->diverged = 0;
+    s->trace_on = 0, s->step_count = 0;
+    s->trace_step = getenv("O3D_TRACE") ? atoi(getenv("O3D_TRACE")) : -1;
     s->sw_a = nullptr, s->sw_b = nullptr;
     s->ctrl_d = nullptr, s->ctrl_h = nullptr, s->flag_d = nullptr, s->flag_h = nullptr;
     s->scal_d = nullptr, s->scal_h = nullptr;
     fill_geom(s);
     cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // highest priority: the exchange and the boundary chunks behind it are dispatched ahead
+        // of the remaining interior CTAs
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&s->st_comm, cudaStreamNonBlocking, hi);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->ctrl_d, sizeof(SorCtrl));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_h, sizeof(SorCtrl), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&s->flag_d, sizeof(int));
@@ -417,6 +515,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
 
 int o3d_session_destroy(o3d_session* s) {
     if (!s) return O3D_OK;
+    if (s->st_comm) cudaStreamSynchronize(s->st_comm);
     if (s->st) cudaStreamSynchronize(s->st);
     comm_destroy(s);
     mg_destroy(s);
@@ -437,6 +536,9 @@ int o3d_session_destroy(o3d_session* s) {
     for (auto e : s->free_events) cudaEventDestroy(e);
     if (s->sw_a) cudaEventDestroy(s->sw_a);
     if (s->sw_b) cudaEventDestroy(s->sw_b);
+    if (s->ev_ready) cudaEventDestroy(s->ev_ready);
+    if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+    if (s->st_comm) cudaStreamDestroy(s->st_comm);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return O3D_OK;
@@ -511,6 +613,12 @@ int o3d_mark_modified(o3d_session* s, int fid) {
 int o3d_sync(o3d_session* s) {
     if (!s) return O3D_ERR_INVALID;
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    poll_flag(s);
+    if (s->diverged) {
+        s->diverged = 0;
+        set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
+        return O3D_ERR_DIVERGED;
+    }
     return O3D_OK;
 }
 
@@ -635,18 +743,22 @@ int o3d_s_predict_velocity(o3d_session* s, int itime) {
     a.csd2 = csd * csd;  // (cs*delta)**2, src/les_turbulence.f90:87
     a.iles = (c.iles == 1);
     // parity table of src/integration.f90:118-165 = natural-parity ghosts of ux, uy, uz
-    if ((rc = ensure_ghosts(s, VEL_IDS, 3, NAT3, 0x7u))) return rc;
+    if ((rc = ensure_ghosts(s, VEL_IDS, 3, NAT3, 0x7u, true))) return rc;
     span_begin(s, ST_RHS);
-    if (launch_rhs(s->st, s->g, a)) {
+    rc = launch_overlapped(
+        s, [&](cudaStream_t q, int zm, int ze) { return launch_rhs(q, s->g, a, zm, ze); });
+    if (rc) {
         set_error("rhs kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return O3D_ERR_CUDA;
+        return rc;
     }
     span_end(s, ST_RHS, 1);
     const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
     for (int k = 0; k < 3; ++k) {
         hist_rotate(s, k, tgt[k]);
         // the RHS kernel wrote the own-axis ghost images of u* (odd closure) with the interior
-        s->gaxes[PRED_IDS[k]] = (k == 2 && zhalo) ? 0u : (1u << k);
+        // (k == 2: z images on the wall sides are in place, bit 0x8; a rank boundary still needs
+        // the exchange)
+        s->gaxes[PRED_IDS[k]] = (k == 2) ? (zhalo ? 0x8u : 0xCu) : (1u << k);
         s->gpar[PRED_IDS[k]] = NAT3[k];
     }
     if (a.iles) touch(s, O3D_F_NU_T);
@@ -668,9 +780,12 @@ int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
     int rc;
     // divergence(..., odd = 1): derxi(ux*), deryi(uy*), derzi(uz*); each field only needs the
     // ghosts of its own axis (src/differential_operators.f90:30-32)
-    if ((rc = ensure_ghosts_own_axis(s, PRED_IDS, NAT3))) return rc;
+    if ((rc = ensure_ghosts_own_axis(s, PRED_IDS, NAT3, true))) return rc;
     span_begin(s, ST_DIV);
-    if (launch_div(s->st, s->g, up, s->cx, s->cy, s->cz, 1, c.dt, rhs)) return O3D_ERR_CUDA;
+    rc = launch_overlapped(s, [&](cudaStream_t q, int zm, int ze) {
+        return launch_div(q, s->g, up, s->cx, s->cy, s->cz, 1, c.dt, rhs, zm, ze);
+    });
+    if (rc) return rc;
     span_end(s, ST_DIV, 1);
     touch(s, O3D_F_RHS);
     if (c.multigrid == 1) {
@@ -684,7 +799,7 @@ int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
     return rc;
 }
 
-int o3d_s_correct_velocity(o3d_session* s) {
+static int correct_velocity_impl(o3d_session* s, bool defer) {
     if (!s) return O3D_ERR_INVALID;
     const o3d_config& c = s->cfg;
     double* up[3] = {field(s, O3D_F_UX_PRED), field(s, O3D_F_UY_PRED), field(s, O3D_F_UZ_PRED)};
@@ -694,28 +809,38 @@ int o3d_s_correct_velocity(o3d_session* s) {
         if (!up[k] || !u[k]) return O3D_ERR_CUDA;
     if (!pp.p) return O3D_ERR_CUDA;
     int rc;
-    if ((rc = ensure_ghosts1(s, O3D_F_PP, 0u, 0x7u))) return rc;  // derxp/deryp/derzp
+    // (before the exchange is issued: the boundary chunks run on the communication stream)
     O3D_CUDA_CHECK(cudaMemsetAsync(s->flag_d, 0, sizeof(int), s->st));
+    if ((rc = ensure_ghosts1(s, O3D_F_PP, 0u, 0x7u, true))) return rc;  // derxp/deryp/derzp
     span_begin(s, ST_CORR);
-    if (launch_corr(s->st, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d))
-        return O3D_ERR_CUDA;
+    rc = launch_overlapped(s, [&](cudaStream_t q, int zm, int ze) {
+        return launch_corr(q, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d, zm, ze);
+    });
+    if (rc) return rc;
     span_end(s, ST_CORR, 1);
     {   // the correction kernel wrote the natural-parity ghost images of u with the interior
         const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
         for (int k = 0; k < 3; ++k) {
-            s->gaxes[VEL_IDS[k]] = zhalo ? 0x3u : 0x7u;
+            s->gaxes[VEL_IDS[k]] = zhalo ? 0xBu : 0xFu;
             s->gpar[VEL_IDS[k]] = NAT3[k];
         }
     }
     O3D_CUDA_CHECK(
         cudaMemcpyAsync(s->flag_h, s->flag_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    if (defer) {
+        s->flag_pending = 1;
+        return O3D_OK;
+    }
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    s->flag_pending = 0;
     if (*s->flag_h) {
         set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
         return O3D_ERR_DIVERGED;
     }
     return O3D_OK;
 }
+
+int o3d_s_correct_velocity(o3d_session* s) { return correct_velocity_impl(s, false); }
 
 int o3d_s_transeq(o3d_session* s, int itime) {
     if (!s) return O3D_ERR_INVALID;
@@ -763,10 +888,24 @@ int o3d_s_transeq(o3d_session* s, int itime) {
 int o3d_step(o3d_session* s, int itime, int* iters, double* dmax) {
     // src/osinco3d_main.f90:105-115
     int rc;
+    s->trace_on = (s->step_count == s->trace_step);
+    trace_mark(s, 0, "step begin");
     if ((rc = o3d_s_predict_velocity(s, itime))) return rc;
+    trace_mark(s, 0, "predict done");
     if ((rc = o3d_s_correct_pression(s, iters, dmax))) return rc;
-    if ((rc = o3d_s_correct_velocity(s))) return rc;
+    trace_mark(s, 0, "pression done");
+    // the guard of the PREVIOUS step's correction was examined at the Poisson solver's host poll
+    if (s->diverged) {
+        s->diverged = 0;
+        set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
+        return O3D_ERR_DIVERGED;
+    }
+    if ((rc = correct_velocity_impl(s, true))) return rc;
+    trace_mark(s, 0, "correct done");
     if (s->cfg.nscr == 1 && (rc = o3d_s_transeq(s, itime))) return rc;
+    if (s->trace_on) trace_dump(s);
+    s->trace_on = 0;
+    s->step_count++;
     return O3D_OK;
 }
 

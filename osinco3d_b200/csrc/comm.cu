@@ -126,32 +126,70 @@ void comm_destroy(o3d_session* s) {
     s->comm = nullptr;
 }
 
-// Ghost-plane exchange of `width` planes per side.  Planes are whole padded planes (px * py
-// doubles, contiguous); `bases` are field allocation starts.  wrap != 0: the slab ring is
-// periodic in z.
-int comm_exchange(o3d_session* s, double* const* bases, int nf, int width, int wrap) {
+// Ghost-plane exchange of widths[f] planes per side of field f.  Planes are whole padded planes
+// (px * py doubles, contiguous); `bases` are field allocation starts.  wrap != 0: the slab ring
+// is periodic in z.  One grouped ncclSend/ncclRecv call on the COMMUNICATION stream, ordered
+// after everything enqueued on the session stream so far.
+int comm_exchange_async(o3d_session* s, double* const* bases, const int* widths, int nf, int wrap) {
     Comm* c = s->comm;
     if (!c) return O3D_OK;
     const int up = (c->rank + 1 < c->nranks) ? c->rank + 1 : (wrap ? 0 : -1);
     const int dn = (c->rank > 0) ? c->rank - 1 : (wrap ? c->nranks - 1 : -1);
     const long long sz = s->g.sz;
-    const size_t cnt = (size_t)width * (size_t)sz;
-    span_begin(s, ST_HALO);
+    O3D_CUDA_CHECK(cudaEventRecord(s->ev_ready, s->st));
+    O3D_CUDA_CHECK(cudaStreamWaitEvent(s->st_comm, s->ev_ready, 0));
+    trace_mark(s, 0, "exchange issued");
+    trace_mark(s, 1, "exchange begin");
     O3D_NCCL_CHECK(g_api.GroupStart());
     for (int f = 0; f < nf; ++f) {
+        const int width = widths[f];
+        const size_t cnt = (size_t)width * (size_t)sz;
         double* b = bases[f];
         double* top_owned = b + sz * (long long)(GH + s->nzl - width);  // last `width` planes
         double* bot_owned = b + sz * (long long)GH;                     // first `width` planes
         double* ghost_lo = b + sz * (long long)(GH - width);
         double* ghost_hi = b + sz * (long long)(GH + s->nzl);
-        if (up >= 0) O3D_NCCL_CHECK(g_api.Send(top_owned, cnt, ncclFloat64_, up, c->nccl, s->st));
-        if (dn >= 0) O3D_NCCL_CHECK(g_api.Recv(ghost_lo, cnt, ncclFloat64_, dn, c->nccl, s->st));
-        if (dn >= 0) O3D_NCCL_CHECK(g_api.Send(bot_owned, cnt, ncclFloat64_, dn, c->nccl, s->st));
-        if (up >= 0) O3D_NCCL_CHECK(g_api.Recv(ghost_hi, cnt, ncclFloat64_, up, c->nccl, s->st));
+        if (up >= 0)
+            O3D_NCCL_CHECK(g_api.Send(top_owned, cnt, ncclFloat64_, up, c->nccl, s->st_comm));
+        if (dn >= 0)
+            O3D_NCCL_CHECK(g_api.Recv(ghost_lo, cnt, ncclFloat64_, dn, c->nccl, s->st_comm));
+        if (dn >= 0)
+            O3D_NCCL_CHECK(g_api.Send(bot_owned, cnt, ncclFloat64_, dn, c->nccl, s->st_comm));
+        if (up >= 0)
+            O3D_NCCL_CHECK(g_api.Recv(ghost_hi, cnt, ncclFloat64_, up, c->nccl, s->st_comm));
     }
     O3D_NCCL_CHECK(g_api.GroupEnd());
-    span_end(s, ST_HALO, 1);
+    trace_mark(s, 1, "exchange end");
+    O3D_CUDA_CHECK(cudaEventRecord(s->ev_halo, s->st_comm));
+    s->halo_pending = 1;
+    s->t_cnt[ST_HALO] += 1;
     return O3D_OK;
+}
+
+int comm_wait(o3d_session* s) {
+    if (!s->comm || !s->halo_pending) return O3D_OK;
+    O3D_CUDA_CHECK(cudaStreamWaitEvent(s->st, s->ev_halo, 0));
+    s->halo_pending = 0;
+    return O3D_OK;
+}
+
+// blocking form (in stream order): exchange, then the session stream waits for the ghosts
+int comm_exchange(o3d_session* s, double* const* bases, int nf, int width, int wrap) {
+    if (!s->comm) return O3D_OK;
+    int widths[8];
+    if (nf > 8) return O3D_ERR_INVALID;
+    for (int f = 0; f < nf; ++f) widths[f] = width;
+    span_begin(s, ST_HALO);
+    int rc = comm_exchange_async(s, bases, widths, nf, wrap);
+    if (!rc) rc = comm_wait(s);
+    span_end(s, ST_HALO, 0);
+    return rc;
+}
+
+int split_edge(const o3d_session* s) {
+    const int EDGE = 8;
+    if (!s->comm || s->nzl < 4 * EDGE) return 0;
+    return EDGE;
 }
 
 int comm_allreduce(o3d_session* s, double* dev, int n, int op) {
@@ -163,7 +201,9 @@ int comm_allreduce(o3d_session* s, double* dev, int n, int op) {
     const int ro = (op == RED_MAXBITS || op == RED_MAX || op == RED_ABSMAX)
                        ? ncclMax_
                        : (op == RED_MIN ? ncclMin_ : ncclSum_);
+    trace_mark(s, 0, "allreduce begin");
     O3D_NCCL_CHECK(g_api.AllReduce(dev, dev, (size_t)n, dt, ro, c->nccl, s->st));
+    trace_mark(s, 0, "allreduce end");
     return O3D_OK;
 }
 

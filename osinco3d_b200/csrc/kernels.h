@@ -57,7 +57,7 @@ struct RhsArgs {
     double onere, adu, bdu, cdu, csd2;
     int iles;
 };
-int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& a);
+int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& a, int zmode = 0, int zedge = 0);
 
 // ---- Smagorinsky nu_t alone (src/les_turbulence.f90:10-97) ----
 int launch_nu_t(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,
@@ -66,13 +66,14 @@ int launch_nu_t(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& c
 // ---- divergence (src/differential_operators.f90:7-38) [/dt -> Poisson rhs,
 //      src/integration.f90:239]; f[0] needs x ghosts, f[1] y ghosts, f[2] z ghosts ----
 int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx, const Coef& cy,
-               const Coef& cz, int divide_by_dt, double dt, double* out);
+               const Coef& cz, int divide_by_dt, double dt, double* out, int zmode = 0,
+               int zedge = 0);
 
 // ---- projection correction (src/integration.f90:257-330) ----
 // flag: device int, OR-ed with 1 when a NaN or a value > 1000 is produced.
 int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const double* const* up,
                 double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
-                int* flag);
+                int* flag, int zmode = 0, int zedge = 0);
 
 // ---- curl and Q criterion (src/differential_operators.f90:40-108) ----
 int launch_rot(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx, const Coef& cy,
@@ -126,8 +127,9 @@ struct SorArgs {
 // one colour class: colour in {0,1}, seam_class in {0,1} (popcount parity of the seam mask)
 int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl);
 // fused red+black iteration (one pass, ping-pong p_old -> p_new); needs a 2-colourable grid
+// zmode / zedge: split launch as for the march kernels (0 = whole slab)
 int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,
-                     SorCtrl* ctrl);
+                     SorCtrl* ctrl, int zmode = 0, int zedge = 0);
 // end-of-iteration control: exits and dynamic omega, src/poisson.f90:110-122
 int launch_sor_control(cudaStream_t st, SorCtrl* ctrl, double eps, int kmax, int idyn,
                        double factor);

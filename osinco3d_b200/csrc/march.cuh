@@ -36,6 +36,10 @@ struct MarchGeom {
     int nx, ny, nz;
     long long sy, sz;
     int zchunk;
+    // z range of this launch.  zmode 0/1: chunks of [zlo, zhi) (1 = interior of a split launch);
+    // zmode 2: the two boundary chunks [0, zedge) and [nz - zedge, nz) of a split launch, which
+    // run after the z-slab halo exchange that the interior launch overlaps
+    int zmode, zlo, zhi, zedge;
     int sim2d;
     int bx, by, bz_lo, bz_hi;  // closures, for epilogues that also write ghost images
 };
@@ -111,8 +115,14 @@ __global__ void __launch_bounds__(MNT, MINB)
     const int tx = tid & (MTX - 1), ty = tid >> 5;
     const int i0 = blockIdx.x * MTX, j0 = blockIdx.y * MTY;
     const int i = i0 + tx, j = j0 + ty;
-    const int kb = blockIdx.z * g.zchunk;
-    const int ke = min(g.nz, kb + g.zchunk);
+    int kb, ke;
+    if (g.zmode == 2) {
+        kb = (blockIdx.z == 0) ? 0 : g.nz - g.zedge;
+        ke = kb + g.zedge;
+    } else {
+        kb = g.zlo + blockIdx.z * g.zchunk;
+        ke = min(g.zhi, kb + g.zchunk);
+    }
     const bool in_dom = (i < g.nx) && (j < g.ny);
 
     const uint32_t zring_s = smem_u32(zring), cring_s = smem_u32(cring);
@@ -186,8 +196,12 @@ __global__ void __launch_bounds__(MNT, MINB)
     epi.finish(tid, zring);
 }
 
+// zmode: ZFULL whole slab | ZINTERIOR planes [zedge, nz - zedge) | ZBOUNDARY the two end chunks
+enum { ZFULL = 0, ZINTERIOR = 1, ZBOUNDARY = 2 };
+
 template <int NFZ, int NFC, int P, class Epi, int MINB>
-int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC>& maps, const Epi& epi) {
+int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC>& maps, const Epi& epi,
+                 int zmode = ZFULL, int zedge = 0) {
     static bool attr_set = false;
     auto kern = march_kernel<NFZ, NFC, P, Epi, MINB>;
     constexpr int smem = march_smem_bytes<NFZ, NFC, P>();
@@ -203,8 +217,19 @@ int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC>& map
     mg.sim2d = g.sim2d;
     mg.bx = g.bx, mg.by = g.by, mg.bz_lo = g.bz_lo, mg.bz_hi = g.bz_hi;
     const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
-    mg.zchunk = pick_zchunk(gx * gy, g.nz);
-    const int gz = (g.nz + mg.zchunk - 1) / mg.zchunk;
+    mg.zmode = zmode, mg.zedge = zedge;
+    mg.zlo = (zmode == ZINTERIOR) ? zedge : 0;
+    mg.zhi = (zmode == ZINTERIOR) ? g.nz - zedge : g.nz;
+    int gz;
+    if (zmode == ZBOUNDARY) {
+        mg.zchunk = zedge;
+        gz = 2;
+    } else {
+        const int span = mg.zhi - mg.zlo;
+        if (span <= 0) return 0;
+        mg.zchunk = pick_zchunk(gx * gy, span);
+        gz = (span + mg.zchunk - 1) / mg.zchunk;
+    }
     kern<<<dim3(gx, gy, gz), dim3(MNT, 1, 1), smem, st>>>(maps, mg, epi);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

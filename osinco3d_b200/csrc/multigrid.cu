@@ -291,6 +291,7 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
         O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h, maxbits, sizeof(double), cudaMemcpyDeviceToHost,
                                        s->st));
         O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+        poll_flag(s);
         last = s->scal_h[0] / absA;
         if (last < tol || cyc >= MG_MAX_CYCLES) break;
         if (cyc >= 2 && last > 0.9 * prev) break;  // stalled at the round-off / compatibility floor

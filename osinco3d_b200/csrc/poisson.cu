@@ -79,13 +79,7 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     if (wavefront) batch = 1;
     const long long ioff = interior_offset(s->g);
     const int zwrap = (s->sor_variant != 2);  // _0000 / _0011 wrap in z, _111111 mirrors
-    if (fused && multi) {
-        // the fused pass recomputes the red points of the first ghost plane on each side
-        // (bit-identical to the neighbour rank's values), which needs rhs there: constant over
-        // the solve, so one exchange of one plane per side
-        double* rb[1] = {const_cast<double*>(rhs) - ioff};
-        if (comm_exchange(s, rb, 1, 1, zwrap)) return O3D_ERR_COMM;
-    }
+    bool rhs_sent = false;
     while (true) {
         if (launched + batch > c.kmax) batch = c.kmax - launched;
         if (batch < 1) batch = 1;
@@ -100,10 +94,22 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                 double* src = (t & 1) ? alt : pp;
                 double* dst = (t & 1) ? pp : alt;
                 if (multi) {
-                    double* bases[1] = {src - ioff};
-                    if (comm_exchange(s, bases, 1, 2, zwrap)) return O3D_ERR_COMM;
+                    // 2 ghost planes of the previous iterate; the first pass also ships the one
+                    // rhs plane per side that the redundant red update of the ghost plane reads
+                    // (constant over the solve).  One grouped NCCL call on the comm stream,
+                    // overlapped with the interior chunks of this pass.
+                    double* bases[2] = {src - ioff, const_cast<double*>(rhs) - ioff};
+                    const int widths[2] = {2, 1};
+                    if (comm_exchange_async(s, bases, widths, rhs_sent ? 1 : 2, zwrap))
+                        return O3D_ERR_COMM;
+                    rhs_sent = true;
+                    const int rc = launch_overlapped(s, [&](cudaStream_t q, int zm, int ze) {
+                        return launch_sor_fused(q, a, src, dst, s->ctrl_d, zm, ze);
+                    });
+                    if (rc) return rc;
+                } else if (launch_sor_fused(s->st, a, src, dst, s->ctrl_d)) {
+                    return O3D_ERR_CUDA;
                 }
-                if (launch_sor_fused(s->st, a, src, dst, s->ctrl_d)) return O3D_ERR_CUDA;
             } else {
                 double* ppf[1] = {pp - ioff};
                 for (int colour = 0; colour < 2; ++colour) {
@@ -126,6 +132,7 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         O3D_CUDA_CHECK(
             cudaMemcpyAsync(h, s->ctrl_d, sizeof(SorCtrl), cudaMemcpyDeviceToHost, s->st));
         O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+        poll_flag(s);
         if (h->done || launched >= c.kmax) break;
         batch = 4;
         if (c.sor_check_every > 0) batch = c.sor_check_every;

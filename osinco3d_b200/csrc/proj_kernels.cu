@@ -105,7 +105,7 @@ struct CorrEpi {
 }  // namespace
 
 int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx, const Coef& cy,
-               const Coef& cz, int divide_by_dt, double dt, double* out) {
+               const Coef& cz, int divide_by_dt, double dt, double* out, int zmode, int zedge) {
     DivEpi e;
     e.out = out;
     e.cx = cx, e.cy = cy, e.cz = cz;
@@ -114,19 +114,19 @@ int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx
     m.m[0] = *f[2].tm;  // z-window field first
     m.m[1] = *f[0].tm;
     m.m[2] = *f[1].tm;
-    return launch_march<1, 2, 2, DivEpi, 3>(st, g, m, e);
+    return launch_march<1, 2, 2, DivEpi, 3>(st, g, m, e, zmode, zedge);
 }
 
 int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const double* const* up,
                 double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
-                int* flag) {
+                int* flag, int zmode, int zedge) {
     CorrEpi e;
     for (int c = 0; c < 3; ++c) e.up[c] = up[c], e.u[c] = u[c];
     e.cx = cx, e.cy = cy, e.cz = cz;
     e.dt = dt, e.flag = flag, e.sim2d = g.sim2d, e.bad = 0;
     MarchMaps<1> m;
     m.m[0] = *pp.tm;
-    return launch_march<1, 0, 1, CorrEpi, 3>(st, g, m, e);
+    return launch_march<1, 0, 1, CorrEpi, 3>(st, g, m, e, zmode, zedge);
 }
 
 }  // namespace o3d

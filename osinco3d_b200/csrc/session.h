@@ -1,5 +1,6 @@
 // session.h -- internal definition of o3d_session (device-resident state of one rank).
 #pragma once
+#include <functional>
 #include <vector>
 
 #include "../../include/o3d_b200.h"
@@ -17,6 +18,11 @@ struct o3d_session {
     long long nloc;        // interior points of this rank: nx*ny*nzl
     long long felems;      // doubles per padded field allocation
     cudaStream_t st;
+    // halo exchanges run on their own stream so that they overlap interior compute: ev_ready is
+    // recorded on st when the planes to send are final, ev_halo on st_comm when ghosts arrived
+    cudaStream_t st_comm;
+    cudaEvent_t ev_ready, ev_halo;
+    int halo_pending;      // an exchange is in flight: comm_wait() before reading z ghosts
     o3d::Coef cx, cy, cz;
 
     // padded fields; history levels are logical views onto three physical buffers
@@ -38,6 +44,9 @@ struct o3d_session {
 
     int* flag_d;
     int* flag_h;           // pinned
+    // o3d_step does not stall on the NaN / >1000 guard of correct_velocity: the flag copy is left
+    // in flight and examined at the next host synchronisation (poll_flag)
+    int flag_pending, diverged;
     double* partial;       // reduction scratch
     long long partial_n;
     double* scal_d;        // 64 device doubles
@@ -55,6 +64,10 @@ struct o3d_session {
     double t_ms[6];
     long long t_cnt[6];
     cudaEvent_t sw_a, sw_b;  // stopwatch
+    // O3D_TRACE=<step>: event timeline of one o3d_step across both streams, printed to stderr
+    int trace_step, trace_on, step_count;
+    struct Mark { cudaEvent_t e; const char* name; int comm; };
+    std::vector<Mark> marks;
 };
 
 namespace o3d {
@@ -88,12 +101,18 @@ unsigned natural_parity(int id);
 void touch(o3d_session* s, int id);
 // make the ghost cells of `n` fields valid on the axes in `axes` with parity `par[q]`
 // (one fused launch + z-slab halo exchange where the z neighbour is another rank)
-int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, unsigned axes);
-int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes);
-int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par);
+int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, unsigned axes,
+                  bool defer = false);
+int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes, bool defer = false);
+int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par,
+                           bool defer = false);
 int ensure_partial(o3d_session* s, long long n);
 void fill_geom(o3d_session* s);
+// call right after a synchronisation of the session stream
+void poll_flag(o3d_session* s);
 
+// timeline mark on the session stream (comm = 0) or the communication stream (comm = 1)
+void trace_mark(o3d_session* s, int comm, const char* name);
 void span_begin(o3d_session* s, int stage);
 void span_end(o3d_session* s, int stage, long long count);
 
@@ -111,6 +130,14 @@ void comm_destroy(o3d_session* s);
 // exchange `width` ghost planes per side of `nf` fields given by their ALLOCATION BASE
 // (no-op when nranks == 1); wrap: the slab ring is periodic in z
 int comm_exchange(o3d_session* s, double* const* bases, int nf, int width, int wrap);
+// same, on the communication stream, per-field widths; returns immediately.  comm_wait() makes the
+// session stream wait for the ghosts (call it before the first kernel that reads z ghost planes)
+int comm_exchange_async(o3d_session* s, double* const* bases, const int* widths, int nf, int wrap);
+int comm_wait(o3d_session* s);
+// planes at each end of a slab that the boundary launches of a split kernel cover (0: the slab
+// is too thin or single-rank -> no split, blocking exchange)
+int split_edge(const o3d_session* s);
+int launch_overlapped(o3d_session* s, const std::function<int(cudaStream_t, int, int)>& launch);
 int comm_allreduce(o3d_session* s, double* dev, int n, int op /* RED_* */);
 int nccl_unique_id(unsigned char* out128);
 

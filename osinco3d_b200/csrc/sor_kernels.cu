@@ -159,6 +159,7 @@ struct FusedArgs {
     long long sy, sz;
     int gz0;
     int zchunk;
+    int zmode, zlo, zhi, zedge;  // split launch, as MarchGeom
 };
 
 __device__ __forceinline__ int fmap(int q, int n, int mlo, int mhi) {
@@ -179,7 +180,14 @@ __global__ void __launch_bounds__(FNT, 3) sor_fused_kernel(const FusedArgs a, So
     const int tid = threadIdx.x;
     const int px = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.x * FTX, j0 = blockIdx.y * FTY;
-    const int kb = blockIdx.z * a.zchunk, ke = min(a.nz, kb + a.zchunk);
+    int kb, ke;
+    if (a.zmode == 2) {
+        kb = (blockIdx.z == 0) ? 0 : a.nz - a.zedge;
+        ke = kb + a.zedge;
+    } else {
+        kb = a.zlo + blockIdx.z * a.zchunk;
+        ke = min(a.zhi, kb + a.zchunk);
+    }
 
     // loader slots: global in-plane offset and shared index of the staged cells this thread
     // fetches (index map of src/poisson.f90:57-92 applied once, outside the march)
@@ -408,7 +416,7 @@ int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class,
 }
 
 int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,
-                     SorCtrl* ctrl) {
+                     SorCtrl* ctrl, int zmode, int zedge) {
     FusedArgs f;
     f.p_old = p_old, f.p_new = p_new, f.rhs = a.rhs;
     f.ox = a.oneondx2, f.oy = a.oneondy2, f.oz = a.oneondz2, f.invA = a.invA;
@@ -417,15 +425,27 @@ int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, dou
     f.sy = a.sy, f.sz = a.sz;
     f.gz0 = a.gz0;
     const int gx = (a.nx + FTX - 1) / FTX, gy = (a.ny + FTY - 1) / FTY;
-    // 4 extra planes per chunk: keep chunks long
-    const int target = 148 * 6;
-    int nch = (target + gx * gy - 1) / (gx * gy);
-    int maxch = a.nz / 48;
-    if (maxch < 1) maxch = 1;
-    if (nch > maxch) nch = maxch;
-    if (nch < 1) nch = 1;
-    f.zchunk = (a.nz + nch - 1) / nch;
-    sor_fused_kernel<<<dim3(gx, gy, (a.nz + f.zchunk - 1) / f.zchunk), FNT, 0, st>>>(f, ctrl);
+    f.zmode = zmode, f.zedge = zedge;
+    f.zlo = (zmode == 1) ? zedge : 0;
+    f.zhi = (zmode == 1) ? a.nz - zedge : a.nz;
+    int gz;
+    if (zmode == 2) {
+        f.zchunk = zedge;
+        gz = 2;
+    } else {
+        const int span = f.zhi - f.zlo;
+        if (span <= 0) return 0;
+        // 4 extra planes per chunk: keep chunks long
+        const int target = 148 * 6;
+        int nch = (target + gx * gy - 1) / (gx * gy);
+        int maxch = span / 48;
+        if (maxch < 1) maxch = 1;
+        if (nch > maxch) nch = maxch;
+        if (nch < 1) nch = 1;
+        f.zchunk = (span + nch - 1) / nch;
+        gz = (span + f.zchunk - 1) / f.zchunk;
+    }
+    sor_fused_kernel<<<dim3(gx, gy, gz), FNT, 0, st>>>(f, ctrl);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

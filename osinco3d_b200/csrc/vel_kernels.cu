@@ -244,7 +244,7 @@ Coefs3 coefs(const Coef& cx, const Coef& cy, const Coef& cz) {
 
 }  // namespace
 
-int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r) {
+int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int zedge) {
     RhsEpi e;
     for (int c = 0; c < 3; ++c)
         e.f2[c] = r.f2[c], e.f3[c] = r.f3[c], e.f1[c] = r.f1[c], e.up[c] = r.up[c];
@@ -252,7 +252,7 @@ int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r) {
     e.q = coefs(r.cx, r.cy, r.cz);
     e.onere = r.onere, e.adu = r.adu, e.bdu = r.bdu, e.cdu = r.cdu, e.csd2 = r.csd2;
     e.iles = r.iles, e.sim2d = g.sim2d;
-    return launch_march<3, 0, 1, RhsEpi, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e);
+    return launch_march<3, 0, 1, RhsEpi, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e, zmode, zedge);
 }
 
 int launch_nu_t(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,

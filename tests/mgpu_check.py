@@ -73,6 +73,11 @@ def main():
         ("periodic_even_fusedSOR", 32, 16 * world, (0, 0, 0), 0, 1, 1e-7, 0, 3),
         ("periodic_odd_seamSOR", 33, 16 * world + 1, (0, 0, 0), 1, 0, 1e-6, 0, 3),
         ("mixed_0011_ragged", 33, 16 * world + 3, (0, 1, 0), 0, 1, 1e-6, 1, 3),
+        # slabs of >= 32 planes: kernels are split into interior + boundary launches and the halo
+        # exchange runs on the communication stream underneath the interior launch
+        ("freeslip_overlap_les_scalar", 40, 40 * world + 1, (1, 1, 1), 1, 1, 1e-6, 1, 4),
+        ("periodic_overlap_fusedSOR", 32, 36 * world, (0, 0, 0), 0, 0, 1e-7, 0, 3),
+        ("mixed_0011_overlap_seamSOR", 33, 34 * world + 1, (0, 1, 0), 0, 0, 1e-6, 0, 3),
     ]
     for name, n, nz, bc, iles, nscr, eps, idyn, steps in cases:
         L = np.pi if bc[0] == 1 else 2 * np.pi
