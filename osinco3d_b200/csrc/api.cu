@@ -86,8 +86,9 @@ double* field(o3d_session* s, int id) {
             return nullptr;
         }
         s->base[id] = p;
+        s->tmap_sor_ok[id] = 0;
         // an all-zero field has valid ghosts for any closure
-        s->gaxes[id] = 0xFu;
+        s->gaxes[id] = 0x1Fu;
         s->gpar[id] = natural_parity(id);
     }
     return s->base[id] + interior_offset(s->g);
@@ -203,6 +204,30 @@ int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par, 
         return comm_exchange(s, xbase, nxch, R, wrap);
     }
     return O3D_OK;
+}
+
+int ensure_local_ghosts(o3d_session* s, int id, unsigned par, bool edges) {
+    double* p = field(s, id);
+    if (!p) return O3D_ERR_CUDA;
+    const unsigned want = 0x1u | 0x2u | 0x8u | (edges ? 0x10u : 0u);
+    const bool par_ok = ((s->gpar[id] ^ par) & 0x7u) == 0;
+    if ((s->gaxes[id] & want) == want && par_ok) return O3D_OK;
+    if (launch_fill_ghosts_full(s->st, s->g, p, par)) return O3D_ERR_CUDA;
+    const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+    s->gaxes[id] = 0x1u | 0x2u | 0x8u | 0x10u | (zhalo ? 0u : 0x4u);
+    s->gpar[id] = par & 0x7u;
+    return O3D_OK;
+}
+
+const CUtensorMap* sor_tmap(o3d_session* s, int id) {
+    if (!field(s, id)) return nullptr;
+    if (!s->tmap_sor_ok[id]) {
+        if (make_field_tmap(&s->tmap_sor[id], s->base[id], s->g.px, s->g.py, s->g.nz + 2 * GH,
+                            sor_tma_box_x(), sor_tma_box_y()))
+            return nullptr;
+        s->tmap_sor_ok[id] = 1;
+    }
+    return &s->tmap_sor[id];
 }
 
 int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes, bool defer) {
@@ -459,7 +484,8 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
         return O3D_ERR_INVALID;
     }
     s->nloc = (long long)cfg->nx * cfg->ny * s->nzl;
-    for (int f = 0; f < O3D_F_COUNT; ++f) s->base[f] = nullptr, s->gaxes[f] = 0, s->gpar[f] = 0;
+    for (int f = 0; f < O3D_F_COUNT; ++f)
+        s->base[f] = nullptr, s->gaxes[f] = 0, s->gpar[f] = 0, s->tmap_sor_ok[f] = 0;
     s->stage_d = nullptr;
     for (int c = 0; c < 4; ++c)
         for (int l = 0; l < 3; ++l) s->lv[c][l] = l;
@@ -787,7 +813,11 @@ int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
     });
     if (rc) return rc;
     span_end(s, ST_DIV, 1);
-    touch(s, O3D_F_RHS);
+    {   // the divergence kernel wrote the even ghost images of rhs with the interior
+        const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+        s->gaxes[O3D_F_RHS] = zhalo ? 0xBu : 0xFu;
+        s->gpar[O3D_F_RHS] = 0u;
+    }
     if (c.multigrid == 1) {
         int cycles = 0;
         rc = mg_solve(s, pp, rhs, c.kmax, 5, 4, c.eps, &cycles, dmax);  // src/integration.f90:244
@@ -795,8 +825,7 @@ int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
     } else {
         rc = sor_solve(s, pp, rhs, iters, dmax);
     }
-    touch(s, O3D_F_PP);
-    return rc;
+    return rc;  // the solvers record the ghost state of pp themselves
 }
 
 static int correct_velocity_impl(o3d_session* s, bool defer) {
@@ -922,7 +951,11 @@ int o3d_s_divergence(o3d_session* s, int fx, int fy, int fz, int dst, int odd) {
     const unsigned dpar[3] = {odd ? 0x1u : 0u, odd ? 0x2u : 0u, odd ? 0x4u : 0u};
     if ((rc = ensure_ghosts_own_axis(s, ids, dpar))) return rc;
     if (launch_div(s->st, s->g, f, s->cx, s->cy, s->cz, 0, 1.0, out)) return O3D_ERR_CUDA;
-    touch(s, out_id);
+    {
+        const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+        s->gaxes[out_id] = zhalo ? 0xBu : 0xFu;
+        s->gpar[out_id] = 0u;
+    }
     return O3D_OK;
 }
 

@@ -50,6 +50,44 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const Geom g, const Gh
     }
 }
 
+// One axis of the FULL closure (faces, edges, corners): the ghost cells of `axis` over the other
+// two extents widened by `ea` / `eb` ghost cells, so that x, then y (over the x ghosts), then z
+// (over the x and y ghosts) produces the images of images the SOR kernel's halo reads.
+__global__ void __launch_bounds__(256) fill_axis_kernel(const Geom g, double* __restrict__ p,
+                                                        int axis, int odd, int ea, int eb) {
+    const int n = (axis == 0) ? g.nx : (axis == 1) ? g.ny : g.nz;
+    const long long s = (axis == 0) ? 1 : (axis == 1) ? g.sy : g.sz;
+    const int mlo = (axis == 0) ? g.bx : (axis == 1) ? g.by : g.bz_lo;
+    const int mhi = (axis == 0) ? g.bx : (axis == 1) ? g.by : g.bz_hi;
+    const int na = ((axis == 0) ? g.ny : g.nx) + 2 * ea;
+    const int nb = ((axis == 2) ? g.ny : g.nz) + 2 * eb;
+    const long long sa = (axis == 0) ? g.sy : 1;
+    const long long sb = (axis == 2) ? g.sy : g.sz;
+    const long long total = (long long)na * nb * 6;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int ia, ib, g6;
+        if (axis == 0) {
+            g6 = (int)(t % 6);
+            const long long row = t / 6;
+            ia = (int)(row % na), ib = (int)(row / na);
+        } else {
+            ia = (int)(t % na);
+            const long long rest = t / na;
+            g6 = (int)(rest % 6), ib = (int)(rest / 6);
+        }
+        const int side = g6 / 3, gg = g6 % 3 + 1;
+        const int mode = side ? mhi : mlo;
+        if (mode == BM_HALO) continue;
+        const int q = side ? (n - 1 + gg) : -gg;
+        bool refl;
+        const int src = map_index(q, n, mlo, mhi, refl);
+        const long long base = (long long)(ia - ea) * sa + (long long)(ib - eb) * sb;
+        const double v = p[base + (long long)src * s];
+        p[base + (long long)q * s] = (refl && odd) ? -v : v;
+    }
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const Geom g, const double* __restrict__ src,
                                                     double* __restrict__ dst, int to_padded) {
     const long long rows = (long long)g.ny * g.nz;
@@ -74,6 +112,21 @@ int launch_fill_ghosts(cudaStream_t st, const Geom& g, const GhostArgs& a) {
     if (b < 1) b = 1;
     fill_ghosts_kernel<<<dim3((unsigned)b, 1, 3 * a.njobs), 256, 0, st>>>(g, a);
     count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_fill_ghosts_full(cudaStream_t st, const Geom& g, double* p, unsigned par) {
+    for (int axis = 0; axis < 3; ++axis) {
+        const int ea = (axis == 0) ? 0 : R;               // x ghosts exist once axis 0 is done
+        const int eb = (axis == 2) ? R : 0;               // y ghosts exist once axis 1 is done
+        const long long na = ((axis == 0) ? g.ny : g.nx) + 2 * ea;
+        const long long nb = ((axis == 2) ? g.ny : g.nz) + 2 * eb;
+        long long b = (na * nb * 6 + 255) / 256;
+        if (b > 148 * 8) b = 148 * 8;
+        if (b < 1) b = 1;
+        fill_axis_kernel<<<(unsigned)b, 256, 0, st>>>(g, p, axis, (par >> axis) & 1u, ea, eb);
+        count_launch();
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -37,6 +37,8 @@ struct GhostArgs {
     int njobs;
 };
 int launch_fill_ghosts(cudaStream_t st, const Geom& g, const GhostArgs& a);
+// faces + edges + corners, axis by axis (x, then y over the x ghosts, then z over both)
+int launch_fill_ghosts_full(cudaStream_t st, const Geom& g, double* p, unsigned par);
 int launch_pack(cudaStream_t st, const Geom& g, const double* contiguous, double* padded);
 int launch_unpack(cudaStream_t st, const Geom& g, const double* padded, double* contiguous);
 
@@ -130,6 +132,14 @@ int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class,
 // zmode / zedge: split launch as for the march kernels (0 = whole slab)
 int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,
                      SorCtrl* ctrl, int zmode = 0, int zedge = 0);
+// TMA-staged fused red+black iteration (sor_tma_kernel.cu): p_old and rhs are read through
+// tensor maps with sor_tma_box_x() x sor_tma_box_y() x 1 boxes and must carry valid ghost cells
+// (p_old: faces + edges, 2 deep; rhs: faces, 1 deep); p_new is written with its ghost images
+int sor_tma_box_x();
+int sor_tma_box_y();
+int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_map,
+                   const CUtensorMap* rhs_map, double* p_new, int bx, int by, int bz_lo,
+                   int bz_hi, SorCtrl* ctrl, int zmode = 0, int zedge = 0);
 // end-of-iteration control: exits and dynamic omega, src/poisson.f90:110-122
 int launch_sor_control(cudaStream_t st, SorCtrl* ctrl, double eps, int kmax, int idyn,
                        double factor);

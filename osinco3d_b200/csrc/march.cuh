@@ -175,12 +175,12 @@ __global__ void __launch_bounds__(MNT, MINB)
     const int cell = (ty + R) * MBX + tx + MXO;
 
     for (int k = kb; k < ke; ++k) {
-        const int it = k - kb;
+        const unsigned it = (unsigned)(k - kb);  // unsigned: ring indices compile to AND / cheap MOD
         // streamed operands of the next plane
         typename Epi::Pre nxt = epi.prefetch(m0 + (long long)(k + 1) * g.sz, in_dom && (k + 1 < ke));
         // every thread is done with plane k-1: its stages can be refilled with group it+P
         __syncthreads();
-        if (tid == 0 && it + P < niter) issue_group(it + P);
+        if (tid == 0 && (int)it + P < niter) issue_group((int)it + P);
         // group `it` has landed?
         mbar_wait(bars_s + 8 * (it % NB), (it / NB) & 1);
         if (in_dom) {
@@ -231,6 +231,139 @@ int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC>& map
         gz = (span + mg.zchunk - 1) / mg.zchunk;
     }
     kern<<<dim3(gx, gy, gz), dim3(MNT, 1, 1), smem, st>>>(maps, mg, epi);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Role-split variant of the engine: NROLE threads per grid point (blockDim = MNT * NROLE), each
+// role running the SAME code on its own z-field (role r differentiates field r).  Used by the
+// RHS kernel with one role per velocity component: a third of the work and of the live FP64
+// state per thread, so 24 warps/SM are resident at <= 85 registers instead of 16 at 128, and
+// the FP64 / shared-memory latency chains per plane are three times shorter.
+//
+// Epilogue concept (all threads call apply(); it may contain block-wide barriers):
+//   void setup(const MarchGeom&, int i, int j, int role);
+//   struct Pre;  Pre prefetch(long long m, bool ok) const;
+//   void apply(const Ring<NFZ,0>&, long long m, int k, const Pre&, bool ok, int pt, double* xch);
+// xch = NROLE * 3 * MNT doubles of shared scratch for exchanges between the roles.
+template <int NFZ, int P, int NROLE, class Epi>
+__global__ void __launch_bounds__(MNT* NROLE, 1)
+    march_roles_kernel(const __grid_constant__ MarchMaps<NFZ> maps, const MarchGeom g, Epi epi) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NZS = 7 + P, NB = P + 1;
+    constexpr int ZSTAGE = NFZ * MFIELD;  // doubles
+    double* zring = reinterpret_cast<double*>(smem_raw);
+    double* xch = zring + NZS * ZSTAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + NROLE * 3 * MNT);
+    constexpr uint32_t PLANE_BYTES = MFIELD * 8;
+
+    const int tid = threadIdx.x;
+    const int pt = tid & (MNT - 1), role = tid / MNT;
+    const int tx = pt & (MTX - 1), ty = pt >> 5;
+    const int i0 = blockIdx.x * MTX, j0 = blockIdx.y * MTY;
+    const int i = i0 + tx, j = j0 + ty;
+    int kb, ke;
+    if (g.zmode == 2) {
+        kb = (blockIdx.z == 0) ? 0 : g.nz - g.zedge;
+        ke = kb + g.zedge;
+    } else {
+        kb = g.zlo + blockIdx.z * g.zchunk;
+        ke = min(g.zhi, kb + g.zchunk);
+    }
+    const bool in_dom = (i < g.nx) && (j < g.ny);
+
+    const uint32_t zring_s = smem_u32(zring), bars_s = smem_u32(bars);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NB; ++s) mbar_init(bars_s + 8 * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int cx = GX + i0 - MXO, cy = GH + j0 - R;
+    auto issue_z = [&](int plane, uint32_t bar) {
+        const int st = (plane - (kb - R)) % NZS;
+#pragma unroll
+        for (int f = 0; f < NFZ; ++f)
+            tma_load_3d(zring_s + (uint32_t)(st * ZSTAGE + f * MFIELD) * 8, &maps.m[f], bar, cx, cy,
+                        GH + plane);
+    };
+    const int niter = ke - kb;
+    auto issue_group = [&](int n) {
+        const uint32_t bar = bars_s + 8 * (n % NB);
+        const int nz_planes = (n == 0) ? 7 : 1;
+        mbar_expect_tx(bar, (uint32_t)(nz_planes * NFZ) * PLANE_BYTES);
+        if (n == 0) {
+#pragma unroll
+            for (int s = 0; s < 6; ++s) issue_z(kb - R + s, bar);
+        }
+        issue_z(kb + n + R, bar);
+    };
+    if (tid == 0) {
+        for (int n = 0; n < P && n < niter; ++n) issue_group(n);
+    }
+
+    const long long m0 = (long long)j * g.sy + i;
+    epi.setup(g, i, j, role);
+    typename Epi::Pre cur = epi.prefetch(m0 + (long long)kb * g.sz, in_dom);
+    const int cell = (ty + R) * MBX + tx + MXO;
+
+    for (int k = kb; k < ke; ++k) {
+        const unsigned it = (unsigned)(k - kb);
+        typename Epi::Pre nxt = epi.prefetch(m0 + (long long)(k + 1) * g.sz, in_dom && (k + 1 < ke));
+        __syncthreads();
+        if (tid == 0 && (int)it + P < niter) issue_group((int)it + P);
+        mbar_wait(bars_s + 8 * (it % NB), (it / NB) & 1);
+        Ring<NFZ, 0> r;
+#pragma unroll
+        for (int m = 0; m < 7; ++m) r.p[m] = zring + ((it + m) % NZS) * ZSTAGE + cell;
+        r.q = nullptr;
+        epi.apply(r, m0 + (long long)k * g.sz, k, cur, in_dom, pt, xch);
+        cur = nxt;
+    }
+}
+
+template <int NFZ, int P, int NROLE, class Epi>
+int launch_march_roles(cudaStream_t st, const Geom& g, const MarchMaps<NFZ>& maps, const Epi& epi,
+                       int zmode = ZFULL, int zedge = 0) {
+    static bool attr_set = false;
+    auto kern = march_roles_kernel<NFZ, P, NROLE, Epi>;
+    constexpr int smem = NFZ * (7 + P) * MFIELD * 8 + NROLE * 3 * MNT * 8 + (P + 1) * 8;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+            return 1;
+        attr_set = true;
+    }
+    MarchGeom mg;
+    mg.nx = g.nx, mg.ny = g.ny, mg.nz = g.nz;
+    mg.sy = g.sy, mg.sz = g.sz;
+    mg.sim2d = g.sim2d;
+    mg.bx = g.bx, mg.by = g.by, mg.bz_lo = g.bz_lo, mg.bz_hi = g.bz_hi;
+    const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
+    mg.zmode = zmode, mg.zedge = zedge;
+    mg.zlo = (zmode == ZINTERIOR) ? zedge : 0;
+    mg.zhi = (zmode == ZINTERIOR) ? g.nz - zedge : g.nz;
+    int gz;
+    if (zmode == ZBOUNDARY) {
+        mg.zchunk = zedge;
+        gz = 2;
+    } else {
+        const int span = mg.zhi - mg.zlo;
+        if (span <= 0) return 0;
+        // one CTA per SM: several waves of 148, chunks of >= 32 planes
+        const int target_ctas = 148 * 6;
+        int nchunks = (target_ctas + gx * gy - 1) / (gx * gy);
+        int max_chunks = span / 32;
+        if (max_chunks < 1) max_chunks = 1;
+        if (nchunks > max_chunks) nchunks = max_chunks;
+        if (nchunks < 1) nchunks = 1;
+        mg.zchunk = (span + nchunks - 1) / nchunks;
+        gz = (span + mg.zchunk - 1) / mg.zchunk;
+    }
+    kern<<<dim3(gx, gy, gz), dim3(MNT * NROLE, 1, 1), smem, st>>>(maps, mg, epi);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

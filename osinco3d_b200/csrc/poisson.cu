@@ -3,6 +3,8 @@
 //               path or lexicographic-wavefront verification ordering; exit tests and dynamic
 //               omega (src/poisson.f90:110-122) evaluated on the device.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <utility>
 
 #include "session.h"
@@ -64,12 +66,43 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     O3D_CUDA_CHECK(cudaMemcpyAsync(s->ctrl_d, h, sizeof(SorCtrl), cudaMemcpyHostToDevice, s->st));
     const bool seams = a.seam_x || a.seam_y || a.seam_z;
     const bool wavefront = (c.sor_order == O3D_SOR_LEXI_WAVEFRONT);
-    // fast path: fused red+black pass with ping-pong buffers (needs a 2-colourable grid)
+    // fast path: fused red+black pass with ping-pong buffers (needs a 2-colourable grid).
+    // O3D_SOR_FUSED=legacy selects the first-generation kernel (index maps, register staging).
     const bool fused = !wavefront && !seams;
+    static const bool legacy = getenv("O3D_SOR_FUSED") && !strcmp(getenv("O3D_SOR_FUSED"), "legacy");
+    const bool tma = fused && !legacy;
     double* alt = nullptr;
     if (fused) {
         alt = field(s, O3D_F_PP2);
         if (!alt) return O3D_ERR_CUDA;
+    }
+    int id_pp = -1, id_rhs = -1;
+    bool same_bc = false;
+    if (tma) {
+        // the TMA kernel reads the boundary rule from ghost cells: which session fields are these?
+        for (int f = 0; f < O3D_F_COUNT; ++f) {
+            if (s->base[f] && s->base[f] + interior_offset(s->g) == pp) id_pp = f;
+            if (s->base[f] && s->base[f] + interior_offset(s->g) == rhs) id_rhs = f;
+        }
+        if (id_pp < 0 || id_rhs < 0) return O3D_ERR_INVALID;
+        if (!sor_tmap(s, id_pp) || !sor_tmap(s, O3D_F_PP2) || !sor_tmap(s, id_rhs))
+            return O3D_ERR_CUDA;
+        // ghost cells = the solver variant's neighbour rule (it may differ from the session's
+        // derivative closures when a stateless poisson_solver_xxxx call names another variant)
+        same_bc = (a.mx == s->g.bx && a.my == s->g.by && a.mz_lo == s->g.bz_lo &&
+                   a.mz_hi == s->g.bz_hi);
+        if (same_bc) {
+            int rc;
+            if ((rc = ensure_local_ghosts(s, id_pp, 0u, true))) return rc;
+            if ((rc = ensure_local_ghosts(s, id_rhs, 0u, false))) return rc;
+        } else {
+            Geom gs = s->g;
+            gs.bx = a.mx, gs.by = a.my, gs.bz_lo = a.mz_lo, gs.bz_hi = a.mz_hi;
+            if (launch_fill_ghosts_full(s->st, gs, pp, 0u)) return O3D_ERR_CUDA;
+            if (launch_fill_ghosts_full(s->st, gs, const_cast<double*>(rhs), 0u))
+                return O3D_ERR_CUDA;
+            touch(s, id_pp), touch(s, id_rhs);
+        }
     }
     const double factor = sor_factor(s);
     int launched = 0;
@@ -93,6 +126,13 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                 const int t = launched + b;  // iteration t reads src, writes dst
                 double* src = (t & 1) ? alt : pp;
                 double* dst = (t & 1) ? pp : alt;
+                const int id_src = (t & 1) ? O3D_F_PP2 : id_pp;
+                auto pass = [&](cudaStream_t q, int zm, int ze) {
+                    if (tma)
+                        return launch_sor_tma(q, a, sor_tmap(s, id_src), sor_tmap(s, id_rhs), dst,
+                                              a.mx, a.my, a.mz_lo, a.mz_hi, s->ctrl_d, zm, ze);
+                    return launch_sor_fused(q, a, src, dst, s->ctrl_d, zm, ze);
+                };
                 if (multi) {
                     // 2 ghost planes of the previous iterate; the first pass also ships the one
                     // rhs plane per side that the redundant red update of the ghost plane reads
@@ -103,11 +143,9 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                     if (comm_exchange_async(s, bases, widths, rhs_sent ? 1 : 2, zwrap))
                         return O3D_ERR_COMM;
                     rhs_sent = true;
-                    const int rc = launch_overlapped(s, [&](cudaStream_t q, int zm, int ze) {
-                        return launch_sor_fused(q, a, src, dst, s->ctrl_d, zm, ze);
-                    });
+                    const int rc = launch_overlapped(s, pass);
                     if (rc) return rc;
-                } else if (launch_sor_fused(s->st, a, src, dst, s->ctrl_d)) {
+                } else if (pass(s->st, 0, 0)) {
                     return O3D_ERR_CUDA;
                 }
             } else {
@@ -143,9 +181,18 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         // two physical fields (O(1), no copy)
         std::swap(s->base[O3D_F_PP], s->base[O3D_F_PP2]);
         std::swap(s->tmap[O3D_F_PP], s->tmap[O3D_F_PP2]);
+        std::swap(s->tmap_sor[O3D_F_PP], s->tmap_sor[O3D_F_PP2]);
+        std::swap(s->tmap_sor_ok[O3D_F_PP], s->tmap_sor_ok[O3D_F_PP2]);
     }
     touch(s, O3D_F_PP);
     touch(s, O3D_F_PP2);
+    if (tma && same_bc && h->iter > 0) {
+        // the last pass wrote the even ghost images (faces, edges) of the iterate it stored:
+        // the projection correction and the next solve find the closure in place
+        const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+        s->gaxes[O3D_F_PP] = 0x1u | 0x2u | 0x8u | 0x10u | (zhalo ? 0u : 0x4u);
+        s->gpar[O3D_F_PP] = 0u;
+    }
     s->t_cnt[ST_SOR] += h->iter;
     s->omega = h->omega;  // omega is intent(inout) and persists, src/integration.f90:222,247
     s->last_iters = h->iter;

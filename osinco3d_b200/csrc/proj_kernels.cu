@@ -14,26 +14,48 @@ struct NoPre {};
 
 // Divergence: fz needs the z window, fx and fy only the plane being computed (centre-only ring
 // of the march engine), prefetched 2 planes ahead.
+// S2 = sim2d resolved at compile time (no basic-block break in the common 3-D case)
+template <bool S2>
 struct DivEpi {
     double* out;
     Coef cx, cy, cz;
     double dt;
     int divide, sim2d;
+    // even ghost images of the result (faces): the Poisson right-hand side is read by the SOR
+    // pass through its ghost cells (the index rule of src/poisson.f90:57-92 as data)
+    Img2 ix, iy;
+    int nz, bz_lo, bz_hi;
+    long long sy_, sz_;
     typedef NoPre Pre;
-    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
+    __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j) {
+        ix = image_offsets(i, g.nx, g.bx, g.bx);
+        iy = image_offsets(j, g.ny, g.by, g.by);
+        nz = g.nz, bz_lo = g.bz_lo, bz_hi = g.bz_hi;
+        sy_ = g.sy, sz_ = g.sz;
+    }
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
-    __device__ __forceinline__ void apply(const Ring<1, 2>& r, long long m, int, int, int,
+    __device__ __forceinline__ void apply(const Ring<1, 2>& r, long long m, int, int, int k,
                                           const Pre&) {
         const double dfx = r.c_d1x(0, cx);
         const double dfy = r.c_d1y(1, cy);
-        const double dfz = sim2d ? 0.0 : r.d1z(0, cz);
+        const double dfz = S2 ? 0.0 : r.d1z(0, cz);
         double v = dfx + dfy + dfz;  // src/differential_operators.f90:35
         if (divide) v = v / dt;      // src/integration.f90:239
         out[m] = v;
+        const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
+        if (ix.lo | ix.hi | iy.lo | iy.hi | iz.lo | iz.hi) {  // boundary-adjacent threads only
+            if (ix.lo) out[m + ix.lo] = v;
+            if (ix.hi) out[m + ix.hi] = v;
+            if (iy.lo) out[m + iy.lo * sy_] = v;
+            if (iy.hi) out[m + iy.hi * sy_] = v;
+            if (iz.lo) out[m + iz.lo * sz_] = v;
+            if (iz.hi) out[m + iz.hi * sz_] = v;
+        }
     }
     __device__ __forceinline__ void finish(int, double*) {}
 };
 
+template <bool S2>
 struct CorrEpi {
     const double* up[3];
     double* u[3];
@@ -70,7 +92,7 @@ struct CorrEpi {
         // src/integration.f90:298-300 (derxp, deryp, derzp)
         const double dpdx = r.d1x(0, cx);
         const double dpdy = r.d1y(0, cy);
-        const double dpdz = sim2d ? 0.0 : r.d1z(0, cz);
+        const double dpdz = S2 ? 0.0 : r.d1z(0, cz);
         // src/integration.f90:304-306
         const double u0 = pre.v[0] - dt * dpdx;
         const double u1 = pre.v[1] - dt * dpdy;
@@ -104,9 +126,11 @@ struct CorrEpi {
 
 }  // namespace
 
-int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx, const Coef& cy,
-               const Coef& cz, int divide_by_dt, double dt, double* out, int zmode, int zedge) {
-    DivEpi e;
+template <bool S2>
+static int launch_div_t(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx,
+                        const Coef& cy, const Coef& cz, int divide_by_dt, double dt, double* out,
+                        int zmode, int zedge) {
+    DivEpi<S2> e;
     e.out = out;
     e.cx = cx, e.cy = cy, e.cz = cz;
     e.divide = divide_by_dt, e.dt = dt, e.sim2d = g.sim2d;
@@ -114,19 +138,34 @@ int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx
     m.m[0] = *f[2].tm;  // z-window field first
     m.m[1] = *f[0].tm;
     m.m[2] = *f[1].tm;
-    return launch_march<1, 2, 2, DivEpi, 3>(st, g, m, e, zmode, zedge);
+    return launch_march<1, 2, 2, DivEpi<S2>, 3>(st, g, m, e, zmode, zedge);
 }
 
-int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const double* const* up,
-                double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
-                int* flag, int zmode, int zedge) {
-    CorrEpi e;
+int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx, const Coef& cy,
+               const Coef& cz, int divide_by_dt, double dt, double* out, int zmode, int zedge) {
+    return g.sim2d ? launch_div_t<true>(st, g, f, cx, cy, cz, divide_by_dt, dt, out, zmode, zedge)
+                   : launch_div_t<false>(st, g, f, cx, cy, cz, divide_by_dt, dt, out, zmode, zedge);
+}
+
+template <bool S2>
+static int launch_corr_t(cudaStream_t st, const Geom& g, const FieldRef& pp,
+                         const double* const* up, double* const* u, const Coef& cx,
+                         const Coef& cy, const Coef& cz, double dt, int* flag, int zmode,
+                         int zedge) {
+    CorrEpi<S2> e;
     for (int c = 0; c < 3; ++c) e.up[c] = up[c], e.u[c] = u[c];
     e.cx = cx, e.cy = cy, e.cz = cz;
     e.dt = dt, e.flag = flag, e.sim2d = g.sim2d, e.bad = 0;
     MarchMaps<1> m;
     m.m[0] = *pp.tm;
-    return launch_march<1, 0, 1, CorrEpi, 3>(st, g, m, e, zmode, zedge);
+    return launch_march<1, 0, 1, CorrEpi<S2>, 3>(st, g, m, e, zmode, zedge);
+}
+
+int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const double* const* up,
+                double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
+                int* flag, int zmode, int zedge) {
+    return g.sim2d ? launch_corr_t<true>(st, g, pp, up, u, cx, cy, cz, dt, flag, zmode, zedge)
+                   : launch_corr_t<false>(st, g, pp, up, u, cx, cy, cz, dt, flag, zmode, zedge);
 }
 
 }  // namespace o3d

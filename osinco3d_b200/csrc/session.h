@@ -28,8 +28,12 @@ struct o3d_session {
     // padded fields; history levels are logical views onto three physical buffers
     double* base[O3D_F_COUNT];       // allocation start (ghosts included)
     CUtensorMap tmap[O3D_F_COUNT];   // 40 x 14 x 1 boxes for the march engine
+    CUtensorMap tmap_sor[O3D_F_COUNT];  // 36 x 20 x 1 boxes for the fused SOR pass (lazy)
+    unsigned char tmap_sor_ok[O3D_F_COUNT];
     // ghost-cell state per field: which axes currently hold a valid closure and with which
     // parity bits (bit a: odd along axis a).  Producers / uploads reset gaxes to 0.
+    // gaxes: 0x1 / 0x2 / 0x4 = faces of x / y / z valid (z including rank-boundary halos);
+    // 0x8 = z faces valid on the wall (non-halo) sides; 0x10 = edges and corners valid too.
     unsigned gaxes[O3D_F_COUNT], gpar[O3D_F_COUNT];
     int lv[4][3];          // history: physical buffer per component (0..2 = fu?, 3 = fphi)
 
@@ -106,6 +110,9 @@ int ensure_ghosts(o3d_session* s, const int* ids, int n, const unsigned* par, un
 int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes, bool defer = false);
 int ensure_ghosts_own_axis(o3d_session* s, const int* ids, const unsigned* par,
                            bool defer = false);
+// x, y and wall-side z ghosts (plus edges / corners if `edges`) valid, WITHOUT any exchange
+int ensure_local_ghosts(o3d_session* s, int id, unsigned par, bool edges);
+const CUtensorMap* sor_tmap(o3d_session* s, int id);
 int ensure_partial(o3d_session* s, long long n);
 void fill_geom(o3d_session* s);
 // call right after a synchronisation of the session stream

@@ -1,0 +1,287 @@
+// sor_tma_kernel.cu -- fused red+black SOR iteration, TMA-staged (the fast path of the pressure
+// Poisson solve, src/poisson.f90:6-381, for 2-colourable grids).
+//
+// One pass over the grid per SOR iteration, ping-pong p_old -> p_new:
+//   read p (8) + read rhs (8) + write p (8) = 24 B/pt per ITERATION
+// (the reference streams pp, rhs and p_new: 32 B/pt, with a loop-carried dependence).
+//
+// The boundary rule of src/poisson.f90:57-92 (periodic wrap / mirror) lives in the GHOST CELLS
+// of p_old and rhs (o3d_common.cuh): this kernel writes the ghost images of every point it
+// stores (faces and edges), so the next pass -- and the projection correction after the last
+// one -- find their closure in place and a plane is a plain rectangular TMA box for interior
+// and boundary tiles alike: no index maps, no boundary branches.  A ghost cell's red update is
+// recomputed from ghost data with the same arithmetic as the interior point it mirrors, so it is
+// bit-identical to it.
+//
+// A CTA (256 threads, each owning an x-pair = one red + one black cell per plane) owns a 32 x 16
+// column and marches in z.  Planes are staged with a 2-cell halo (36 x 20 boxes) in a ring of 7
+// (p) + 5 (rhs) shared-memory stages, two planes prefetched ahead.  At march step k:
+//   red(k+2): tile + its 1-cell ring (ring cells recomputed redundantly instead of waiting for
+//             the neighbouring CTA: same inputs, same arithmetic -> same bits), from the OLD
+//             black values of planes k+1, k+2, k+3;
+//   black(k): tile, from the NEW red values of planes k-1, k, k+1; plane k of p_new is stored.
+// The two phases touch disjoint data, so ONE __syncthreads per plane suffices.
+// Result == a red half-sweep followed by a black half-sweep (sor_rb_kernel twice), bit for bit.
+#include "kernels.h"
+#include "tma.cuh"
+
+namespace o3d {
+namespace {
+
+constexpr int GTX = 32, GTY = 16, GNT = 256;
+constexpr int GBX = GTX + 4, GBY = GTY + 4, GPL = GBX * GBY;  // 36 x 20 = 720 cells, 5760 B
+constexpr int GP = 2;                                         // planes prefetched ahead
+constexpr int GNP = 5 + GP, GNR = 3 + GP, GNB = GP + 1;       // p stages, rhs stages, barriers
+constexpr int GSMEM = (GNP + GNR) * GPL * 8 + GNB * 8 + 32 * 8;
+
+struct TmaSorArgs {
+    double* p_new;
+    double ox, oy, oz, invA;
+    int nx, ny, nz;
+    long long sy, sz;
+    int bx, by, bz_lo, bz_hi;  // closures (BM_*), for the ghost images of p_new
+    int gz0;
+    int zchunk, zmode, zlo, zhi, zedge;
+};
+
+struct alignas(64) TmaSorMaps {
+    CUtensorMap p, rhs;
+};
+
+// store v at element m and at every ghost image of the point (faces, edges, corners)
+__device__ __forceinline__ void store_images(double* __restrict__ q, long long m, double v,
+                                             const Img2& ix, long long ylo, long long yhi,
+                                             long long zlo, long long zhi) {
+    const long long xo[3] = {0, ix.lo, ix.hi};
+    const long long yo[3] = {0, ylo, yhi};
+    const long long zo[3] = {0, zlo, zhi};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c && !zo[c]) continue;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (b && !yo[b]) continue;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (a && !xo[a]) continue;
+                if (a | b | c) q[m + xo[a] + yo[b] + zo[c]] = v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GNT, 3)
+    sor_tma_kernel(const __grid_constant__ TmaSorMaps maps, const TmaSorArgs a, SorCtrl* ctrl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sp = reinterpret_cast<double*>(smem_raw);
+    double* sr = sp + GNP * GPL;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sr + GNR * GPL);
+    double* red = reinterpret_cast<double*>(bars + GNB);
+    if (*((volatile int*)&ctrl->done)) return;
+    const double omega = *((volatile double*)&ctrl->omega);
+    const double one_m_omega = 1.0 - omega;
+
+    const int tid = threadIdx.x;
+    const int px = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.x * GTX, j0 = blockIdx.y * GTY;
+    int kb, ke;
+    if (a.zmode == 2) {
+        kb = (blockIdx.z == 0) ? 0 : a.nz - a.zedge;
+        ke = kb + a.zedge;
+    } else {
+        kb = a.zlo + blockIdx.z * a.zchunk;
+        ke = min(a.zhi, kb + a.zchunk);
+    }
+    const int niter = ke - kb;
+    const int ngroups = niter > 1 ? niter - 1 : 1;  // group n feeds red(kb + n + 2)
+
+    const uint32_t sp_s = smem_u32(sp), sr_s = smem_u32(sr), bars_s = smem_u32(bars);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GNB; ++s) mbar_init(bars_s + 8 * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // p plane q lives in stage (q - (kb-2)) mod GNP, rhs plane q in (q - (kb-1)) mod GNR
+    const int cx = GX + i0 - 2, cy = GH + j0 - 2;
+    auto issue_p = [&](int plane, uint32_t bar) {
+        const unsigned st = (unsigned)(plane - (kb - 2)) % GNP;
+        tma_load_3d(sp_s + st * (GPL * 8), &maps.p, bar, cx, cy, GH + plane);
+    };
+    auto issue_r = [&](int plane, uint32_t bar) {
+        const unsigned st = (unsigned)(plane - (kb - 1)) % GNR;
+        tma_load_3d(sr_s + st * (GPL * 8), &maps.rhs, bar, cx, cy, GH + plane);
+    };
+    auto issue_group = [&](int n) {
+        const uint32_t bar = bars_s + 8 * (n % GNB);
+        if (n == 0) {
+            mbar_expect_tx(bar, (6 + 4) * GPL * 8);
+#pragma unroll
+            for (int q = -2; q <= 3; ++q) issue_p(kb + q, bar);
+#pragma unroll
+            for (int q = -1; q <= 2; ++q) issue_r(kb + q, bar);
+        } else {
+            mbar_expect_tx(bar, 2 * GPL * 8);
+            issue_p(kb + n + 3, bar);
+            issue_r(kb + n + 2, bar);
+        }
+    };
+    if (tid == 0) {
+        for (int n = 0; n < GP && n < ngroups; ++n) issue_group(n);
+    }
+
+    // own x-pair: cells (2+2px, 3+2px) of row 2+ty; pe = colour of the even member in plane 0
+    const int own = (ty + 2) * GBX + 2 + 2 * px;
+    const int gi = i0 + 2 * px, gj = j0 + ty;
+    const bool in0 = gi < a.nx && gj < a.ny, in1 = gi + 1 < a.nx && gj < a.ny;
+    const int pe = (gi + gj + a.gz0) & 1;
+    // ring-1 pairs (48 threads): each pair holds exactly one red cell in every plane
+    int rcell = -1, rstep = 0, rpar = 0;
+    if (tid < 48) {
+        int lx, ly;
+        if (tid < 16) lx = 2 + 2 * tid, ly = 1, rstep = 1;                       // below the tile
+        else if (tid < 32) lx = 2 + 2 * (tid - 16), ly = GBY - 2, rstep = 1;     // above
+        else if (tid < 40) lx = 1, ly = 2 + 2 * (tid - 32), rstep = GBX;         // left
+        else lx = GBX - 2, ly = 2 + 2 * (tid - 40), rstep = GBX;                 // right
+        rcell = ly * GBX + lx;
+        rpar = (i0 - 2 + lx + j0 - 2 + ly + a.gz0) & 1;
+    }
+    // ghost images of the own points in x and y
+    const Img2 ix0 = image_offsets(gi, a.nx, a.bx, a.bx);
+    const Img2 ix1 = image_offsets(gi + 1, a.nx, a.bx, a.bx);
+    const Img2 iy = image_offsets(gj, a.ny, a.by, a.by);
+    const long long ylo = iy.lo * a.sy, yhi = iy.hi * a.sy;
+    const bool xy_img = (ix0.lo | ix0.hi | ix1.lo | ix1.hi | iy.lo | iy.hi) != 0;
+
+    double dmax = 0.0;
+    // SOR update of cell c of plane S0 (src/poisson.f90:95-102, "/ A" as "* (1/A)": this ordering
+    // is not the bit-parity one); returns the relaxed value, d = |p_new - p_old|
+    auto update = [&](const double* Sm, const double* S0, const double* Sp, const double* Rr,
+                      int c, double& d) -> double {
+        const double pc = S0[c];
+        const double p_new = (-(a.ox * (S0[c - 1] + S0[c + 1])) -
+                              a.oy * (S0[c - GBX] + S0[c + GBX]) - a.oz * (Sm[c] + Sp[c]) + Rr[c]) *
+                             a.invA;
+        d = fabs(p_new - pc);                      // :100
+        return one_m_omega * pc + omega * p_new;   // :102
+    };
+    // Stage of p plane q: (q - (kb-2)) mod GNP; of rhs plane q: (q - (kb-1)) mod GNR.  The march
+    // keeps the stage indices of planes k-1 .. k+3 (p) and k .. k+2 (rhs) in registers and rotates
+    // them, so the hot loop has no modulo arithmetic.
+    auto nextp = [](int st) { return st + 1 == GNP ? 0 : st + 1; };
+    auto nextr = [](int st) { return st + 1 == GNR ? 0 : st + 1; };
+    // red half-sweep of plane q (stages sm, s0, s1 = planes q-1, q, q+1; rs = rhs plane q) over
+    // the own pair and the ring pair; counted: the plane is owned by this chunk
+    auto red_plane = [&](int q, int sm, int s0, int s1, int rs, bool counted) {
+        double* S0 = sp + s0 * GPL;
+        const double *Sm = sp + sm * GPL, *Sp = sp + s1 * GPL, *Rr = sr + rs * GPL;
+        const int r = (pe + q) & 1;  // which member of the own pair is red in plane q
+        double d;
+        const double v = update(Sm, S0, Sp, Rr, own + r, d);
+        if (rcell >= 0) {  // warps 0 and 1 only
+            double dr;
+            const int rc = rcell + (((rpar + q) & 1) ? rstep : 0);
+            S0[rc] = update(Sm, S0, Sp, Rr, rc, dr);
+        }
+        // (a red cell has no red neighbour: every read above is of a black cell or of the cell's
+        // own centre, every write below of a red cell owned by exactly one thread)
+        S0[own + r] = v;
+        if (counted && (r ? in1 : in0)) dmax = fmax(dmax, d);
+    };
+
+    mbar_wait(bars_s, 0);  // group 0: p planes kb-2 .. kb+3 in stages 0 .. 5, rhs kb-1 .. kb+2 in 0 .. 3
+    red_plane(kb - 1, 0, 1, 2, 0, false);
+    red_plane(kb, 1, 2, 3, 1, true);
+    red_plane(kb + 1, 2, 3, 4, 2, kb + 1 < ke);
+
+    int p_m1 = 1, p_0 = 2, p_1 = 3, p_2 = 4, p_3 = 5;  // stages of planes k-1 .. k+3 (k = kb)
+    int r_0 = 1, r_2 = 3;                              // stages of rhs planes k, k+2
+    double* outp = a.p_new + (long long)kb * a.sz + (long long)gj * a.sy + gi;
+    const long long ylo_z = ylo, yhi_z = yhi;
+    for (int k = kb; k < ke; ++k) {
+        const int n = k - kb;
+        __syncthreads();  // step k-1 done: its oldest stages may be refilled; red(k+1) visible
+        if (tid == 0 && n + GP < ngroups) issue_group(n + GP);
+        if (n >= 1 && n < ngroups) mbar_wait(bars_s + 8 * (n % GNB), (n / GNB) & 1);
+        if (k + 2 <= ke) red_plane(k + 2, p_1, p_2, p_3, r_2, k + 2 < ke);
+        {
+            // black member of the own pair in plane k: all six neighbours hold new red values
+            const int r = (pe + k) & 1;
+            const double* S0 = sp + p_0 * GPL;
+            double d;
+            const double vb = update(sp + p_m1 * GPL, S0, sp + p_1 * GPL, sr + r_0 * GPL,
+                                     own + 1 - r, d);
+            const double vred = S0[own + r];
+            if (r ? in0 : in1) dmax = fmax(dmax, d);
+            const double v0 = r ? vb : vred, v1 = r ? vred : vb;
+            if (in1) {
+                *reinterpret_cast<double2*>(outp) = make_double2(v0, v1);
+            } else if (in0) {
+                outp[0] = v0;
+            }
+            const Img2 iz = image_offsets(k, a.nz, a.bz_lo, a.bz_hi);
+            if (xy_img || (iz.lo | iz.hi)) {
+                if (in0) store_images(outp, 0, v0, ix0, ylo_z, yhi_z, iz.lo * a.sz, iz.hi * a.sz);
+                if (in1) store_images(outp, 1, v1, ix1, ylo_z, yhi_z, iz.lo * a.sz, iz.hi * a.sz);
+            }
+        }
+        outp += a.sz;
+        p_m1 = p_0, p_0 = p_1, p_1 = p_2, p_2 = p_3, p_3 = nextp(p_3);
+        r_0 = nextr(r_0), r_2 = nextr(r_2);
+    }
+    const double bm = block_max(dmax, red);
+    if (tid == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+}
+
+}  // namespace
+
+int sor_tma_box_x() { return GBX; }
+int sor_tma_box_y() { return GBY; }
+
+int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_map,
+                   const CUtensorMap* rhs_map, double* p_new, int bx, int by, int bz_lo,
+                   int bz_hi, SorCtrl* ctrl, int zmode, int zedge) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(sor_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 GSMEM) != cudaSuccess)
+            return 1;
+        attr_set = true;
+    }
+    TmaSorMaps maps;
+    maps.p = *p_old_map, maps.rhs = *rhs_map;
+    TmaSorArgs f;
+    f.p_new = p_new;
+    f.ox = a.oneondx2, f.oy = a.oneondy2, f.oz = a.oneondz2, f.invA = a.invA;
+    f.nx = a.nx, f.ny = a.ny, f.nz = a.nz;
+    f.sy = a.sy, f.sz = a.sz;
+    f.bx = bx, f.by = by, f.bz_lo = bz_lo, f.bz_hi = bz_hi;
+    f.gz0 = a.gz0;
+    const int gx = (a.nx + GTX - 1) / GTX, gy = (a.ny + GTY - 1) / GTY;
+    f.zmode = zmode, f.zedge = zedge;
+    f.zlo = (zmode == 1) ? zedge : 0;
+    f.zhi = (zmode == 1) ? a.nz - zedge : a.nz;
+    int gz;
+    if (zmode == 2) {
+        f.zchunk = zedge;
+        gz = 2;
+    } else {
+        const int span = f.zhi - f.zlo;
+        if (span <= 0) return 0;
+        // 5 extra planes per chunk: keep chunks long, but fill 148 SMs x 3 CTAs a few times
+        const int target = 148 * 3 * 3;
+        int nch = (target + gx * gy - 1) / (gx * gy);
+        int maxch = span / 40;
+        if (maxch < 1) maxch = 1;
+        if (nch > maxch) nch = maxch;
+        if (nch < 1) nch = 1;
+        f.zchunk = (span + nch - 1) / nch;
+        gz = (span + f.zchunk - 1) / f.zchunk;
+    }
+    sor_tma_kernel<<<dim3(gx, gy, gz), GNT, GSMEM, st>>>(maps, f, ctrl);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace o3d

@@ -13,6 +13,8 @@
 //   StatsEpi : statistics_calc (src/utils.f90:243-375), 16 sums          24 B/pt
 //
 // HBM-bound FP64 stencils: no tensor cores (nothing here is a contraction).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "march.cuh"
 
@@ -50,6 +52,10 @@ __device__ __forceinline__ double smagorinsky(const Grad& G, double csd2) {
 }
 
 // ---------------------------------------------------------------------------------------
+// FAST: DNS in 3-D with sim2d / iles resolved at compile time (straight-line code, no basic-block
+// breaks between the derivative evaluations).  !FAST: both are runtime flags; the branches keep
+// the live ranges of the LES instantiation inside 128 registers (no spills).
+template <bool FAST>
 struct RhsEpi {
     const double* f2[3];
     const double* f3[3];
@@ -89,9 +95,9 @@ struct RhsEpi {
     }
     __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int k,
                                           const Pre& pre) {
-        const Grad G = gradient(r, q, sim2d);
+        const Grad G = gradient(r, q, FAST ? 0 : sim2d);
         double nut = 0.0;
-        if (iles) {
+        if (!FAST && iles) {
             nut = smagorinsky(G, csd2);
             nu_t[m] = nut;
         }
@@ -100,7 +106,7 @@ struct RhsEpi {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double lx = r.d2x(c, q.x), ly = r.d2y(c, q.y);
-            const double lz = sim2d ? 0.0 : r.d2z(c, q.z);
+            const double lz = (!FAST && sim2d) ? 0.0 : r.d2z(c, q.z);
             // src/integration.f90:129-134 (and :149-154, :169-174)
             const double f = nu_eff * (lx + ly + lz) -
                              (u0 * G.d[c][0] + u1 * G.d[c][1] + u2 * G.d[c][2]);
@@ -122,6 +128,97 @@ struct RhsEpi {
         }
     }
     __device__ __forceinline__ void finish(int, double*) {}
+};
+
+// ---------------------------------------------------------------------------------------
+// Role-split RHS (march_roles_kernel): thread role c in {0,1,2} owns velocity component c of its
+// grid point -- grad(u_c), lap(u_c), f_c and u_c* -- exactly the per-component blocks of the
+// reference (src/integration.f90:118-134, :138-154, :158-174).  The roles only meet for the
+// Smagorinsky viscosity, which needs all nine first derivatives (src/les_turbulence.f90:55-88):
+// each role publishes its three through shared memory.
+struct RhsRoleEpi {
+    const double* f2[3];
+    const double* f3[3];
+    double* f1[3];
+    double* up[3];
+    double* nu_t;
+    Coefs3 q;
+    double onere, adu, bdu, cdu, csd2;
+    int iles, sim2d;
+    // per thread
+    int c, fo;                 // component, field offset in a ring stage
+    const double *f2c, *f3c;
+    double *f1c, *upc;
+    long long img_lo, img_hi;  // own-axis ghost images of u* (x for c = 0, y for c = 1)
+    double sg_xy;
+    int nz, bz_lo, bz_hi;
+    long long sz_;
+    __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j, int role) {
+        c = role, fo = role * MFIELD;
+        f2c = f2[role], f3c = f3[role], f1c = f1[role], upc = up[role];
+        img_lo = img_hi = 0;
+        sg_xy = 1.0;
+        if (role == 0) {
+            const Img2 ix = image_offsets(i, g.nx, g.bx, g.bx);
+            img_lo = ix.lo, img_hi = ix.hi;
+            sg_xy = (g.bx == BM_MIRROR) ? -1.0 : 1.0;
+        } else if (role == 1) {
+            const Img2 iy = image_offsets(j, g.ny, g.by, g.by);
+            img_lo = iy.lo * g.sy, img_hi = iy.hi * g.sy;
+            sg_xy = (g.by == BM_MIRROR) ? -1.0 : 1.0;
+        }
+        nz = g.nz, bz_lo = g.bz_lo, bz_hi = g.bz_hi, sz_ = g.sz;
+    }
+    struct Pre {
+        double f2v, f3v;
+    };
+    __device__ __forceinline__ Pre prefetch(long long m, bool ok) const {
+        Pre p;
+        p.f2v = ok ? __ldg(f2c + m) : 0.0;
+        p.f3v = ok ? f3c[m] : 0.0;  // plain load: f3 may alias f1 (read before written, per point)
+        return p;
+    }
+    __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int k, const Pre& pre,
+                                          bool ok, int pt, double* xch) {
+        const double g0 = r.d1x(c, q.x);
+        const double g1 = r.d1y(c, q.y);
+        const double g2 = sim2d ? 0.0 : r.d1z(c, q.z);  // derz_2dsim, src/derivation.f90:481
+        double nut = 0.0;
+        if (iles) {  // uniform across the CTA
+            xch[(3 * c + 0) * MNT + pt] = g0;
+            xch[(3 * c + 1) * MNT + pt] = g1;
+            xch[(3 * c + 2) * MNT + pt] = g2;
+            __syncthreads();
+            Grad G;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) G.d[a][b] = xch[(3 * a + b) * MNT + pt];
+            nut = smagorinsky(G, csd2);
+            if (ok && c == 0) nu_t[m] = nut;
+        }
+        const double nu_eff = onere + nut;  // src/integration.f90:114
+        const double u0 = r.c(0), u1 = r.c(1), u2 = r.c(2);
+        const double lx = r.d2x(c, q.x), ly = r.d2y(c, q.y);
+        const double lz = sim2d ? 0.0 : r.d2z(c, q.z);
+        // src/integration.f90:129-134 (and :149-154, :169-174)
+        const double f = nu_eff * (lx + ly + lz) - (u0 * g0 + u1 * g1 + u2 * g2);
+        const double uc = (c == 0) ? u0 : (c == 1) ? u1 : u2;
+        const double upv = uc + adu * f + bdu * pre.f2v + cdu * pre.f3v;
+        if (!ok) return;
+        f1c[m] = f;
+        upc[m] = upv;
+        // ghost images of u* along the component's own axis (odd closure: mirrored copies change
+        // sign) -- all that divergence(odd = 1) needs, src/differential_operators.f90:30-32
+        if (c < 2) {
+            if (img_lo) upc[m + img_lo] = sg_xy * upv;
+            if (img_hi) upc[m + img_hi] = sg_xy * upv;
+        } else {
+            const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
+            if (iz.lo) upc[m + iz.lo * sz_] = (bz_lo == BM_MIRROR) ? -upv : upv;
+            if (iz.hi) upc[m + iz.hi * sz_] = (bz_hi == BM_MIRROR) ? -upv : upv;
+        }
+    }
 };
 
 struct NoPre {};
@@ -244,15 +341,33 @@ Coefs3 coefs(const Coef& cx, const Coef& cy, const Coef& cz) {
 
 }  // namespace
 
-int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int zedge) {
-    RhsEpi e;
+template <bool FAST>
+static int launch_rhs_t(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int zedge) {
+    RhsEpi<FAST> e;
     for (int c = 0; c < 3; ++c)
         e.f2[c] = r.f2[c], e.f3[c] = r.f3[c], e.f1[c] = r.f1[c], e.up[c] = r.up[c];
     e.nu_t = r.nu_t;
     e.q = coefs(r.cx, r.cy, r.cz);
     e.onere = r.onere, e.adu = r.adu, e.bdu = r.bdu, e.cdu = r.cdu, e.csd2 = r.csd2;
     e.iles = r.iles, e.sim2d = g.sim2d;
-    return launch_march<3, 0, 1, RhsEpi, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e, zmode, zedge);
+    return launch_march<3, 0, 1, RhsEpi<FAST>, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e,
+                                                          zmode, zedge);
+}
+
+int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int zedge) {
+    static const int variant = getenv("O3D_RHS_VARIANT") ? atoi(getenv("O3D_RHS_VARIANT")) : 0;
+    if (variant >= 2) {
+        RhsRoleEpi w;
+        for (int c = 0; c < 3; ++c)
+            w.f2[c] = r.f2[c], w.f3[c] = r.f3[c], w.f1[c] = r.f1[c], w.up[c] = r.up[c];
+        w.nu_t = r.nu_t, w.q = coefs(r.cx, r.cy, r.cz);
+        w.onere = r.onere, w.adu = r.adu, w.bdu = r.bdu, w.cdu = r.cdu, w.csd2 = r.csd2;
+        w.iles = r.iles, w.sim2d = g.sim2d;
+        const MarchMaps<3> mm = maps3(r.u[0], r.u[1], r.u[2]);
+        return launch_march_roles<3, 2, 3, RhsRoleEpi>(st, g, mm, w, zmode, zedge);
+    }
+    if (!g.sim2d && !r.iles) return launch_rhs_t<true>(st, g, r, zmode, zedge);
+    return launch_rhs_t<false>(st, g, r, zmode, zedge);
 }
 
 int launch_nu_t(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,
