@@ -276,3 +276,55 @@ class Sim:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------
+# deterministic initial perturbation (ici = 1), host-side input generation only
+# ---------------------------------------------------------------------------------------------
+def dery1d(f, dy):
+    """src/derivation.f90:950-992: 6th-order centred interior, one-sided / low-order closures"""
+    n = f.size
+    s = 60.0 * dy
+    a, b, c = 1.0 / s, 9.0 / s, 45.0 / s
+    df = np.empty(n)
+    j = np.arange(3, n - 3)
+    df[j] = a * (f[j + 3] - f[j - 3]) - b * (f[j + 2] - f[j - 2]) + c * (f[j + 1] - f[j - 1])
+    df[0] = (-f[2] + 4.0 * f[1] - 3.0 * f[0]) / (2.0 * dy)
+    df[1] = (f[2] - f[0]) / (2.0 * dy)
+    df[2] = (-f[4] + 8.0 * f[3] - 8.0 * f[1] + f[0]) / (12.0 * dy)
+    df[n - 3] = (-f[n - 1] + 8.0 * f[n - 2] - 8.0 * f[n - 4] + f[n - 5]) / (12.0 * dy)
+    df[n - 2] = (f[n - 1] - f[n - 3]) / (2.0 * dy)
+    df[n - 1] = (3.0 * f[n - 1] - 4.0 * f[n - 2] + f[n - 3]) / (2.0 * dy)
+    return df
+
+
+def normalize1d(f, base):
+    """src/utils.f90:20-45"""
+    rng = f.max() - f.min()
+    if abs(rng) < 1e-12:
+        return np.full_like(f, base)
+    return base + (1.0 - base) * (f - f.min()) / rng
+
+
+def add_oscillations_init(g, ux, uy, uz, u0, noise, typesim, x0, xlx):
+    """src/initial_conditions.f90:554-629 (ici = 1): the deterministic perturbation used instead of
+    the shipped clock-seeded FFTW noise (ici = 2), SURVEY 8d.  noise = (x, y, z) intensities."""
+    u_base = dery1d(np.ascontiguousarray(ux[0, :, 0]), g.dy)           # calcul_u_base, utils.f90:9
+    u_base = normalize1d(u_base, 0.0 if typesim == 5 else -1.0)
+    x = x0 + g.dx * np.arange(g.nx)
+    ub = u_base[None, :, None]
+    pi = np.pi
+    if typesim in (5, 3):
+        sx = (np.sin(8 * pi * x / xlx) + np.sin(4 * pi * x / xlx) / 8.0
+              + np.sin(2 * pi * x / xlx) / 16.0)[:, None, None]
+        cxx = (np.cos(8 * pi * x / xlx) + np.cos(4 * pi * x / xlx) / 8.0
+               + np.cos(2 * pi * x / xlx) / 16.0)[:, None, None]
+        ux = ux + u0 * noise[0] * ub * sx
+        uy = uy + u0 * noise[1] * ub * cxx + 0.0 * uz
+    else:
+        ph = np.sin(2 * pi * 9 * x / xlx)[:, None, None]
+        ux = ux + u0 * noise[0] * ub * ph
+        uy = uy + u0 * noise[1] * ub * ph
+        uz = uz + u0 * noise[2] * ub * ph
+    f = np.asfortranarray
+    return f(ux), f(uy), f(uz)
