@@ -81,7 +81,8 @@ double* field(o3d_session* s, int id) {
             return nullptr;
         }
         cudaMemsetAsync(p, 0, n * sizeof(double), s->st);
-        if (make_field_tmap(&s->tmap[id], p, s->g.px, s->g.py, s->g.nz + 2 * GH, MBX, MBY)) {
+        if (make_field_tmap(&s->tmap[id], p, s->g.px, s->g.py, s->g.nz + 2 * GH, MBX, MBY) ||
+            make_field_tmap(&s->tmap_st[id], p, s->g.px, s->g.py, s->g.nz + 2 * GH, MTX, MTY)) {
             cudaFree(p);
             return nullptr;
         }
@@ -98,6 +99,7 @@ FieldRef fref(o3d_session* s, int id) {
     FieldRef r;
     r.p = field(s, id);
     r.tm = &s->tmap[id];
+    r.tms = &s->tmap_st[id];
     return r;
 }
 
@@ -831,11 +833,11 @@ int o3d_s_correct_pression(o3d_session* s, int* iters, double* dmax) {
 static int correct_velocity_impl(o3d_session* s, bool defer) {
     if (!s) return O3D_ERR_INVALID;
     const o3d_config& c = s->cfg;
-    double* up[3] = {field(s, O3D_F_UX_PRED), field(s, O3D_F_UY_PRED), field(s, O3D_F_UZ_PRED)};
+    FieldRef up[3] = {fref(s, O3D_F_UX_PRED), fref(s, O3D_F_UY_PRED), fref(s, O3D_F_UZ_PRED)};
     double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
     FieldRef pp = fref(s, O3D_F_PP);
     for (int k = 0; k < 3; ++k)
-        if (!up[k] || !u[k]) return O3D_ERR_CUDA;
+        if (!up[k].p || !u[k]) return O3D_ERR_CUDA;
     if (!pp.p) return O3D_ERR_CUDA;
     int rc;
     // (before the exchange is issued: the boundary chunks run on the communication stream)

@@ -10,7 +10,8 @@ namespace o3d {
 // a padded field and its TMA tensor map (40 x 14 x 1 boxes, march.cuh)
 struct FieldRef {
     double* p;
-    const CUtensorMap* tm;
+    const CUtensorMap* tm;   // 40 x 14 x 1 boxes (tile + 3-cell x/y halo)
+    const CUtensorMap* tms;  // 32 x 8 x 1 boxes (tile only: stream operands)
 };
 
 // z-chunking heuristic shared by the z-marching kernels: enough CTAs for several waves on
@@ -73,7 +74,7 @@ int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx
 
 // ---- projection correction (src/integration.f90:257-330) ----
 // flag: device int, OR-ed with 1 when a NaN or a value > 1000 is produced.
-int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const double* const* up,
+int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const FieldRef* up,
                 double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
                 int* flag, int zmode = 0, int zedge = 0);
 

@@ -45,25 +45,31 @@ struct MarchGeom {
 };
 
 // NFZ fields need the 7-plane z window (ring of 7+P stages), NFC fields only the plane being
-// computed (ring of 1+P stages); P = prefetch distance in planes.  Fields are ordered z-fields
-// first in MarchMaps.
-template <int NFZ, int NFC, int P>
+// computed, with its x/y halo (ring of 1+P stages), NFS "stream" fields only the point itself
+// (32 x 8 boxes without halo, ring of 1+P stages: the streamed operands of an epilogue, fetched
+// by TMA P planes ahead instead of through registers).  P = prefetch distance in planes.
+// Fields are ordered z-fields, c-fields, s-fields in MarchMaps.
+constexpr int MSFIELD = MTX * MTY;  // doubles per staged stream-field plane (2 KB)
+template <int NFZ, int NFC, int P, int NFS = 0>
 constexpr int march_smem_bytes() {
-    return (NFZ * (7 + P) + NFC * (1 + P)) * MFIELD * 8 + (P + 1) * 8;
+    return (NFZ * (7 + P) + NFC * (1 + P)) * MFIELD * 8 + NFS * (1 + P) * MSFIELD * 8 + (P + 1) * 8;
 }
 
 // The staged data seen by one thread: p[m] points at this thread's cell of z-field 0 in plane
-// k-3+m (z-field f is MFIELD doubles further); q points at its cell of c-field 0 in plane k.
+// k-3+m (z-field f is MFIELD doubles further); q points at its cell of c-field 0 in plane k; s at
+// its value of s-field 0 in plane k (s-field f is MSFIELD doubles further).
 template <int NFZ, int NFC = 0>
 struct Ring {
     const double* p[7];
     const double* q;
+    const double* s;
     __device__ __forceinline__ double c(int f) const { return p[3][f * MFIELD]; }
     __device__ __forceinline__ double x(int f, int d) const { return p[3][f * MFIELD + d]; }
     __device__ __forceinline__ double y(int f, int d) const { return p[3][f * MFIELD + d * MBX]; }
     __device__ __forceinline__ double z(int f, int d) const { return p[3 + d][f * MFIELD]; }
     __device__ __forceinline__ double cx(int f, int d) const { return q[f * MFIELD + d]; }
     __device__ __forceinline__ double cy(int f, int d) const { return q[f * MFIELD + d * MBX]; }
+    __device__ __forceinline__ double st(int f) const { return s[f * MSFIELD]; }
     // src/derivation.f90:43-47 / :529-533 along each axis
     __device__ __forceinline__ double d1x(int f, const Coef& k) const {
         return d1_expr(k.a1, k.b1, k.c1, x(f, -3), x(f, -2), x(f, -1), x(f, 1), x(f, 2), x(f, 3));
@@ -96,20 +102,22 @@ struct Ring {
 
 // Epilogue concept:
 //   void setup(const MarchGeom&, int i, int j);   per-thread constants, before the march
-//   struct Pre;                                   streamed operands of one point
+//   struct Pre;                                   streamed operands of one point (register path)
 //   Pre  prefetch(long long m, bool ok) const;    issue their loads (m = element offset)
 //   void apply(const Ring<NFZ,NFC>&, long long m, int i, int j, int k, const Pre&);
 //   void finish(int tid, double* smem);           after the march (block reductions)
-template <int NFZ, int NFC, int P, class Epi, int MINB>
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0>
 __global__ void __launch_bounds__(MNT, MINB)
-    march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC> maps, const MarchGeom g, Epi epi) {
+    march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC + NFS> maps, const MarchGeom g,
+                 Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NZS = 7 + P, NCS = 1 + P, NB = P + 1;
-    constexpr int ZSTAGE = NFZ * MFIELD, CSTAGE = NFC * MFIELD;  // doubles
+    constexpr int ZSTAGE = NFZ * MFIELD, CSTAGE = NFC * MFIELD, SSTAGE = NFS * MSFIELD;  // doubles
     double* zring = reinterpret_cast<double*>(smem_raw);
     double* cring = zring + NZS * ZSTAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cring + NCS * CSTAGE);
-    constexpr uint32_t PLANE_BYTES = MFIELD * 8;
+    double* sring = cring + NCS * CSTAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sring + NCS * SSTAGE);
+    constexpr uint32_t PLANE_BYTES = MFIELD * 8, SPLANE_BYTES = MSFIELD * 8;
 
     const int tid = threadIdx.x;
     const int tx = tid & (MTX - 1), ty = tid >> 5;
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(MNT, MINB)
     }
     const bool in_dom = (i < g.nx) && (j < g.ny);
 
-    const uint32_t zring_s = smem_u32(zring), cring_s = smem_u32(cring);
+    const uint32_t zring_s = smem_u32(zring), cring_s = smem_u32(cring), sring_s = smem_u32(sring);
     const uint32_t bars_s = smem_u32(bars);
     if (tid == 0) {
 #pragma unroll
@@ -136,28 +144,32 @@ __global__ void __launch_bounds__(MNT, MINB)
 
     // box origin in tensor coordinates: element (GX + i0 - MXO, GH + j0 - R, GH + plane)
     const int cx = GX + i0 - MXO, cy = GH + j0 - R;
-    // z-plane `plane` lives in z-stage (plane - (kb-3)) mod NZS, c-plane in (plane - kb) mod NCS
+    // z-plane `plane` lives in z-stage (plane - (kb-3)) mod NZS, c/s-plane in (plane - kb) mod NCS
     auto issue_z = [&](int plane, uint32_t bar) {
-        const int st = (plane - (kb - R)) % NZS;
+        const unsigned st = (unsigned)(plane - (kb - R)) % NZS;
 #pragma unroll
         for (int f = 0; f < NFZ; ++f)
             tma_load_3d(zring_s + (uint32_t)(st * ZSTAGE + f * MFIELD) * 8, &maps.m[f], bar, cx, cy,
                         GH + plane);
     };
     auto issue_c = [&](int plane, uint32_t bar) {
-        const int st = (plane - kb) % NCS;
+        const unsigned st = (unsigned)(plane - kb) % NCS;
 #pragma unroll
         for (int f = 0; f < NFC; ++f)
             tma_load_3d(cring_s + (uint32_t)(st * CSTAGE + f * MFIELD) * 8, &maps.m[NFZ + f], bar,
                         cx, cy, GH + plane);
+#pragma unroll
+        for (int f = 0; f < NFS; ++f)
+            tma_load_3d(sring_s + (uint32_t)(st * SSTAGE + f * MSFIELD) * 8,
+                        &maps.m[NFZ + NFC + f], bar, GX + i0, GH + j0, GH + plane);
     };
-    // "need group" n = what iteration n waits for: z-plane kb+n+3 and c-plane kb+n (group 0 also
+    // "need group" n = what iteration n waits for: z-plane kb+n+3 and c/s-plane kb+n (group 0 also
     // carries z-planes kb-3 .. kb+2); its barrier is n mod NB
     const int niter = ke - kb;
     auto issue_group = [&](int n) {
-        const uint32_t bar = bars_s + 8 * (n % NB);
+        const uint32_t bar = bars_s + 8 * ((unsigned)n % NB);
         const int nz_planes = (n == 0) ? 7 : 1;
-        mbar_expect_tx(bar, (uint32_t)(nz_planes * NFZ + NFC) * PLANE_BYTES);
+        mbar_expect_tx(bar, (uint32_t)(nz_planes * NFZ + NFC) * PLANE_BYTES + NFS * SPLANE_BYTES);
         if (n == 0) {
 #pragma unroll
             for (int s = 0; s < 6; ++s) issue_z(kb - R + s, bar);
@@ -174,23 +186,37 @@ __global__ void __launch_bounds__(MNT, MINB)
     typename Epi::Pre cur = epi.prefetch(m0 + (long long)kb * g.sz, in_dom);
     const int cell = (ty + R) * MBX + tx + MXO;
 
+    // ring positions of the plane being computed, advanced incrementally (no modulo in the loop):
+    // zb = stage of plane k-3, cb = stage of plane k, bi / bpar = barrier index and phase
+    int zb = 0, cb = 0, bi = 0;
+    uint32_t bpar = 0;
+    long long m = m0 + (long long)kb * g.sz;
     for (int k = kb; k < ke; ++k) {
-        const unsigned it = (unsigned)(k - kb);  // unsigned: ring indices compile to AND / cheap MOD
-        // streamed operands of the next plane
-        typename Epi::Pre nxt = epi.prefetch(m0 + (long long)(k + 1) * g.sz, in_dom && (k + 1 < ke));
+        const int it = k - kb;
+        // streamed operands of the next plane (register path)
+        typename Epi::Pre nxt = epi.prefetch(m + g.sz, in_dom && (k + 1 < ke));
         // every thread is done with plane k-1: its stages can be refilled with group it+P
         __syncthreads();
-        if (tid == 0 && (int)it + P < niter) issue_group((int)it + P);
+        if (tid == 0 && it + P < niter) issue_group(it + P);
         // group `it` has landed?
-        mbar_wait(bars_s + 8 * (it % NB), (it / NB) & 1);
+        mbar_wait(bars_s + 8 * bi, bpar);
         if (in_dom) {
             Ring<NFZ, NFC> r;
 #pragma unroll
-            for (int m = 0; m < 7; ++m) r.p[m] = zring + ((it + m) % NZS) * ZSTAGE + cell;
-            r.q = cring + (it % NCS) * CSTAGE + cell;
-            epi.apply(r, m0 + (long long)k * g.sz, i, j, k, cur);
+            for (int w = 0; w < 7; ++w) {
+                int st = zb + w;
+                st = (st >= NZS) ? st - NZS : st;
+                r.p[w] = zring + st * ZSTAGE + cell;
+            }
+            r.q = cring + cb * CSTAGE + cell;
+            r.s = sring + cb * SSTAGE + tid;
+            epi.apply(r, m, i, j, k, cur);
         }
         cur = nxt;
+        m += g.sz;
+        zb = (zb + 1 == NZS) ? 0 : zb + 1;
+        cb = (cb + 1 == NCS) ? 0 : cb + 1;
+        if (++bi == NB) bi = 0, bpar ^= 1u;
     }
     __syncthreads();
     epi.finish(tid, zring);
@@ -199,12 +225,12 @@ __global__ void __launch_bounds__(MNT, MINB)
 // zmode: ZFULL whole slab | ZINTERIOR planes [zedge, nz - zedge) | ZBOUNDARY the two end chunks
 enum { ZFULL = 0, ZINTERIOR = 1, ZBOUNDARY = 2 };
 
-template <int NFZ, int NFC, int P, class Epi, int MINB>
-int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC>& maps, const Epi& epi,
-                 int zmode = ZFULL, int zedge = 0) {
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0>
+int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS>& maps,
+                 const Epi& epi, int zmode = ZFULL, int zedge = 0) {
     static bool attr_set = false;
-    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB>;
-    constexpr int smem = march_smem_bytes<NFZ, NFC, P>();
+    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB, NFS>;
+    constexpr int smem = march_smem_bytes<NFZ, NFC, P, NFS>();
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
             cudaSuccess)

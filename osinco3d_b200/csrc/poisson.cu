@@ -182,6 +182,7 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         std::swap(s->base[O3D_F_PP], s->base[O3D_F_PP2]);
         std::swap(s->tmap[O3D_F_PP], s->tmap[O3D_F_PP2]);
         std::swap(s->tmap_sor[O3D_F_PP], s->tmap_sor[O3D_F_PP2]);
+        std::swap(s->tmap_st[O3D_F_PP], s->tmap_st[O3D_F_PP2]);
         std::swap(s->tmap_sor_ok[O3D_F_PP], s->tmap_sor_ok[O3D_F_PP2]);
     }
     touch(s, O3D_F_PP);

@@ -4,6 +4,7 @@
 //             reference; here 3 reads + 1 write = 32 B/pt.  odd/even closure = ghost parity.
 //   CorrEpi (march engine): u = u* - dt grad p with the NaN / >1000 guard fused in
 //             (src/integration.f90:298-325).  pp(1)+u*(3) reads, u(3) writes = 56 B/pt.
+//             u* arrives through TMA stream fields (32 x 8 boxes, 3 planes ahead).
 #include "kernels.h"
 #include "march.cuh"
 
@@ -57,7 +58,6 @@ struct DivEpi {
 
 template <bool S2>
 struct CorrEpi {
-    const double* up[3];
     double* u[3];
     Coef cx, cy, cz;
     double dt;
@@ -70,6 +70,7 @@ struct CorrEpi {
     int nz, bz_lo, bz_hi;
     long long sy_, sz_;
     bool mx, my, mz_lo, mz_hi;  // mirrored sides
+    typedef NoPre Pre;
     __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j) {
         ix = image_offsets(i, g.nx, g.bx, g.bx);
         iy = image_offsets(j, g.ny, g.by, g.by);
@@ -78,25 +79,18 @@ struct CorrEpi {
         mx = g.bx == BM_MIRROR, my = g.by == BM_MIRROR;
         mz_lo = g.bz_lo == BM_MIRROR, mz_hi = g.bz_hi == BM_MIRROR;
     }
-    struct Pre {
-        double v[3];
-    };
-    __device__ __forceinline__ Pre prefetch(long long m, bool ok) const {
-        Pre p;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) p.v[c] = ok ? __ldg(up[c] + m) : 0.0;
-        return p;
-    }
+    __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
+    // z-field 0 = pp (7-plane window); stream fields 0..2 = u* (TMA, 3 planes ahead)
     __device__ __forceinline__ void apply(const Ring<1>& r, long long m, int, int, int k,
-                                          const Pre& pre) {
+                                          const Pre&) {
         // src/integration.f90:298-300 (derxp, deryp, derzp)
         const double dpdx = r.d1x(0, cx);
         const double dpdy = r.d1y(0, cy);
         const double dpdz = S2 ? 0.0 : r.d1z(0, cz);
         // src/integration.f90:304-306
-        const double u0 = pre.v[0] - dt * dpdx;
-        const double u1 = pre.v[1] - dt * dpdy;
-        const double u2 = pre.v[2] - dt * dpdz;
+        const double u0 = r.st(0) - dt * dpdx;
+        const double u1 = r.st(1) - dt * dpdy;
+        const double u2 = r.st(2) - dt * dpdz;
         u[0][m] = u0;
         u[1][m] = u1;
         u[2][m] = u2;
@@ -148,20 +142,20 @@ int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx
 }
 
 template <bool S2>
-static int launch_corr_t(cudaStream_t st, const Geom& g, const FieldRef& pp,
-                         const double* const* up, double* const* u, const Coef& cx,
-                         const Coef& cy, const Coef& cz, double dt, int* flag, int zmode,
-                         int zedge) {
+static int launch_corr_t(cudaStream_t st, const Geom& g, const FieldRef& pp, const FieldRef* up,
+                         double* const* u, const Coef& cx, const Coef& cy, const Coef& cz,
+                         double dt, int* flag, int zmode, int zedge) {
     CorrEpi<S2> e;
-    for (int c = 0; c < 3; ++c) e.up[c] = up[c], e.u[c] = u[c];
+    for (int c = 0; c < 3; ++c) e.u[c] = u[c];
     e.cx = cx, e.cy = cy, e.cz = cz;
     e.dt = dt, e.flag = flag, e.sim2d = g.sim2d, e.bad = 0;
-    MarchMaps<1> m;
+    MarchMaps<4> m;
     m.m[0] = *pp.tm;
-    return launch_march<1, 0, 1, CorrEpi<S2>, 3>(st, g, m, e, zmode, zedge);
+    for (int c = 0; c < 3; ++c) m.m[1 + c] = *up[c].tms;
+    return launch_march<1, 0, 3, CorrEpi<S2>, 3, 3>(st, g, m, e, zmode, zedge);
 }
 
-int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const double* const* up,
+int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const FieldRef* up,
                 double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
                 int* flag, int zmode, int zedge) {
     return g.sim2d ? launch_corr_t<true>(st, g, pp, up, u, cx, cy, cz, dt, flag, zmode, zedge)

@@ -29,6 +29,7 @@ struct o3d_session {
     double* base[O3D_F_COUNT];       // allocation start (ghosts included)
     CUtensorMap tmap[O3D_F_COUNT];   // 40 x 14 x 1 boxes for the march engine
     CUtensorMap tmap_sor[O3D_F_COUNT];  // 36 x 20 x 1 boxes for the fused SOR pass (lazy)
+    CUtensorMap tmap_st[O3D_F_COUNT];   // 32 x 8 x 1 boxes: stream operands of the march engine
     unsigned char tmap_sor_ok[O3D_F_COUNT];
     // ghost-cell state per field: which axes currently hold a valid closure and with which
     // parity bits (bit a: odd along axis a).  Producers / uploads reset gaxes to 0.
