@@ -14,17 +14,30 @@ struct FieldRef {
     const CUtensorMap* tms;  // 32 x 8 x 1 boxes (tile only: stream operands)
 };
 
-// z-chunking heuristic shared by the z-marching kernels: enough CTAs for several waves on
-// 148 SMs x 2 resident CTAs, but chunks of >= 32 planes so that the 6 extra window planes per
-// chunk stay a small overhead.
-inline int pick_zchunk(int tiles_xy, int nz) {
-    const int target_ctas = 148 * 2 * 4;
-    int nchunks = (target_ctas + tiles_xy - 1) / tiles_xy;
-    int max_chunks = nz / 32;
+// z-chunking shared by the z-marching kernels.  A CTA marches over one chunk of `zchunk` planes
+// and pays `extra` additional plane loads (stencil window / pipeline prologue) per chunk.  CTAs
+// are scheduled dynamically on `slots` resident positions (148 SMs x CTAs per SM), so in units of
+// one plane per slot the run time is about
+//     tiles * nch * (zchunk + extra) / slots   +   (zchunk + extra) / 2
+// (throughput term + half a chunk of tail): more chunks shorten the tail and balance the SMs,
+// fewer chunks save overhead planes.  The number of chunks minimises that estimate.
+inline int pick_zchunk_slots(int tiles_xy, int nz, int slots, int extra) {
+    int best = nz;
+    double best_cost = 1e300;
+    int max_chunks = nz / 16;
     if (max_chunks < 1) max_chunks = 1;
-    if (nchunks > max_chunks) nchunks = max_chunks;
-    if (nchunks < 1) nchunks = 1;
-    return (nz + nchunks - 1) / nchunks;
+    if (max_chunks > 64) max_chunks = 64;
+    for (int nch = 1; nch <= max_chunks; ++nch) {
+        const int zc = (nz + nch - 1) / nch;
+        const int real = (nz + zc - 1) / zc;
+        const double work = (double)tiles_xy * real * (zc + extra);
+        const double cost = work / slots + 0.5 * (zc + extra);
+        if (cost < best_cost - 1e-9) best_cost = cost, best = zc;
+    }
+    return best;
+}
+inline int pick_zchunk(int tiles_xy, int nz, int ctas_per_sm = 2) {
+    return pick_zchunk_slots(tiles_xy, nz, 148 * ctas_per_sm, 6);
 }
 
 // ---- padded-layout maintenance (ghost_kernels.cu) ----

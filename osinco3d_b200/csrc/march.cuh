@@ -253,7 +253,7 @@ int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS
     } else {
         const int span = mg.zhi - mg.zlo;
         if (span <= 0) return 0;
-        mg.zchunk = pick_zchunk(gx * gy, span);
+        mg.zchunk = pick_zchunk(gx * gy, span, MINB);
         gz = (span + mg.zchunk - 1) / mg.zchunk;
     }
     kern<<<dim3(gx, gy, gz), dim3(MNT, 1, 1), smem, st>>>(maps, mg, epi);

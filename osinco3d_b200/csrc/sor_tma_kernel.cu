@@ -13,7 +13,7 @@
 // recomputed from ghost data with the same arithmetic as the interior point it mirrors, so it is
 // bit-identical to it.
 //
-// A CTA (256 threads, each owning an x-pair = one red + one black cell per plane) owns a 32 x 16
+// A CTA (256 threads, each owning a y-pair = one red + one black cell per plane) owns a 32 x 16
 // column and marches in z.  Planes are staged with a 2-cell halo (36 x 20 boxes) in a ring of 7
 // (p) + 5 (rhs) shared-memory stages, two planes prefetched ahead.  At march step k:
 //   red(k+2): tile + its 1-cell ring (ring cells recomputed redundantly instead of waiting for
@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(GNT, 3)
     const double one_m_omega = 1.0 - omega;
 
     const int tid = threadIdx.x;
-    const int px = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.x * GTX, j0 = blockIdx.y * GTY;
     int kb, ke;
     if (a.zmode == 2) {
@@ -131,10 +130,15 @@ __global__ void __launch_bounds__(GNT, 3)
         for (int n = 0; n < GP && n < ngroups; ++n) issue_group(n);
     }
 
-    // own x-pair: cells (2+2px, 3+2px) of row 2+ty; pe = colour of the even member in plane 0
-    const int own = (ty + 2) * GBX + 2 + 2 * px;
-    const int gi = i0 + 2 * px, gj = j0 + ty;
-    const bool in0 = gi < a.nx && gj < a.ny, in1 = gi + 1 < a.nx && gj < a.ny;
+    // Own Y-PAIR: column 2+tx, rows 2+2*typ (member A) and 3+2*typ (member B): one red and one
+    // black cell in every plane.  A warp's lanes address 32 consecutive doubles of two adjacent
+    // rows in a checkerboard; with the even row pitch (36) the two rows fall on complementary
+    // banks, so every shared-memory access of the sweep is conflict-free, and the global stores
+    // are two fully coalesced rows.  pe = colour of member A in global plane 0.
+    const int tx = tid & 31, typ = tid >> 5;
+    const int own = (2 + 2 * typ) * GBX + 2 + tx;
+    const int gi = i0 + tx, gj = j0 + 2 * typ;
+    const bool inA = gi < a.nx && gj < a.ny, inB = gi < a.nx && gj + 1 < a.ny;
     const int pe = (gi + gj + a.gz0) & 1;
     // ring-1 pairs (48 threads): each pair holds exactly one red cell in every plane
     int rcell = -1, rstep = 0, rpar = 0;
@@ -148,11 +152,13 @@ __global__ void __launch_bounds__(GNT, 3)
         rpar = (i0 - 2 + lx + j0 - 2 + ly + a.gz0) & 1;
     }
     // ghost images of the own points in x and y
-    const Img2 ix0 = image_offsets(gi, a.nx, a.bx, a.bx);
-    const Img2 ix1 = image_offsets(gi + 1, a.nx, a.bx, a.bx);
-    const Img2 iy = image_offsets(gj, a.ny, a.by, a.by);
-    const long long ylo = iy.lo * a.sy, yhi = iy.hi * a.sy;
-    const bool xy_img = (ix0.lo | ix0.hi | ix1.lo | ix1.hi | iy.lo | iy.hi) != 0;
+    const Img2 ix = image_offsets(gi, a.nx, a.bx, a.bx);
+    const Img2 iyA = image_offsets(gj, a.ny, a.by, a.by);
+    const Img2 iyB = image_offsets(gj + 1, a.ny, a.by, a.by);
+    const bool xy_img = (ix.lo | ix.hi | iyA.lo | iyA.hi | iyB.lo | iyB.hi) != 0;
+    // planes whose points have z images (walls / periodic wrap handled by this rank)
+    const int zimg_lo = (a.bz_lo == BM_MIRROR || a.bz_hi == BM_WRAP) ? R : -1;      // k <= zimg_lo
+    const int zimg_hi = (a.bz_hi == BM_MIRROR || a.bz_lo == BM_WRAP) ? a.nz - 1 - R : a.nz;
 
     double dmax = 0.0;
     // SOR update of cell c of plane S0 (src/poisson.f90:95-102, "/ A" as "* (1/A)": this ordering
@@ -176,9 +182,10 @@ __global__ void __launch_bounds__(GNT, 3)
     auto red_plane = [&](int q, int sm, int s0, int s1, int rs, bool counted) {
         double* S0 = sp + s0 * GPL;
         const double *Sm = sp + sm * GPL, *Sp = sp + s1 * GPL, *Rr = sr + rs * GPL;
-        const int r = (pe + q) & 1;  // which member of the own pair is red in plane q
+        const int r = (pe + q) & 1;  // 0: member A is red in plane q, 1: member B
         double d;
-        const double v = update(Sm, S0, Sp, Rr, own + r, d);
+        const int c = own + r * GBX;
+        const double v = update(Sm, S0, Sp, Rr, c, d);
         if (rcell >= 0) {  // warps 0 and 1 only
             double dr;
             const int rc = rcell + (((rpar + q) & 1) ? rstep : 0);
@@ -186,8 +193,8 @@ __global__ void __launch_bounds__(GNT, 3)
         }
         // (a red cell has no red neighbour: every read above is of a black cell or of the cell's
         // own centre, every write below of a red cell owned by exactly one thread)
-        S0[own + r] = v;
-        if (counted && (r ? in1 : in0)) dmax = fmax(dmax, d);
+        S0[c] = v;
+        dmax = fmax(dmax, (counted && (r ? inB : inA)) ? d : 0.0);
     };
 
     mbar_wait(bars_s, 0);  // group 0: p planes kb-2 .. kb+3 in stages 0 .. 5, rhs kb-1 .. kb+2 in 0 .. 3
@@ -198,32 +205,37 @@ __global__ void __launch_bounds__(GNT, 3)
     int p_m1 = 1, p_0 = 2, p_1 = 3, p_2 = 4, p_3 = 5;  // stages of planes k-1 .. k+3 (k = kb)
     int r_0 = 1, r_2 = 3;                              // stages of rhs planes k, k+2
     double* outp = a.p_new + (long long)kb * a.sz + (long long)gj * a.sy + gi;
-    const long long ylo_z = ylo, yhi_z = yhi;
+    int bi = 1 % GNB;          // barrier index / phase of group n = 1
+    uint32_t bpar = 0;
     for (int k = kb; k < ke; ++k) {
         const int n = k - kb;
         __syncthreads();  // step k-1 done: its oldest stages may be refilled; red(k+1) visible
         if (tid == 0 && n + GP < ngroups) issue_group(n + GP);
-        if (n >= 1 && n < ngroups) mbar_wait(bars_s + 8 * (n % GNB), (n / GNB) & 1);
+        if (n >= 1) {
+            if (n < ngroups) mbar_wait(bars_s + 8 * bi, bpar);
+            if (++bi == GNB) bi = 0, bpar ^= 1u;
+        }
         if (k + 2 <= ke) red_plane(k + 2, p_1, p_2, p_3, r_2, k + 2 < ke);
         {
             // black member of the own pair in plane k: all six neighbours hold new red values
-            const int r = (pe + k) & 1;
+            const int r = (pe + k) & 1;  // member r is red, member 1-r black
             const double* S0 = sp + p_0 * GPL;
             double d;
             const double vb = update(sp + p_m1 * GPL, S0, sp + p_1 * GPL, sr + r_0 * GPL,
-                                     own + 1 - r, d);
-            const double vred = S0[own + r];
-            if (r ? in0 : in1) dmax = fmax(dmax, d);
-            const double v0 = r ? vb : vred, v1 = r ? vred : vb;
-            if (in1) {
-                *reinterpret_cast<double2*>(outp) = make_double2(v0, v1);
-            } else if (in0) {
-                outp[0] = v0;
-            }
-            const Img2 iz = image_offsets(k, a.nz, a.bz_lo, a.bz_hi);
-            if (xy_img || (iz.lo | iz.hi)) {
-                if (in0) store_images(outp, 0, v0, ix0, ylo_z, yhi_z, iz.lo * a.sz, iz.hi * a.sz);
-                if (in1) store_images(outp, 1, v1, ix1, ylo_z, yhi_z, iz.lo * a.sz, iz.hi * a.sz);
+                                     own + (1 - r) * GBX, d);
+            const double vred = S0[own + r * GBX];
+            dmax = fmax(dmax, (r ? inA : inB) ? d : 0.0);
+            const double vA = r ? vb : vred, vB = r ? vred : vb;
+            if (inA) outp[0] = vA;
+            if (inB) outp[a.sy] = vB;
+            if (xy_img || k <= zimg_lo || k >= zimg_hi) {  // boundary-adjacent points only
+                const Img2 iz = image_offsets(k, a.nz, a.bz_lo, a.bz_hi);
+                if (inA)
+                    store_images(outp, 0, vA, ix, iyA.lo * a.sy, iyA.hi * a.sy, iz.lo * a.sz,
+                                 iz.hi * a.sz);
+                if (inB)
+                    store_images(outp, a.sy, vB, ix, iyB.lo * a.sy, iyB.hi * a.sy, iz.lo * a.sz,
+                                 iz.hi * a.sz);
             }
         }
         outp += a.sz;
@@ -269,14 +281,8 @@ int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_m
     } else {
         const int span = f.zhi - f.zlo;
         if (span <= 0) return 0;
-        // 5 extra planes per chunk: keep chunks long, but fill 148 SMs x 3 CTAs a few times
-        const int target = 148 * 3 * 3;
-        int nch = (target + gx * gy - 1) / (gx * gy);
-        int maxch = span / 40;
-        if (maxch < 1) maxch = 1;
-        if (nch > maxch) nch = maxch;
-        if (nch < 1) nch = 1;
-        f.zchunk = (span + nch - 1) / nch;
+        // 5 extra planes per chunk (pipeline prologue), 3 CTAs per SM
+        f.zchunk = pick_zchunk_slots(gx * gy, span, 148 * 3, 5);
         gz = (span + f.zchunk - 1) / f.zchunk;
     }
     sor_tma_kernel<<<dim3(gx, gy, gz), GNT, GSMEM, st>>>(maps, f, ctrl);

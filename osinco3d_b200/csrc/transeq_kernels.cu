@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) transeq_clip_kernel(const Geom g,
 
 int transeq_blocks(const Geom& g) {
     const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
-    const int zc = pick_zchunk(gx * gy, g.nz);
+    const int zc = pick_zchunk(gx * gy, g.nz, 3);  // same chunking as launch_march<..., MINB = 3>
     return gx * gy * ((g.nz + zc - 1) / zc);
 }
 
