@@ -417,15 +417,19 @@ def main():
             stages[k] = {"launches": int(cnt), "ms_per_launch": ms / cnt, "bytes_per_pt": b,
                          "gbs": b * nloc / (ms / cnt * 1e-3) / 1e9}
     ms_sor, sweeps = tm["sor"]
-    # fused single-pass red+black kernel unless an odd periodic extent forces the 4-class sweep
-    fused = not (bc[0] == 0 and (n % 2 or nz % 2))
+    # fused single-pass red+black kernel; with an odd periodic extent (grid not 2-colourable) the
+    # pass is followed by two thin seam-class launches (inside the same span), unless the in-place
+    # 4-class sweeps are forced with O3D_SOR_SEAM=inplace
+    seams = bc[0] == 0 and (n % 2 or nz % 2)
+    fused = not (seams and os.environ.get("O3D_SOR_SEAM") == "inplace")
     if sweeps:
         nl = sweeps if fused else 2 * sweeps
         bpp = B_SOR_FUSED if fused else B_SOR_HALF
         stages["sor"] = {"launches": int(nl), "ms_per_launch": ms_sor / nl, "bytes_per_pt": bpp,
                          "gbs": bpp * nloc / (ms_sor / nl * 1e-3) / 1e9,
                          "iterations_per_step": sweeps / K,
-                         "kernel": "sor_tma_kernel" if fused else "sor_rb_kernel"}
+                         "kernel": ("sor_tma_kernel<seam> + 2 x sor_seam_kernel" if seams else
+                                    "sor_tma_kernel") if fused else "sor_rb_kernel"}
     for k in stages:
         stages[k]["frac"] = stages[k]["gbs"] / peak
         stages[k]["share_of_step"] = stages[k]["ms_per_launch"] * stages[k]["launches"] / ms_dev

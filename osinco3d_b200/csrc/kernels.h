@@ -140,8 +140,11 @@ struct SorArgs {
     int seam_x, seam_y, seam_z;  // odd periodic extents: last plane is a seam
     int gnz;
 };
-// one colour class: colour in {0,1}, seam_class in {0,1} (popcount parity of the seam mask)
-int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl);
+// one colour class: colour in {0,1}, seam_class in {0,1} (popcount parity of the seam mask);
+// images != 0 (seam class only): also store the ghost images of every point written, so the
+// sweep can follow the fused TMA pass on its output buffer
+int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl,
+                  int images = 0);
 // fused red+black iteration (one pass, ping-pong p_old -> p_new); needs a 2-colourable grid
 // zmode / zedge: split launch as for the march kernels (0 = whole slab)
 int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,

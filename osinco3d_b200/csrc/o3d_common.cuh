@@ -97,6 +97,28 @@ __host__ __device__ __forceinline__ Img2 image_offsets(int p, int n, int mode_lo
     return r;
 }
 
+// store v at element m and at every ghost image of the point (faces, edges, corners)
+__device__ __forceinline__ void store_images(double* __restrict__ q, long long m, double v,
+                                             const Img2& ix, long long ylo, long long yhi,
+                                             long long zlo, long long zhi) {
+    const long long xo[3] = {0, ix.lo, ix.hi};
+    const long long yo[3] = {0, ylo, yhi};
+    const long long zo[3] = {0, zlo, zhi};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c && !zo[c]) continue;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (b && !yo[b]) continue;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (a && !xo[a]) continue;
+                if (a | b | c) q[m + xo[a] + yo[b] + zo[c]] = v;
+            }
+        }
+    }
+}
+
 // Coefficients exactly as the reference computes them.
 struct Coef {
     double a1, b1, c1;  // src/derivation.f90:26-30   1,9,45 / (60 d)

@@ -66,10 +66,18 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     O3D_CUDA_CHECK(cudaMemcpyAsync(s->ctrl_d, h, sizeof(SorCtrl), cudaMemcpyHostToDevice, s->st));
     const bool seams = a.seam_x || a.seam_y || a.seam_z;
     const bool wavefront = (c.sor_order == O3D_SOR_LEXI_WAVEFRONT);
-    // fast path: fused red+black pass with ping-pong buffers (needs a 2-colourable grid).
-    // O3D_SOR_FUSED=legacy selects the first-generation kernel (index maps, register staging).
-    const bool fused = !wavefront && !seams;
-    static const bool legacy = getenv("O3D_SOR_FUSED") && !strcmp(getenv("O3D_SOR_FUSED"), "legacy");
+    // fast path: fused red+black pass with ping-pong buffers.  On a grid that is not
+    // 2-colourable (odd periodic extent) the TMA pass sweeps the two even seam classes and
+    // sor_seam_kernel follows with the two thin odd ones on the pass's output buffer -- the same
+    // class order, hence the same bits, as the four in-place half-sweeps, which stay selectable
+    // with O3D_SOR_SEAM=inplace.  O3D_SOR_FUSED=legacy selects the first-generation fused kernel
+    // (index maps, register staging; 2-colourable grids only).
+    // (read per solve, so that a test can switch paths inside one process)
+    const char* e_fused = getenv("O3D_SOR_FUSED");
+    const char* e_seam = getenv("O3D_SOR_SEAM");
+    const bool legacy = e_fused && !strcmp(e_fused, "legacy");
+    const bool seam_inplace = e_seam && !strcmp(e_seam, "inplace");
+    const bool fused = !wavefront && (!seams || (!legacy && !seam_inplace));
     const bool tma = fused && !legacy;
     double* alt = nullptr;
     if (fused) {
@@ -147,6 +155,17 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                     if (rc) return rc;
                 } else if (pass(s->st, 0, 0)) {
                     return O3D_ERR_CUDA;
+                }
+                if (seams) {
+                    // odd seam classes (red, then black) in place on the pass's output; they
+                    // rewrite the ghost images of the points they touch
+                    SorArgs sa = a;
+                    sa.pp = dst;
+                    double* dstf[1] = {dst - ioff};
+                    for (int colour = 0; colour < 2; ++colour) {
+                        if (multi && comm_exchange(s, dstf, 1, 1, zwrap)) return O3D_ERR_COMM;
+                        if (launch_sor_rb(s->st, sa, colour, 1, s->ctrl_d, 1)) return O3D_ERR_CUDA;
+                    }
                 }
             } else {
                 double* ppf[1] = {pp - ioff};

@@ -41,6 +41,7 @@ __device__ __forceinline__ int seam_pop(const SorArgs& a, int i, int j, int gk) 
            (a.seam_z && gk == a.gnz - 1);
 }
 
+template <bool IMAGES = false>
 __device__ __forceinline__ double sor_point(const SorArgs& a, int i, int j, int k,
                                             double omega) {
     const long long sy = a.sy, sz = a.sz;
@@ -60,8 +61,16 @@ __device__ __forceinline__ double sor_point(const SorArgs& a, int i, int j, int 
     const double p_new = (-(a.oneondx2 * (pw + pe)) - a.oneondy2 * (ps + pn) -
                           a.oneondz2 * (pb + pt) + __ldg(a.rhs + m)) *
                          a.invA;
-    a.pp[m] = (1.0 - omega) * pc + omega * p_new;  // :102
-    return fabs(p_new - pc);                       // :100
+    const double v = (1.0 - omega) * pc + omega * p_new;  // :102
+    a.pp[m] = v;
+    if (IMAGES) {
+        // keep the ghost cells of pp coherent (the fused TMA pass reads its closure from them)
+        const Img2 ix = image_offsets(i, a.nx, a.mx, a.mx);
+        const Img2 iy = image_offsets(j, a.ny, a.my, a.my);
+        const Img2 iz = image_offsets(k, a.nz, a.mz_lo, a.mz_hi);
+        store_images(a.pp, m, v, ix, iy.lo * sy, iy.hi * sy, iz.lo * sz, iz.hi * sz);
+    }
+    return fabs(p_new - pc);  // :100
 }
 
 // bulk classes (seam parity 0)
@@ -87,6 +96,7 @@ __global__ void __launch_bounds__(SBX* SBY) sor_rb_kernel(const SorArgs a, int c
 }
 
 // seam classes (seam parity 1): the union of the seam planes, flattened
+template <bool IMAGES>
 __global__ void __launch_bounds__(256) sor_seam_kernel(const SorArgs a, int colour,
                                                        SorCtrl* ctrl, long long nxf,
                                                        long long nyf, long long nzf) {
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(256) sor_seam_kernel(const SorArgs a, int colo
     if (ok) {
         const int gk = a.gz0 + k;
         if (((i + j + gk) & 1) == colour && (seam_pop(a, i, j, gk) & 1))
-            dmax = sor_point(a, i, j, k, omega);
+            dmax = sor_point<IMAGES>(a, i, j, k, omega);
     }
     const double bm = block_max(dmax, red);
     if (threadIdx.x == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
@@ -393,7 +403,8 @@ __global__ void sor_control_kernel(SorCtrl* c, double eps, int kmax, int idyn, d
 
 }  // namespace
 
-int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl) {
+int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl,
+                  int images) {
     if (seam_class == 0) {
         const int half = (a.nx + 1) / 2;
         const int gx = (half + SBX - 1) / SBX, gy = (a.ny + SBY - 1) / SBY;
@@ -408,8 +419,11 @@ int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class,
         const long long nzf = own_z ? (long long)a.nx * a.ny : 0;
         const long long tot = nxf + nyf + nzf;
         if (tot == 0) return 0;
-        sor_seam_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, colour, ctrl, nxf, nyf,
-                                                                       nzf);
+        const unsigned nb = (unsigned)((tot + 255) / 256);
+        if (images)
+            sor_seam_kernel<true><<<nb, 256, 0, st>>>(a, colour, ctrl, nxf, nyf, nzf);
+        else
+            sor_seam_kernel<false><<<nb, 256, 0, st>>>(a, colour, ctrl, nxf, nyf, nzf);
     }
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -22,6 +22,17 @@
 //   black(k): tile, from the NEW red values of planes k-1, k, k+1; plane k of p_new is stored.
 // The two phases touch disjoint data, so ONE __syncthreads per plane suffices.
 // Result == a red half-sweep followed by a black half-sweep (sor_rb_kernel twice), bit for bit.
+//
+// Odd periodic extents (SEAM = true; every shipped periodic grid: 257 x 513 x 129, 241 x 241 x 81).
+// Planes 0 and n-1 of such an axis are same-colour neighbours, so the grid is not 2-colourable;
+// sor_kernels.cu splits the points into four independent classes (colour, parity of the number
+// of seam planes n-1 the point lies on) swept in the order (red, even) (black, even) (red, odd)
+// (black, odd).  This kernel does the first two -- all but ~3/n of the points -- in its single
+// pass and copies the odd-parity points through unchanged; sor_seam_kernel then sweeps the two
+// thin odd classes in place on p_new.  Why one pass still works: an even-parity point's
+// neighbour ACROSS a seam always has odd parity, i.e. still holds its old value for the whole
+// pass, which is exactly what the ghost cells of p_old on that axis contain; so those ghost
+// cells (and the odd-parity ring cells) are simply never red-updated here.
 #include "kernels.h"
 #include "tma.cuh"
 
@@ -40,7 +51,8 @@ struct TmaSorArgs {
     int nx, ny, nz;
     long long sy, sz;
     int bx, by, bz_lo, bz_hi;  // closures (BM_*), for the ghost images of p_new
-    int gz0;
+    int gz0, gnz;
+    int opx, opy, opz;  // odd periodic extent along the axis: plane n-1 is a seam (SEAM kernels)
     int zchunk, zmode, zlo, zhi, zedge;
 };
 
@@ -48,28 +60,7 @@ struct alignas(64) TmaSorMaps {
     CUtensorMap p, rhs;
 };
 
-// store v at element m and at every ghost image of the point (faces, edges, corners)
-__device__ __forceinline__ void store_images(double* __restrict__ q, long long m, double v,
-                                             const Img2& ix, long long ylo, long long yhi,
-                                             long long zlo, long long zhi) {
-    const long long xo[3] = {0, ix.lo, ix.hi};
-    const long long yo[3] = {0, ylo, yhi};
-    const long long zo[3] = {0, zlo, zhi};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        if (c && !zo[c]) continue;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            if (b && !yo[b]) continue;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                if (a && !xo[a]) continue;
-                if (a | b | c) q[m + xo[a] + yo[b] + zo[c]] = v;
-            }
-        }
-    }
-}
-
+template <bool SEAM>
 __global__ void __launch_bounds__(GNT, 3)
     sor_tma_kernel(const __grid_constant__ TmaSorMaps maps, const TmaSorArgs a, SorCtrl* ctrl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -151,6 +142,32 @@ __global__ void __launch_bounds__(GNT, 3)
         rcell = ly * GBX + lx;
         rpar = (i0 - 2 + lx + j0 - 2 + ly + a.gz0) & 1;
     }
+    // SEAM: seam parity of the own pair in x,y (bit 0: member A, bit 1: member B) and of the two
+    // cells of the ring pair (2 bits each: 0 / 1 = parity, 2 = ghost cell of an odd periodic axis,
+    // never updated)
+    int own_par = 0, ring_code = 0;
+    if (SEAM) {
+        const int sx = (a.opx && gi == a.nx - 1) ? 1 : 0;
+        own_par = (sx ^ ((a.opy && gj == a.ny - 1) ? 1 : 0)) |
+                  ((sx ^ ((a.opy && gj + 1 == a.ny - 1) ? 1 : 0)) << 1);
+        if (rcell >= 0) {
+            for (int m = 0; m < 2; ++m) {
+                const int c = rcell + m * rstep;
+                const int ri = i0 - 2 + c % GBX, rj = j0 - 2 + c / GBX;
+                int code = 0;
+                if (a.opx) code = (ri < 0 || ri >= a.nx) ? 2 : (ri == a.nx - 1);
+                if (a.opy && code != 2)
+                    code = (rj < 0 || rj >= a.ny) ? 2 : (code ^ (rj == a.ny - 1 ? 1 : 0));
+                ring_code |= code << (2 * m);
+            }
+        }
+    }
+    // seam state of plane q: 0 / 1 = parity contribution, 2 = ghost plane of an odd periodic z
+    auto zseam = [&](int q) -> int {
+        if (!SEAM || !a.opz) return 0;
+        const int gk = a.gz0 + q;
+        return (gk < 0 || gk >= a.gnz) ? 2 : (gk == a.gnz - 1 ? 1 : 0);
+    };
     // ghost images of the own points in x and y
     const Img2 ix = image_offsets(gi, a.nx, a.bx, a.bx);
     const Img2 iyA = image_offsets(gj, a.ny, a.by, a.by);
@@ -185,10 +202,18 @@ __global__ void __launch_bounds__(GNT, 3)
         const int r = (pe + q) & 1;  // 0: member A is red in plane q, 1: member B
         double d;
         const int c = own + r * GBX;
-        const double v = update(Sm, S0, Sp, Rr, c, d);
-        if (rcell >= 0) {  // warps 0 and 1 only
+        double v = update(Sm, S0, Sp, Rr, c, d);
+        bool ring_on = rcell >= 0;  // warps 0 and 1 only
+        const int rm = (rpar + q) & 1;
+        if (SEAM) {
+            const int zs = zseam(q);
+            if (zs == 2 || (((own_par >> r) ^ zs) & 1)) v = S0[c], d = 0.0;  // odd class: keep
+            const int code = (ring_code >> (2 * rm)) & 3;
+            ring_on = ring_on && zs != 2 && code != 2 && !((code ^ zs) & 1);
+        }
+        if (ring_on) {
             double dr;
-            const int rc = rcell + (((rpar + q) & 1) ? rstep : 0);
+            const int rc = rcell + (rm ? rstep : 0);
             S0[rc] = update(Sm, S0, Sp, Rr, rc, dr);
         }
         // (a red cell has no red neighbour: every read above is of a black cell or of the cell's
@@ -221,8 +246,10 @@ __global__ void __launch_bounds__(GNT, 3)
             const int r = (pe + k) & 1;  // member r is red, member 1-r black
             const double* S0 = sp + p_0 * GPL;
             double d;
-            const double vb = update(sp + p_m1 * GPL, S0, sp + p_1 * GPL, sr + r_0 * GPL,
-                                     own + (1 - r) * GBX, d);
+            double vb = update(sp + p_m1 * GPL, S0, sp + p_1 * GPL, sr + r_0 * GPL,
+                               own + (1 - r) * GBX, d);
+            if (SEAM && (((own_par >> (1 - r)) ^ zseam(k)) & 1))
+                vb = S0[own + (1 - r) * GBX], d = 0.0;  // odd class: swept by sor_seam_kernel
             const double vred = S0[own + r * GBX];
             dmax = fmax(dmax, (r ? inA : inB) ? d : 0.0);
             const double vA = r ? vb : vred, vB = r ? vred : vb;
@@ -256,7 +283,11 @@ int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_m
                    int bz_hi, SorCtrl* ctrl, int zmode, int zedge) {
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(sor_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(sor_tma_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 GSMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(sor_tma_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  GSMEM) != cudaSuccess)
             return 1;
         attr_set = true;
@@ -269,7 +300,8 @@ int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_m
     f.nx = a.nx, f.ny = a.ny, f.nz = a.nz;
     f.sy = a.sy, f.sz = a.sz;
     f.bx = bx, f.by = by, f.bz_lo = bz_lo, f.bz_hi = bz_hi;
-    f.gz0 = a.gz0;
+    f.gz0 = a.gz0, f.gnz = a.gnz;
+    f.opx = a.seam_x, f.opy = a.seam_y, f.opz = a.seam_z;
     const int gx = (a.nx + GTX - 1) / GTX, gy = (a.ny + GTY - 1) / GTY;
     f.zmode = zmode, f.zedge = zedge;
     f.zlo = (zmode == 1) ? zedge : 0;
@@ -285,7 +317,10 @@ int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_m
         f.zchunk = pick_zchunk_slots(gx * gy, span, 148 * 3, 5);
         gz = (span + f.zchunk - 1) / f.zchunk;
     }
-    sor_tma_kernel<<<dim3(gx, gy, gz), GNT, GSMEM, st>>>(maps, f, ctrl);
+    if (f.opx || f.opy || f.opz)
+        sor_tma_kernel<true><<<dim3(gx, gy, gz), GNT, GSMEM, st>>>(maps, f, ctrl);
+    else
+        sor_tma_kernel<false><<<dim3(gx, gy, gz), GNT, GSMEM, st>>>(maps, f, ctrl);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
