@@ -505,6 +505,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->ev_ready = nullptr, s->ev_halo = nullptr;
     s->halo_pending = 0;
     s->flag_pending = 0, s->diverged = 0;
+    s->spec_arm = 0, s->spec_state = 0;
     s->trace_on = 0, s->step_count = 0;
     s->trace_step = getenv("O3D_TRACE") ? atoi(getenv("O3D_TRACE")) : -1;
     s->sw_a = nullptr, s->sw_b = nullptr;
@@ -644,6 +645,7 @@ int o3d_sync(o3d_session* s) {
     poll_flag(s);
     if (s->diverged) {
         s->diverged = 0;
+        cudaMemsetAsync(s->flag_d, 0, sizeof(int), s->st);
         set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
         return O3D_ERR_DIVERGED;
     }
@@ -873,6 +875,42 @@ static int correct_velocity_impl(o3d_session* s, bool defer) {
 
 int o3d_s_correct_velocity(o3d_session* s) { return correct_velocity_impl(s, false); }
 
+static void corr_wrote_ghosts(o3d_session* s) {
+    // the correction kernel wrote the natural-parity ghost images of u with the interior
+    const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+    for (int k = 0; k < 3; ++k) {
+        s->gaxes[VEL_IDS[k]] = zhalo ? 0xBu : 0xFu;
+        s->gpar[VEL_IDS[k]] = NAT3[k];
+    }
+}
+
+extern "C++" {
+namespace o3d {
+// Called by sor_solve with the first batch of passes queued and before its host poll: the same
+// correction launch as correct_velocity_impl, but gated on the solver's control block and reading
+// whichever ping-pong buffer holds the final iterate.  The NaN / >1000 flag is NOT cleared here
+// (it is sticky until reported), so the copy below also carries the previous step's verdict.
+int spec_correct_launch(o3d_session* s) {
+    const o3d_config& c = s->cfg;
+    FieldRef up[3] = {fref(s, O3D_F_UX_PRED), fref(s, O3D_F_UY_PRED), fref(s, O3D_F_UZ_PRED)};
+    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
+    FieldRef pp = fref(s, O3D_F_PP), alt = fref(s, O3D_F_PP2);
+    for (int k = 0; k < 3; ++k)
+        if (!up[k].p || !u[k]) return O3D_ERR_CUDA;
+    if (!pp.p || !alt.p) return O3D_ERR_CUDA;
+    span_begin(s, ST_CORR);
+    if (launch_corr(s->st, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d, 0, 0, &alt,
+                    s->ctrl_d))
+        return O3D_ERR_CUDA;
+    span_end(s, ST_CORR, 0);
+    O3D_CUDA_CHECK(
+        cudaMemcpyAsync(s->flag_h, s->flag_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    s->flag_pending = 1;
+    return O3D_OK;
+}
+}  // namespace o3d
+}  // extern "C++"
+
 int o3d_s_transeq(o3d_session* s, int itime) {
     if (!s) return O3D_ERR_INVALID;
     const o3d_config& c = s->cfg;
@@ -923,15 +961,30 @@ int o3d_step(o3d_session* s, int itime, int* iters, double* dmax) {
     trace_mark(s, 0, "step begin");
     if ((rc = o3d_s_predict_velocity(s, itime))) return rc;
     trace_mark(s, 0, "predict done");
-    if ((rc = o3d_s_correct_pression(s, iters, dmax))) return rc;
+    {
+        const char* e = getenv("O3D_SPEC");
+        s->spec_arm = !(e && e[0] == '0');
+    }
+    rc = o3d_s_correct_pression(s, iters, dmax);
+    s->spec_arm = 0;
+    if (rc) return rc;
     trace_mark(s, 0, "pression done");
-    // the guard of the PREVIOUS step's correction was examined at the Poisson solver's host poll
+    // the guard of the PREVIOUS step's correction (and of this step's, if it was queued behind the
+    // SOR passes) was examined at the Poisson solver's host poll
     if (s->diverged) {
         s->diverged = 0;
+        cudaMemsetAsync(s->flag_d, 0, sizeof(int), s->st);
         set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
         return O3D_ERR_DIVERGED;
     }
-    if ((rc = correct_velocity_impl(s, true))) return rc;
+    if (s->spec_state == 2) {
+        // the correction already ran on the device, gated on the solver's exit
+        s->t_cnt[ST_CORR] += 1;
+        corr_wrote_ghosts(s);
+    } else if ((rc = correct_velocity_impl(s, true))) {
+        return rc;
+    }
+    s->spec_state = 0;
     trace_mark(s, 0, "correct done");
     if (s->cfg.nscr == 1 && (rc = o3d_s_transeq(s, itime))) return rc;
     if (s->trace_on) trace_dump(s);

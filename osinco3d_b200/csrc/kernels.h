@@ -87,9 +87,13 @@ int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx
 
 // ---- projection correction (src/integration.f90:257-330) ----
 // flag: device int, OR-ed with 1 when a NaN or a value > 1000 is produced.
+// gate != null: the launch does nothing unless gate->done is set, and reads pp_alt instead of pp
+// when gate->iter is odd (queued behind a batch of ping-pong SOR passes, see sor_solve)
+struct SorCtrl;
 int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const FieldRef* up,
                 double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
-                int* flag, int zmode = 0, int zedge = 0);
+                int* flag, int zmode = 0, int zedge = 0, const FieldRef* pp_alt = nullptr,
+                const SorCtrl* gate = nullptr);
 
 // ---- curl and Q criterion (src/differential_operators.f90:40-108) ----
 int launch_rot(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx, const Coef& cy,

@@ -42,6 +42,11 @@ struct MarchGeom {
     int zmode, zlo, zhi, zedge;
     int sim2d;
     int bx, by, bz_lo, bz_hi;  // closures, for epilogues that also write ghost images
+    // gated launches (NALT = 1): run only if the SOR control block says the solve has finished,
+    // and read z-field 0 from the ping-pong buffer the last pass wrote (alternate tensor map when
+    // the number of passes was odd).  Lets the projection correction be queued BEHIND a batch of
+    // SOR passes without a host round trip in between.
+    const SorCtrl* gate;
 };
 
 // NFZ fields need the 7-plane z window (ring of 7+P stages), NFC fields only the plane being
@@ -106,11 +111,16 @@ struct Ring {
 //   Pre  prefetch(long long m, bool ok) const;    issue their loads (m = element offset)
 //   void apply(const Ring<NFZ,NFC>&, long long m, int i, int j, int k, const Pre&);
 //   void finish(int tid, double* smem);           after the march (block reductions)
-template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0>
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0>
 __global__ void __launch_bounds__(MNT, MINB)
-    march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC + NFS> maps, const MarchGeom g,
+    march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC + NFS + NALT> maps, const MarchGeom g,
                  Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const CUtensorMap* map0 = &maps.m[0];
+    if (NALT) {
+        if (!*((volatile const int*)&g.gate->done)) return;  // solve not finished: do nothing
+        if (*((volatile const int*)&g.gate->iter) & 1) map0 = &maps.m[NFZ + NFC + NFS];
+    }
     constexpr int NZS = 7 + P, NCS = 1 + P, NB = P + 1;
     constexpr int ZSTAGE = NFZ * MFIELD, CSTAGE = NFC * MFIELD, SSTAGE = NFS * MSFIELD;  // doubles
     double* zring = reinterpret_cast<double*>(smem_raw);
@@ -149,8 +159,8 @@ __global__ void __launch_bounds__(MNT, MINB)
         const unsigned st = (unsigned)(plane - (kb - R)) % NZS;
 #pragma unroll
         for (int f = 0; f < NFZ; ++f)
-            tma_load_3d(zring_s + (uint32_t)(st * ZSTAGE + f * MFIELD) * 8, &maps.m[f], bar, cx, cy,
-                        GH + plane);
+            tma_load_3d(zring_s + (uint32_t)(st * ZSTAGE + f * MFIELD) * 8,
+                        (NALT && f == 0) ? map0 : &maps.m[f], bar, cx, cy, GH + plane);
     };
     auto issue_c = [&](int plane, uint32_t bar) {
         const unsigned st = (unsigned)(plane - kb) % NCS;
@@ -225,11 +235,11 @@ __global__ void __launch_bounds__(MNT, MINB)
 // zmode: ZFULL whole slab | ZINTERIOR planes [zedge, nz - zedge) | ZBOUNDARY the two end chunks
 enum { ZFULL = 0, ZINTERIOR = 1, ZBOUNDARY = 2 };
 
-template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0>
-int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS>& maps,
-                 const Epi& epi, int zmode = ZFULL, int zedge = 0) {
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0>
+int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS + NALT>& maps,
+                 const Epi& epi, int zmode = ZFULL, int zedge = 0, const SorCtrl* gate = nullptr) {
     static bool attr_set = false;
-    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB, NFS>;
+    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB, NFS, NALT>;
     constexpr int smem = march_smem_bytes<NFZ, NFC, P, NFS>();
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
@@ -242,6 +252,7 @@ int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS
     mg.sy = g.sy, mg.sz = g.sz;
     mg.sim2d = g.sim2d;
     mg.bx = g.bx, mg.by = g.by, mg.bz_lo = g.bz_lo, mg.bz_hi = g.bz_hi;
+    mg.gate = gate;
     const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
     mg.zmode = zmode, mg.zedge = zedge;
     mg.zlo = (zmode == ZINTERIOR) ? zedge : 0;
@@ -368,6 +379,7 @@ int launch_march_roles(cudaStream_t st, const Geom& g, const MarchMaps<NFZ>& map
     mg.sy = g.sy, mg.sz = g.sz;
     mg.sim2d = g.sim2d;
     mg.bx = g.bx, mg.by = g.by, mg.bz_lo = g.bz_lo, mg.bz_hi = g.bz_hi;
+    mg.gate = nullptr;
     const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
     mg.zmode = zmode, mg.zedge = zedge;
     mg.zlo = (zmode == ZINTERIOR) ? zedge : 0;

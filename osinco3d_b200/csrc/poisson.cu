@@ -121,6 +121,10 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     const long long ioff = interior_offset(s->g);
     const int zwrap = (s->sor_variant != 2);  // _0000 / _0011 wrap in z, _111111 mirrors
     bool rhs_sent = false;
+    // speculative projection: see session.h.  Needs the iterate's closure in the ghost cells of
+    // whichever ping-pong buffer the last pass wrote (TMA passes do that) and no halo exchange.
+    const bool speculate = s->spec_arm && tma && same_bc && !multi && id_pp == O3D_F_PP;
+    s->spec_state = 0;
     while (true) {
         if (launched + batch > c.kmax) batch = c.kmax - launched;
         if (batch < 1) batch = 1;
@@ -185,11 +189,18 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                 return O3D_ERR_CUDA;
         }
         span_end(s, ST_SOR, 0);
+        if (speculate && launched == 0) {
+            const int rc = spec_correct_launch(s);
+            if (rc) return rc;
+            s->spec_state = 1;
+        }
         launched += batch;
         O3D_CUDA_CHECK(
             cudaMemcpyAsync(h, s->ctrl_d, sizeof(SorCtrl), cudaMemcpyDeviceToHost, s->st));
         O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
         poll_flag(s);
+        // the gated correction ran iff the solve had finished within the first batch
+        if (s->spec_state == 1) s->spec_state = h->done ? 2 : 0;
         if (h->done || launched >= c.kmax) break;
         batch = 4;
         if (c.sor_check_every > 0) batch = c.sor_check_every;

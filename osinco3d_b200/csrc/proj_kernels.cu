@@ -144,11 +144,19 @@ int launch_div(cudaStream_t st, const Geom& g, const FieldRef* f, const Coef& cx
 template <bool S2>
 static int launch_corr_t(cudaStream_t st, const Geom& g, const FieldRef& pp, const FieldRef* up,
                          double* const* u, const Coef& cx, const Coef& cy, const Coef& cz,
-                         double dt, int* flag, int zmode, int zedge) {
+                         double dt, int* flag, int zmode, int zedge, const FieldRef* pp_alt,
+                         const SorCtrl* gate) {
     CorrEpi<S2> e;
     for (int c = 0; c < 3; ++c) e.u[c] = u[c];
     e.cx = cx, e.cy = cy, e.cz = cz;
     e.dt = dt, e.flag = flag, e.sim2d = g.sim2d, e.bad = 0;
+    if (gate) {  // gated on the SOR control block; pp or pp_alt by the parity of the pass count
+        MarchMaps<5> m;
+        m.m[0] = *pp.tm;
+        for (int c = 0; c < 3; ++c) m.m[1 + c] = *up[c].tms;
+        m.m[4] = *pp_alt->tm;
+        return launch_march<1, 0, 3, CorrEpi<S2>, 3, 3, 1>(st, g, m, e, zmode, zedge, gate);
+    }
     MarchMaps<4> m;
     m.m[0] = *pp.tm;
     for (int c = 0; c < 3; ++c) m.m[1 + c] = *up[c].tms;
@@ -157,9 +165,11 @@ static int launch_corr_t(cudaStream_t st, const Geom& g, const FieldRef& pp, con
 
 int launch_corr(cudaStream_t st, const Geom& g, const FieldRef& pp, const FieldRef* up,
                 double* const* u, const Coef& cx, const Coef& cy, const Coef& cz, double dt,
-                int* flag, int zmode, int zedge) {
-    return g.sim2d ? launch_corr_t<true>(st, g, pp, up, u, cx, cy, cz, dt, flag, zmode, zedge)
-                   : launch_corr_t<false>(st, g, pp, up, u, cx, cy, cz, dt, flag, zmode, zedge);
+                int* flag, int zmode, int zedge, const FieldRef* pp_alt, const SorCtrl* gate) {
+    return g.sim2d ? launch_corr_t<true>(st, g, pp, up, u, cx, cy, cz, dt, flag, zmode, zedge,
+                                         pp_alt, gate)
+                   : launch_corr_t<false>(st, g, pp, up, u, cx, cy, cz, dt, flag, zmode, zedge,
+                                          pp_alt, gate);
 }
 
 }  // namespace o3d

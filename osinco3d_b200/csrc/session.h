@@ -52,6 +52,11 @@ struct o3d_session {
     // o3d_step does not stall on the NaN / >1000 guard of correct_velocity: the flag copy is left
     // in flight and examined at the next host synchronisation (poll_flag)
     int flag_pending, diverged;
+    // speculative projection (o3d_step; single rank, fused TMA SOR): the correction kernel is
+    // queued right behind the first batch of SOR passes, gated on the device by the solver's
+    // control block, so the GPU does not idle while the host polls for convergence.
+    // spec_arm: o3d_step allows it for this solve; spec_state: 1 = launched, 2 = took effect
+    int spec_arm, spec_state;
     double* partial;       // reduction scratch
     long long partial_n;
     double* scal_d;        // 64 device doubles
@@ -123,6 +128,9 @@ void poll_flag(o3d_session* s);
 void trace_mark(o3d_session* s, int comm, const char* name);
 void span_begin(o3d_session* s, int stage);
 void span_end(o3d_session* s, int stage, long long count);
+
+// gated launch of the projection correction behind the SOR passes already queued (api.cu)
+int spec_correct_launch(o3d_session* s);
 
 // Poisson solvers (poisson.cu)
 int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double* dmax);

@@ -228,3 +228,33 @@ def test_reductions(gpu, O):
     assert abs(ses.reduce("ux", gpu.RED_SUM) - ux.sum()) < 1e-9
     assert ses.function_stats("ux")[:2] == O.function_stats(ux)[:2]
     ses.close()
+
+
+@pytest.mark.parametrize("bc,n,idyn", [((1, 1, 1), 40, 0), ((0, 0, 0), 33, 1), ((0, 1, 0), 36, 1),
+                                       ((0, 0, 0), 32, 0)])
+def test_gated_correction_behind_sor_equals_host_polled_step_bitwise(gpu, O, bc, n, idyn,
+                                                                     monkeypatch):
+    """o3d_step queues the projection correction behind the SOR passes, gated on the device by the
+    solver's control block (no host round trip between solve and correction).  Same kernels, same
+    data: fields, iteration counts and the dynamic omega must equal the host-polled sequence
+    (O3D_SPEC=0) bit for bit -- also when the iteration count changes from step to step, so that
+    the first batch is too short or too long and the pass count is odd or even."""
+    d = ((PI if bc[0] else 2 * PI) / (n - 1), (PI if bc[1] else 2 * PI) / (n - 1),
+         (PI if bc[2] else 2 * PI) / (n - 1))
+    g = O.grid(n, n, n, *d, bc)
+    ux, uy, uz, pp, phi = O.init_tgv(g, nscr=1)
+    res = {}
+    for spec in ("0", "1"):
+        monkeypatch.setenv("O3D_SPEC", spec)
+        cfg = gpu.make_config(n, n, n, *d, bc=bc, re=400.0, dt=0.02 * d[0], itscheme=3, iles=1,
+                              cs=0.17, nscr=1, omega=1.7, eps=1e-6, kmax=500, idyn=idyn)
+        ses = gpu.Session(cfg)
+        ses.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+        iters = [ses.step() for _ in range(7)]
+        res[spec] = (iters, ses.omega, {k: ses.download(k) for k in ("ux", "uy", "uz", "pp", "phi")})
+        ses.close()
+    assert res["0"][0] == res["1"][0], (res["0"][0], res["1"][0])
+    assert res["0"][1] == res["1"][1]
+    assert len(set(res["1"][0])) > 1, res["1"][0]     # iteration counts did vary
+    for k, a in res["0"][2].items():
+        assert np.array_equal(a, res["1"][2][k]), (k, rel_max(a, res["1"][2][k]))
