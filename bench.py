@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=256)
     ap.add_argument("--bc", default="freeslip", choices=["freeslip", "periodic"])
     ap.add_argument("--les", action="store_true")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -32,6 +32,8 @@ struct Api {
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t,
+                              cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -67,6 +69,7 @@ bool load_api() {
     O3D_SYM(Send, "ncclSend")
     O3D_SYM(Recv, "ncclRecv")
     O3D_SYM(AllReduce, "ncclAllReduce")
+    O3D_SYM(Broadcast, "ncclBroadcast")
     O3D_SYM(GroupStart, "ncclGroupStart")
     O3D_SYM(GroupEnd, "ncclGroupEnd")
     O3D_SYM(GetErrorString, "ncclGetErrorString")
@@ -184,6 +187,23 @@ int comm_exchange(o3d_session* s, double* const* bases, int nf, int width, int w
     if (!rc) rc = comm_wait(s);
     span_end(s, ST_HALO, 0);
     return rc;
+}
+
+// Replicate a buffer whose consecutive chunks were produced by different ranks: rank r owns
+// elements [first[r], first[r] + count[r]); after the call every rank holds all of them.  One
+// grouped set of in-place broadcasts on the session stream (multigrid: coarse right-hand sides).
+int comm_allgather_chunks(o3d_session* s, double* buf, const long long* first,
+                          const long long* count) {
+    Comm* c = s->comm;
+    if (!c) return O3D_OK;
+    O3D_NCCL_CHECK(g_api.GroupStart());
+    for (int r = 0; r < c->nranks; ++r) {
+        if (count[r] <= 0) continue;
+        O3D_NCCL_CHECK(g_api.Broadcast(buf + first[r], buf + first[r], (size_t)count[r],
+                                       ncclFloat64_, r, c->nccl, s->st));
+    }
+    O3D_NCCL_CHECK(g_api.GroupEnd());
+    return O3D_OK;
 }
 
 int split_edge(const o3d_session* s) {

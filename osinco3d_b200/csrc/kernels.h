@@ -171,7 +171,9 @@ int launch_sor_wavefront(cudaStream_t st, const SorArgs& a, int h, SorCtrl* ctrl
 struct MgGrid {
     int nx, ny, nz;
     long long sy, sz;     // element strides (level 0: padded field; coarser levels: compact)
-    int mx, my, mz;       // neighbour rule per axis: BM_WRAP | BM_MIRROR
+    int mx, my;           // neighbour rule in x, y: BM_WRAP | BM_MIRROR
+    int mz_lo, mz_hi;     // z: BM_WRAP | BM_MIRROR | BM_HALO (level 0 of a z-slab run: the ghost
+                          // planes of the padded field, filled by the halo exchange)
     double ox, oy, oz;    // 1/d^2 per axis, src/poisson.f90:42-47
     double A, invA;       // -(2ox + 2oy + 2oz), :48-51
 };
@@ -184,10 +186,13 @@ struct MgTables {
 };
 int launch_mg_residual(cudaStream_t st, const MgGrid& g, const double* p, const double* rhs,
                        double* res, unsigned long long* maxbits);
+// coarse planes [ck0, ck0 + nck) only (a z-slab rank restricts the coarse planes it owns; the
+// z entries of t.ridx are then plane offsets relative to the rank's first fine plane)
 int launch_mg_restrict(cudaStream_t st, const MgGrid& f, const MgGrid& c, const MgTables& t,
-                       const double* res, double* rhs_c, double* p_c);
+                       const double* res, double* rhs_c, double* p_c, int ck0, int nck);
+// kz0: global index of the fine grid's plane 0 (z-slab runs; the z tables are global)
 int launch_mg_prolong(cudaStream_t st, const MgGrid& f, const MgGrid& c, const MgTables& t,
-                      const double* e, double* p);
+                      const double* e, double* p, int kz0);
 int launch_mg_coarse(cudaStream_t st, const MgGrid& g, double* p, double* rhs, int sweeps);
 
 // ---- reductions over the interior ----

@@ -16,11 +16,11 @@
 namespace o3d {
 namespace {
 
-__device__ __forceinline__ void mg_nbr(int p, int n, int mode, int& m1, int& p1) {
-    // src/poisson.f90:57-66 (periodic) / :197-206 (mirrored)
+__device__ __forceinline__ void mg_nbr(int p, int n, int mlo, int mhi, int& m1, int& p1) {
+    // src/poisson.f90:57-66 (periodic) / :197-206 (mirrored); BM_HALO: stored ghost plane
     m1 = p - 1, p1 = p + 1;
-    if (p == 0) m1 = (mode == BM_WRAP) ? n - 1 : 1;
-    if (p == n - 1) p1 = (mode == BM_WRAP) ? 0 : n - 2;
+    if (p == 0 && mlo != BM_HALO) m1 = (mlo == BM_WRAP) ? n - 1 : 1;
+    if (p == n - 1 && mhi != BM_HALO) p1 = (mhi == BM_WRAP) ? 0 : n - 2;
 }
 
 __global__ void __launch_bounds__(256) mg_residual_kernel(const MgGrid g,
@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(256) mg_residual_kernel(const MgGrid g,
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int j = (int)(row % g.ny), k = (int)(row / g.ny);
         int jm, jp, km, kp;
-        mg_nbr(j, g.ny, g.my, jm, jp);
-        mg_nbr(k, g.nz, g.mz, km, kp);
+        mg_nbr(j, g.ny, g.my, g.my, jm, jp);
+        mg_nbr(k, g.nz, g.mz_lo, g.mz_hi, km, kp);
         const long long base = (long long)k * g.sz + (long long)j * g.sy;
         const double* ps = p + (long long)k * g.sz + (long long)jm * g.sy;
         const double* pn = p + (long long)k * g.sz + (long long)jp * g.sy;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) mg_residual_kernel(const MgGrid g,
         const double* pt = p + (long long)kp * g.sz + (long long)j * g.sy;
         for (int i = threadIdx.x; i < g.nx; i += blockDim.x) {
             int im, ip;
-            mg_nbr(i, g.nx, g.mx, im, ip);
+            mg_nbr(i, g.nx, g.mx, g.mx, im, ip);
             const double lp = g.ox * (p[base + im] + p[base + ip]) + g.oy * (ps[i] + pn[i]) +
                               g.oz * (pb[i] + pt[i]) + g.A * p[base + i];
             const double r = __ldg(rhs + base + i) - lp;
@@ -62,10 +62,11 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(const MgGrid f, const 
                                                           const MgTables t,
                                                           const double* __restrict__ res,
                                                           double* __restrict__ rhs_c,
-                                                          double* __restrict__ p_c) {
-    const long long rows = (long long)c.ny * c.nz;
+                                                          double* __restrict__ p_c, int ck0,
+                                                          int nck) {
+    const long long rows = (long long)c.ny * nck;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-        const int cj = (int)(row % c.ny), ck = (int)(row / c.ny);
+        const int cj = (int)(row % c.ny), ck = ck0 + (int)(row / c.ny);
         const long long cbase = (long long)ck * c.sz + (long long)cj * c.sy;
         for (int ci = threadIdx.x; ci < c.nx; ci += blockDim.x) {
             double acc = 0.0;
@@ -101,15 +102,15 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(const MgGrid f, const 
 __global__ void __launch_bounds__(256) mg_prolong_kernel(const MgGrid f, const MgGrid c,
                                                          const MgTables t,
                                                          const double* __restrict__ e,
-                                                         double* __restrict__ p) {
+                                                         double* __restrict__ p, int kz0) {
     const long long rows = (long long)f.ny * f.nz;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int j = (int)(row % f.ny), k = (int)(row / f.ny);
-        const int j0 = __ldg(t.c0[1] + j), k0 = __ldg(t.c0[2] + k);
+        const int j0 = __ldg(t.c0[1] + j), k0 = __ldg(t.c0[2] + kz0 + k);
         int j1 = j0 + 1, k1 = k0 + 1;
         if (j1 >= c.ny) j1 = (c.my == BM_WRAP) ? 0 : c.ny - 1;
-        if (k1 >= c.nz) k1 = (c.mz == BM_WRAP) ? 0 : c.nz - 1;
-        const double wy = __ldg(t.w[1] + j), wz = __ldg(t.w[2] + k);
+        if (k1 >= c.nz) k1 = (c.mz_lo == BM_WRAP) ? 0 : c.nz - 1;
+        const double wy = __ldg(t.w[1] + j), wz = __ldg(t.w[2] + kz0 + k);
         const double* e00 = e + (long long)k0 * c.sz + (long long)j0 * c.sy;
         const double* e10 = e + (long long)k0 * c.sz + (long long)j1 * c.sy;
         const double* e01 = e + (long long)k1 * c.sz + (long long)j0 * c.sy;
@@ -142,14 +143,14 @@ __global__ void __launch_bounds__(CNT) mg_coarse_kernel(const MgGrid g, double* 
     const int tid = threadIdx.x;
     const long long n = (long long)g.nx * g.ny * g.nz;
     const int seam_x = (g.mx == BM_WRAP) && (g.nx & 1), seam_y = (g.my == BM_WRAP) && (g.ny & 1),
-              seam_z = (g.mz == BM_WRAP) && (g.nz & 1);
+              seam_z = (g.mz_lo == BM_WRAP) && (g.nz & 1);
     double sw = 0.0, sr = 0.0;
     for (long long m = tid; m < n; m += CNT) {
         const int i = (int)(m % g.nx), j = (int)((m / g.nx) % g.ny), k = (int)(m / ((long long)g.nx * g.ny));
         double w = 1.0;
         if (g.mx == BM_MIRROR && (i == 0 || i == g.nx - 1)) w *= 0.5;
         if (g.my == BM_MIRROR && (j == 0 || j == g.ny - 1)) w *= 0.5;
-        if (g.mz == BM_MIRROR && (k == 0 || k == g.nz - 1)) w *= 0.5;
+        if (g.mz_lo == BM_MIRROR && (k == 0 || k == g.nz - 1)) w *= 0.5;
         sw += w;
         sr += w * rhs[(long long)k * g.sz + (long long)j * g.sy + i];
     }
@@ -178,9 +179,9 @@ __global__ void __launch_bounds__(CNT) mg_coarse_kernel(const MgGrid g, double* 
                                 (seam_z && k == g.nz - 1);
                 if (((i + j + k) & 1) != colour || (pop & 1) != sp) continue;
                 int im, ip, jm, jp, km, kp;
-                mg_nbr(i, g.nx, g.mx, im, ip);
-                mg_nbr(j, g.ny, g.my, jm, jp);
-                mg_nbr(k, g.nz, g.mz, km, kp);
+                mg_nbr(i, g.nx, g.mx, g.mx, im, ip);
+                mg_nbr(j, g.ny, g.my, g.my, jm, jp);
+                mg_nbr(k, g.nz, g.mz_lo, g.mz_hi, km, kp);
                 const long long kz = (long long)k * g.sz, jy = (long long)j * g.sy;
                 volatile double* vp = p;
                 const double s6 = g.ox * (vp[kz + jy + im] + vp[kz + jy + ip]) +
@@ -212,16 +213,17 @@ int launch_mg_residual(cudaStream_t st, const MgGrid& g, const double* p, const 
 }
 
 int launch_mg_restrict(cudaStream_t st, const MgGrid& f, const MgGrid& c, const MgTables& t,
-                       const double* res, double* rhs_c, double* p_c) {
-    mg_restrict_kernel<<<blocks_for((long long)c.ny * c.nz), 256, 0, st>>>(f, c, t, res, rhs_c,
-                                                                          p_c);
+                       const double* res, double* rhs_c, double* p_c, int ck0, int nck) {
+    if (nck <= 0) return 0;
+    mg_restrict_kernel<<<blocks_for((long long)c.ny * nck), 256, 0, st>>>(f, c, t, res, rhs_c,
+                                                                         p_c, ck0, nck);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 int launch_mg_prolong(cudaStream_t st, const MgGrid& f, const MgGrid& c, const MgTables& t,
-                      const double* e, double* p) {
-    mg_prolong_kernel<<<blocks_for((long long)f.ny * f.nz), 256, 0, st>>>(f, c, t, e, p);
+                      const double* e, double* p, int kz0) {
+    mg_prolong_kernel<<<blocks_for((long long)f.ny * f.nz), 256, 0, st>>>(f, c, t, e, p, kz0);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

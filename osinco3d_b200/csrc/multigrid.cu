@@ -20,6 +20,7 @@ namespace o3d {
 
 struct MgLevel {
     MgGrid g;
+    int gn[3];  // global extents (level 0 of a z-slab run holds only nz_local planes)
     double d[3];
     double *p = nullptr, *rhs = nullptr, *res = nullptr;  // level 0: p/rhs alias pp/rhs fields
     MgTables t;                                           // to the next coarser level
@@ -33,6 +34,13 @@ struct MgHierarchy {
     int n[3], variant, max_levels;
     double d[3];
     double* res0_base = nullptr;  // padded residual buffer of level 0
+    // z-slab runs (nranks > 1): level 0 is distributed, every coarser level is REPLICATED on all
+    // ranks.  A rank restricts the level-1 planes [ck0, ck0 + nck) whose centre tap it owns --
+    // its residual carries 2 exchanged ghost planes per side, which covers every tap -- and the
+    // planes are then replicated with grouped broadcasts.  Same taps, same order as on one GPU.
+    int ck0 = 0, nck = 0;
+    const int* ridx_z_local = nullptr;        // z restriction taps as local plane offsets
+    std::vector<long long> gfirst, gcount;    // element ranges of the ranks' level-1 chunks
 };
 
 namespace {
@@ -149,26 +157,41 @@ SorArgs smoother_args(const MgLevel& L) {
     a.pp = L.p, a.rhs = L.rhs;
     a.oneondx2 = L.g.ox, a.oneondy2 = L.g.oy, a.oneondz2 = L.g.oz;
     a.A = L.g.A, a.invA = L.g.invA;
-    a.mx = L.g.mx, a.my = L.g.my, a.mz_lo = a.mz_hi = L.g.mz;
+    a.mx = L.g.mx, a.my = L.g.my, a.mz_lo = L.g.mz_lo, a.mz_hi = L.g.mz_hi;
     a.nx = L.g.nx, a.ny = L.g.ny, a.nz = L.g.nz;
     a.sy = L.g.sy, a.sz = L.g.sz;
     a.gz0 = 0, a.gnz = L.g.nz;
     a.seam_x = (a.mx == BM_WRAP) && (a.nx & 1);
     a.seam_y = (a.my == BM_WRAP) && (a.ny & 1);
-    a.seam_z = (L.g.mz == BM_WRAP) && (a.nz & 1);
+    a.seam_z = (L.g.mz_lo == BM_WRAP) && (a.nz & 1);
     return a;
 }
 
-// red-black Gauss-Seidel sweeps (the SOR half-sweep kernels with omega = 1)
-int smooth(o3d_session* s, const MgLevel& L, int sweeps) {
-    const SorArgs a = smoother_args(L);
+// red-black Gauss-Seidel sweeps (the SOR half-sweep kernels with omega = 1).  dist: level 0 of
+// a z-slab run -- global colouring / seam plane, one ghost plane of p exchanged before every
+// class sweep (exactly the multi-rank in-place SOR of sor_solve)
+int smooth(o3d_session* s, const MgLevel& L, int sweeps, bool dist) {
+    SorArgs a = smoother_args(L);
+    double* pf[1] = {nullptr};
+    int zwrap = 0;
+    if (dist) {
+        const SorArgs g = make_sor_args(s, L.p, L.rhs);
+        a.mz_lo = g.mz_lo, a.mz_hi = g.mz_hi;
+        a.gz0 = g.gz0, a.gnz = g.gnz, a.seam_z = g.seam_z;
+        pf[0] = L.p - interior_offset(s->g);
+        zwrap = (s->sor_variant != 2);
+    }
     const bool seams = a.seam_x || a.seam_y || a.seam_z;
     for (int q = 0; q < sweeps; ++q) {
-        for (int colour = 0; colour < 2; ++colour)
+        for (int colour = 0; colour < 2; ++colour) {
+            if (dist && comm_exchange(s, pf, 1, 1, zwrap)) return 1;
             if (launch_sor_rb(s->st, a, colour, 0, s->mg->ctrl)) return 1;
+        }
         if (seams)
-            for (int colour = 0; colour < 2; ++colour)
+            for (int colour = 0; colour < 2; ++colour) {
+                if (dist && comm_exchange(s, pf, 1, 1, zwrap)) return 1;
                 if (launch_sor_rb(s->st, a, colour, 1, s->mg->ctrl)) return 1;
+            }
     }
     return 0;
 }
@@ -179,6 +202,7 @@ int build(o3d_session* s, int max_levels) {
     const int v = s->sor_variant;
     const int modes[3] = {(v == 2) ? BM_MIRROR : BM_WRAP, (v >= 1) ? BM_MIRROR : BM_WRAP,
                           (v == 2) ? BM_MIRROR : BM_WRAP};
+    const bool multi = s->cfg.nranks > 1;
     H->n[0] = s->g.nx, H->n[1] = s->g.ny, H->n[2] = s->g.nz;
     H->d[0] = s->cfg.dx, H->d[1] = s->cfg.dy, H->d[2] = s->cfg.dz;
     H->variant = v, H->max_levels = max_levels;
@@ -191,7 +215,12 @@ int build(o3d_session* s, int max_levels) {
     MgLevel L0;
     L0.g.nx = s->g.nx, L0.g.ny = s->g.ny, L0.g.nz = s->g.nz;
     L0.g.sy = s->g.sy, L0.g.sz = s->g.sz;
-    L0.g.mx = modes[0], L0.g.my = modes[1], L0.g.mz = modes[2];
+    L0.g.mx = modes[0], L0.g.my = modes[1];
+    L0.g.mz_lo = multi ? s->g.bz_lo : modes[2];
+    L0.g.mz_hi = multi ? s->g.bz_hi : modes[2];
+    if (multi && s->g.bz_lo != BM_HALO) L0.g.mz_lo = modes[2];  // wall side of an end rank
+    if (multi && s->g.bz_hi != BM_HALO) L0.g.mz_hi = modes[2];
+    L0.gn[0] = s->g.nx, L0.gn[1] = s->g.ny, L0.gn[2] = s->cfg.nz;
     for (int a = 0; a < 3; ++a) L0.d[a] = H->d[a];
     set_operator(L0.g, L0.d);
     if (cudaMalloc(&H->res0_base, (size_t)s->felems * sizeof(double)) != cudaSuccess) return 1;
@@ -201,7 +230,8 @@ int build(o3d_session* s, int max_levels) {
 
     while ((int)H->lv.size() < max_levels) {
         MgLevel& F = H->lv.back();
-        const int fn[3] = {F.g.nx, F.g.ny, F.g.nz};
+        const int fn[3] = {F.gn[0], F.gn[1], F.gn[2]};
+        const bool from_dist = multi && H->lv.size() == 1;
         int nc[3];
         bool any = false;
         for (int a = 0; a < 3; ++a) {
@@ -218,10 +248,60 @@ int build(o3d_session* s, int max_levels) {
             if (to_device(F, t.c0, &F.t.c0[a]) || to_device(F, t.w, &F.t.w[a]) ||
                 to_device(F, t.ridx, &F.t.ridx[a]) || to_device(F, t.rw, &F.t.rw[a]))
                 return 1;
+            if (a == 2 && from_dist) {
+                // owner of a level-1 plane = the rank that owns its heaviest (centre) fine tap;
+                // every other tap must lie within the 2 exchanged ghost planes of that rank
+                const int P = s->cfg.nranks, gnz = s->cfg.nz, ncz = cn[2];
+                std::vector<int> owner(ncz), local(t.ridx.size(), 0);
+                for (int ck = 0; ck < ncz; ++ck) {
+                    int best = 0;
+                    for (int q = 1; q < 4; ++q)
+                        if (t.rw[4 * ck + q] > t.rw[4 * ck + best]) best = q;
+                    const int centre = t.ridx[4 * ck + best];
+                    int z0r = 0, nzr = 0, r = 0;
+                    for (r = 0; r < P; ++r) {
+                        o3d_slab_partition(gnz, P, r, &z0r, &nzr);
+                        if (centre >= z0r && centre < z0r + nzr) break;
+                    }
+                    owner[ck] = r;
+                    if (ck > 0 && owner[ck] < owner[ck - 1]) {
+                        set_error("multigrid: level-1 plane ownership is not monotone in z");
+                        return 2;
+                    }
+                    if (r != s->cfg.rank) continue;
+                    for (int q = 0; q < 4; ++q) {
+                        if (t.rw[4 * ck + q] == 0.0) continue;
+                        int off = t.ridx[4 * ck + q] - s->z0;
+                        if (modes[2] == BM_WRAP) {  // periodic image inside [-2, nz_local + 2)
+                            off = ((off % gnz) + gnz) % gnz;
+                            if (off >= s->nzl + 2) off -= gnz;
+                        }
+                        if (off < -2 || off >= s->nzl + 2) {
+                            set_error("multigrid: restriction tap %d planes outside the slab", off);
+                            return 2;
+                        }
+                        local[4 * ck + q] = off;
+                    }
+                }
+                H->gfirst.assign(P, 0), H->gcount.assign(P, 0);
+                const long long plane = (long long)cn[0] * cn[1];
+                for (int r = 0; r < P; ++r) {
+                    int a0 = -1, cnt = 0;
+                    for (int ck = 0; ck < ncz; ++ck)
+                        if (owner[ck] == r) {
+                            if (a0 < 0) a0 = ck;
+                            ++cnt;
+                        }
+                    H->gfirst[r] = (a0 < 0 ? 0 : a0) * plane, H->gcount[r] = cnt * plane;
+                    if (r == s->cfg.rank) H->ck0 = a0 < 0 ? 0 : a0, H->nck = cnt;
+                }
+                if (to_device(F, local, &H->ridx_z_local)) return 1;
+            }
         }
         C.g.nx = cn[0], C.g.ny = cn[1], C.g.nz = cn[2];
+        C.gn[0] = cn[0], C.gn[1] = cn[1], C.gn[2] = cn[2];
         C.g.sy = cn[0], C.g.sz = (long long)cn[0] * cn[1];
-        C.g.mx = modes[0], C.g.my = modes[1], C.g.mz = modes[2];
+        C.g.mx = modes[0], C.g.my = modes[1], C.g.mz_lo = C.g.mz_hi = modes[2];
         set_operator(C.g, C.d);
         const size_t n = (size_t)cn[0] * cn[1] * cn[2];
         double* buf = nullptr;
@@ -249,11 +329,8 @@ void mg_destroy(o3d_session* s) {
 
 int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npre, int npost,
              double tol, int* cycles, double* dmax) {
-    if (s->cfg.nranks > 1) {
-        set_error("multigrid is single-GPU in this build; use the SOR solver with z-slabs");
-        return O3D_ERR_UNSUPPORTED;
-    }
     if (s->sor_variant < 0) return O3D_ERR_BC;
+    const bool multi = s->cfg.nranks > 1;
     if (npre < 0 || npost < 0 || npre + npost < 1) {
         set_error("multigrid needs npre + npost >= 1");
         return O3D_ERR_INVALID;
@@ -268,11 +345,13 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
         H = nullptr;
     }
     if (!H) {
-        if (build(s, max_levels)) {
-            set_error("multigrid hierarchy allocation failed: %s",
-                      cudaGetErrorString(cudaGetLastError()));
+        const int brc = build(s, max_levels);
+        if (brc) {
+            if (brc == 1)
+                set_error("multigrid hierarchy allocation failed: %s",
+                          cudaGetErrorString(cudaGetLastError()));
             mg_destroy(s);
-            return O3D_ERR_CUDA;
+            return brc == 1 ? O3D_ERR_CUDA : O3D_ERR_UNSUPPORTED;
         }
         H = s->mg;
     }
@@ -283,11 +362,17 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
     const double absA = fabs(H->lv[0].g.A);
     double last = 0.0, prev = 1e300;
     int cyc = 0;
+    double* ppf[1] = {pp - interior_offset(s->g)};
+    double* resf[1] = {H->res0_base};
+    const int zwrap = (s->sor_variant != 2);
     span_begin(s, ST_SOR);
     for (;; ++cyc) {
         // stopping test on the true residual, same measure as SOR's dmax (src/poisson.f90:100)
         O3D_CUDA_CHECK(cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), s->st));
+        if (multi && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
         if (launch_mg_residual(s->st, H->lv[0].g, pp, rhs, nullptr, maxbits)) return O3D_ERR_CUDA;
+        if (multi && comm_allreduce(s, reinterpret_cast<double*>(maxbits), 1, RED_MAXBITS))
+            return O3D_ERR_COMM;
         O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h, maxbits, sizeof(double), cudaMemcpyDeviceToHost,
                                        s->st));
         O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
@@ -300,12 +385,27 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
         for (int l = 0; l < nl - 1; ++l) {
             MgLevel& F = H->lv[l];
             MgLevel& C = H->lv[l + 1];
-            if (smooth(s, F, npre)) return O3D_ERR_CUDA;
+            const bool dist = multi && l == 0;
+            if (smooth(s, F, npre, dist)) return O3D_ERR_CUDA;
+            if (dist && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
             if (launch_mg_residual(s->st, F.g, F.p, F.rhs, F.res, nullptr)) return O3D_ERR_CUDA;
-            if (launch_mg_restrict(s->st, F.g, C.g, F.t, F.res, C.rhs, C.p)) return O3D_ERR_CUDA;
+            if (dist) {
+                // 2 ghost planes of the residual, restrict the owned level-1 planes, replicate
+                if (comm_exchange(s, resf, 1, 2, zwrap)) return O3D_ERR_COMM;
+                MgTables tl = F.t;
+                tl.ridx[2] = H->ridx_z_local;
+                const size_t nc = (size_t)C.g.nx * C.g.ny * C.g.nz;
+                O3D_CUDA_CHECK(cudaMemsetAsync(C.p, 0, nc * sizeof(double), s->st));
+                if (launch_mg_restrict(s->st, F.g, C.g, tl, F.res, C.rhs, C.p, H->ck0, H->nck))
+                    return O3D_ERR_CUDA;
+                if (comm_allgather_chunks(s, C.rhs, H->gfirst.data(), H->gcount.data()))
+                    return O3D_ERR_COMM;
+            } else if (launch_mg_restrict(s->st, F.g, C.g, F.t, F.res, C.rhs, C.p, 0, C.g.nz)) {
+                return O3D_ERR_CUDA;
+            }
         }
         if (nl == 1) {
-            if (smooth(s, H->lv[0], npre + npost)) return O3D_ERR_CUDA;
+            if (smooth(s, H->lv[0], npre + npost, multi)) return O3D_ERR_CUDA;
         } else {
             MgLevel& B = H->lv[nl - 1];
             if (launch_mg_coarse(s->st, B.g, B.p, B.rhs, MG_COARSE_SWEEPS)) return O3D_ERR_CUDA;
@@ -313,8 +413,10 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
         for (int l = nl - 2; l >= 0; --l) {
             MgLevel& F = H->lv[l];
             MgLevel& C = H->lv[l + 1];
-            if (launch_mg_prolong(s->st, F.g, C.g, F.t, C.p, F.p)) return O3D_ERR_CUDA;
-            if (smooth(s, F, npost)) return O3D_ERR_CUDA;
+            const bool dist = multi && l == 0;
+            if (launch_mg_prolong(s->st, F.g, C.g, F.t, C.p, F.p, dist ? s->z0 : 0))
+                return O3D_ERR_CUDA;
+            if (smooth(s, F, npost, dist)) return O3D_ERR_CUDA;
         }
     }
     span_end(s, ST_SOR, cyc);

@@ -155,6 +155,9 @@ int comm_wait(o3d_session* s);
 int split_edge(const o3d_session* s);
 int launch_overlapped(o3d_session* s, const std::function<int(cudaStream_t, int, int)>& launch);
 int comm_allreduce(o3d_session* s, double* dev, int n, int op /* RED_* */);
+// rank r produced buf[first[r] .. first[r] + count[r]); replicate all chunks on every rank
+int comm_allgather_chunks(o3d_session* s, double* buf, const long long* first,
+                          const long long* count);
 int nccl_unique_id(unsigned char* out128);
 
 }  // namespace o3d

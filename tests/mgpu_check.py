@@ -67,7 +67,7 @@ def main():
         return bytes(idt.cpu().tolist())
 
     cases = [
-        # name, n, nz, bc, iles, nscr, eps, idyn, steps
+        # name, n, nz, bc, iles, nscr, eps, idyn, steps [, multigrid]
         ("freeslip_dns_fusedSOR", 48, 24 * world, (1, 1, 1), 0, 0, 1e-7, 0, 4),
         ("freeslip_les_scalar_dynomega", 40, 16 * world + 1, (1, 1, 1), 1, 1, 1e-6, 1, 4),
         ("periodic_even_fusedSOR", 32, 16 * world, (0, 0, 0), 0, 1, 1e-7, 0, 3),
@@ -78,13 +78,24 @@ def main():
         ("freeslip_overlap_les_scalar", 40, 40 * world + 1, (1, 1, 1), 1, 1, 1e-6, 1, 4),
         ("periodic_overlap_fusedSOR", 32, 36 * world, (0, 0, 0), 0, 0, 1e-7, 0, 3),
         ("mixed_0011_overlap_seamSOR", 33, 34 * world + 1, (0, 1, 0), 0, 0, 1e-6, 0, 3),
+        # multigrid V-cycles (src/integration.f90:244, multigrid = 1): level 0 distributed in z,
+        # coarser levels replicated; nested (even periodic / odd mirrored) and non-nested extents
+        ("freeslip_multigrid", 33, 16 * world + 1, (1, 1, 1), 0, 0, 1e-8, 0, 3, 1),
+        ("periodic_even_multigrid", 32, 16 * world, (0, 0, 0), 0, 1, 1e-8, 0, 3, 1),
+        ("periodic_odd_multigrid_ragged", 33, 16 * world + 3, (0, 0, 0), 1, 0, 1e-8, 0, 3, 1),
+        ("mixed_0011_multigrid", 40, 20 * world + 1, (0, 1, 0), 0, 0, 1e-8, 0, 3, 1),
     ]
-    for name, n, nz, bc, iles, nscr, eps, idyn, steps in cases:
+    only = os.environ.get("O3D_MGPU_ONLY")
+    for case in cases:
+        name, n, nz, bc, iles, nscr, eps, idyn, steps = case[:9]
+        mg = case[9] if len(case) > 9 else 0
+        if only and only not in name:
+            continue
         L = np.pi if bc[0] == 1 else 2 * np.pi
         d = L / (n - 1)
         fields = dict(zip(("ux", "uy", "uz", "pp", "phi"), tgv_like(n, nz, d, bc)))
         kw = dict(bc=bc, re=800.0, cs=0.17, dt=0.02 * d, itscheme=3, iles=iles, nscr=nscr,
-                  omega=1.6, eps=eps, kmax=3000, idyn=idyn)
+                  omega=1.6, eps=eps, kmax=3000, idyn=idyn, multigrid=mg)
         cfg = o3d.make_config(n, n, nz, d, d, d, rank=rank, nranks=world, nccl_id=make_id(), **kw)
         ses = o3d.Session(cfg)
         assert (ses.z0, ses.nz_local) == slab.slab_range(nz, rank, world)
@@ -147,4 +158,15 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:
+        # a rank that fails must not leave its peers blocked inside NCCL: die at once so that
+        # torchrun tears the whole group down
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
