@@ -46,7 +46,9 @@ enum {
     O3D_ERR_ITSCHEME = 5,      /* "itscheme unrecognized" stop, src/integration.f90:99-104     */
     O3D_ERR_DIVERGED = 6,      /* NaN or max(u) > 1000 abort, src/integration.f90:309-325      */
     O3D_ERR_COMM = 7,          /* NCCL / multi-GPU set-up failure                              */
-    O3D_ERR_UNSUPPORTED = 8
+    O3D_ERR_UNSUPPORTED = 8,
+    O3D_ERR_IO = 9             /* "Error opening file" (src/IOfunctions.f90:389-392,
+                                  src/visualization.f90:231-234) or a failed read / write       */
 };
 
 /* boundary flags, src/initialization.f90 (PERIODIC = 0, FREE_SLIP = 1) */
@@ -279,6 +281,30 @@ int o3d_s_function_stats(o3d_session* s, int field, double* stats6);
 int o3d_s_statistics(o3d_session* s, double t, double* out17);
 int o3d_s_rotational(o3d_session* s, int rotx, int roty, int rotz);
 int o3d_s_q_criterion(o3d_session* s, int dst);
+/* sqrt(rotx**2 + roty**2 + rotz**2), the "vort" array of write_all_data
+ * (src/visualization.f90:258-259), in one fused kernel */
+int o3d_s_vorticity_magnitude(o3d_session* s, int dst);
+
+/* ---- field output in the reference's binary formats, straight from device-resident state.
+ * Writes are ASYNCHRONOUS: the call snapshots the fields on the device (the time loop may go
+ * on at once), the D2H copies run on a separate stream and a writer thread does the file I/O.
+ * With z slabs every rank writes its own contiguous byte range of the shared file (call on all
+ * ranks, same path on a shared file system).  o3d_s_io_wait blocks until everything queued has
+ * reached the file and reports the first write error; o3d_session_destroy drains the queue. */
+/* save_fields, src/IOfunctions.f90:360-402: time | nx ny nz | x y z | ux uy uz pp phi */
+int o3d_s_save_fields(o3d_session* s, const char* filename, double time, const double* x,
+                      const double* y, const double* z);
+/* read_fields, src/IOfunctions.f90:404-470; a grid-size mismatch is O3D_ERR_INVALID and nothing
+ * is read (:452-459).  x, y, z: GLOBAL coordinate arrays (nx, ny, nz) */
+int o3d_s_read_fields(o3d_session* s, const char* filename, double* time, double* x, double* y,
+                      double* z);
+/* write_binary, src/visualization.f90:224-241: one raw f64 array */
+int o3d_s_write_binary(o3d_session* s, const char* filename, int field);
+/* write_all_data, src/visualization.f90:243-276: <dir>/ux_<num>.bin uy uz pp vort qcrit
+ * [phi if nscr == 1] [nu_t if iles == 1]; vort and qcrit are computed here (the driver calls
+ * rotational / calculate_Q_criterion just before, src/osinco3d_main.f90:130-133) */
+int o3d_s_write_all_data(o3d_session* s, const char* dir, int num);
+int o3d_s_io_wait(o3d_session* s);
 
 /* current SOR relaxation factor (inout across steps, src/integration.f90:222,247) */
 int o3d_get_omega(const o3d_session* s, double* omega);

@@ -13,10 +13,10 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_BC, ERR_ITSCHEME, ERR_DIVERGED, ERR_COMM, \
-    ERR_UNSUPPORTED = range(9)
+    ERR_UNSUPPORTED, ERR_IO = range(10)
 ERR_NAMES = {1: "O3D_ERR_INVALID", 2: "O3D_ERR_NO_DEVICE", 3: "O3D_ERR_CUDA", 4: "O3D_ERR_BC",
              5: "O3D_ERR_ITSCHEME", 6: "O3D_ERR_DIVERGED", 7: "O3D_ERR_COMM",
-             8: "O3D_ERR_UNSUPPORTED"}
+             8: "O3D_ERR_UNSUPPORTED", 9: "O3D_ERR_IO"}
 
 PERIODIC, FREE_SLIP = 0, 1
 CLOSURE_00, CLOSURE_P11, CLOSURE_I11, CLOSURE_2DSIM = 0, 1, 2, 3
@@ -89,6 +89,12 @@ def lib():
         _lib.o3d_s_statistics.argtypes = [C.c_void_p, C.c_double, dp]
         _lib.o3d_s_rotational.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.o3d_s_q_criterion.argtypes = [C.c_void_p, C.c_int]
+        _lib.o3d_s_vorticity_magnitude.argtypes = [C.c_void_p, C.c_int]
+        _lib.o3d_s_save_fields.argtypes = [C.c_void_p, C.c_char_p, C.c_double, dp, dp, dp]
+        _lib.o3d_s_read_fields.argtypes = [C.c_void_p, C.c_char_p, dp, dp, dp, dp]
+        _lib.o3d_s_write_binary.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        _lib.o3d_s_write_all_data.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        _lib.o3d_s_io_wait.argtypes = [C.c_void_p]
         _lib.o3d_get_omega.argtypes = [C.c_void_p, dp]
         _lib.o3d_set_omega.argtypes = [C.c_void_p, C.c_double]
         _lib.o3d_session_set_poisson.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int,

@@ -498,6 +498,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->partial_n = 0;
     s->comm = nullptr;
     s->mg = nullptr;
+    s->io = nullptr;
     s->timers_on = 0;
     s->use_src = 0;
     for (int q2 = 0; q2 < 6; ++q2) s->t_ms[q2] = 0.0, s->t_cnt[q2] = 0;
@@ -546,6 +547,7 @@ int o3d_session_destroy(o3d_session* s) {
     if (!s) return O3D_OK;
     if (s->st_comm) cudaStreamSynchronize(s->st_comm);
     if (s->st) cudaStreamSynchronize(s->st);
+    io_destroy(s);
     comm_destroy(s);
     mg_destroy(s);
     for (int f = 0; f < O3D_F_COUNT; ++f)
@@ -1088,6 +1090,20 @@ int o3d_s_rotational(o3d_session* s, int rotx, int roty, int rotz) {
     if ((rc = ensure_ghosts(s, VEL_IDS, 3, EVEN3, 0x7u))) return rc;
     if (launch_rot(s->st, s->g, u, s->cx, s->cy, s->cz, r[0], r[1], r[2])) return O3D_ERR_CUDA;
     for (int k = 0; k < 3; ++k) touch(s, rid[k]);
+    return O3D_OK;
+}
+
+int o3d_s_vorticity_magnitude(o3d_session* s, int dst) {
+    if (!s) return O3D_ERR_INVALID;
+    FieldRef u[3] = {fref(s, O3D_F_UX), fref(s, O3D_F_UY), fref(s, O3D_F_UZ)};
+    const int vid = phys_id(s, dst);
+    double* v = field(s, vid);
+    if (!u[0].p || !u[1].p || !u[2].p || !v) return O3D_ERR_CUDA;
+    int rc;
+    // the curl's even closures (src/differential_operators.f90:64-74), as o3d_s_rotational
+    if ((rc = ensure_ghosts(s, VEL_IDS, 3, EVEN3, 0x7u))) return rc;
+    if (launch_vort(s->st, s->g, u, s->cx, s->cy, s->cz, v)) return O3D_ERR_CUDA;
+    touch(s, vid);
     return O3D_OK;
 }
 

@@ -100,6 +100,9 @@ int launch_rot(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx
                const Coef& cz, double* rotx, double* roty, double* rotz);
 int launch_qcrit(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,
                  const Coef& cy, const Coef& cz, double* q);
+// |curl u| as output by write_all_data (src/visualization.f90:258-259); even ghosts as launch_rot
+int launch_vort(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx, const Coef& cy,
+                const Coef& cz, double* vm);
 
 // ---- scalar transport (src/integration.f90:332-468) ----
 struct TranseqArgs {

@@ -9,6 +9,7 @@
 namespace o3d {
 struct Comm;  // z-slab halo exchange + reductions over NCCL (comm.cu)
 struct MgHierarchy;  // level arrays + transfer tables of the V-cycle (multigrid.cu)
+struct IoEngine;     // asynchronous field output: staging buffers, I/O stream, writer thread (io.cu)
 }
 
 struct o3d_session {
@@ -64,6 +65,7 @@ struct o3d_session {
 
     o3d::Comm* comm;
     o3d::MgHierarchy* mg;  // built lazily by mg_solve, cached across steps
+    o3d::IoEngine* io;     // built lazily by the first output call
     int use_src;           // transeq source term uploaded to O3D_F_SCRATCH1
 
     // timers
@@ -137,6 +139,8 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
 int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npre, int npost,
              double tol, int* cycles, double* dmax);
 void mg_destroy(o3d_session* s);
+// drains the output queue, joins the writer thread, frees the staging buffers (io.cu)
+void io_destroy(o3d_session* s);
 // shared with poisson.cu
 SorArgs make_sor_args(o3d_session* s, double* pp, const double* rhs);
 

@@ -255,6 +255,26 @@ struct RotEpi {
     __device__ __forceinline__ void finish(int, double*) {}
 };
 
+// vorticity magnitude as written by write_all_data (src/visualization.f90:258-259):
+// sqrt(rotx**2 + roty**2 + rotz**2) of the curl above, fused -- 32 B/pt instead of curl (48) + a
+// 32 B/pt magnitude pass; same even closure as RotEpi
+struct VortEpi {
+    double* vm;
+    Coefs3 q;
+    int sim2d;
+    typedef NoPre Pre;
+    __device__ __forceinline__ void setup(const MarchGeom&, int, int) {}
+    __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
+    __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int, const Pre&) {
+        const Grad G = gradient(r, q, sim2d);
+        const double rx = G.d[2][1] - G.d[1][2];
+        const double ry = G.d[0][2] - G.d[2][0];
+        const double rz = G.d[1][0] - G.d[0][1];
+        vm[m] = sqrt(rx * rx + ry * ry + rz * rz);
+    }
+    __device__ __forceinline__ void finish(int, double*) {}
+};
+
 struct QEpi {
     double* qc;
     Coefs3 q;
@@ -382,6 +402,13 @@ int launch_rot(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx
     RotEpi e;
     e.rx = rotx, e.ry = roty, e.rz = rotz, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d;
     return launch_march<3, 0, 1, RotEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
+}
+
+int launch_vort(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx, const Coef& cy,
+                const Coef& cz, double* vm) {
+    VortEpi e;
+    e.vm = vm, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d;
+    return launch_march<3, 0, 1, VortEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
 }
 
 int launch_qcrit(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,

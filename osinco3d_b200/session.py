@@ -2,6 +2,7 @@
 main loop (src/osinco3d_main.f90:97-128) kept in HBM across calls.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -137,6 +138,40 @@ class Session:
 
     def q_criterion(self, dst="scratch0"):
         check(lib().o3d_s_q_criterion(self._h, L.FIELD_ID[dst]))
+
+    def vorticity_magnitude(self, dst="scratch0"):
+        check(lib().o3d_s_vorticity_magnitude(self._h, L.FIELD_ID[dst]))
+
+    # -- field output in the reference's binary formats (asynchronous; io_wait() drains) --
+    def save_fields(self, filename, time, x, y, z):
+        """IOfunctions.save_fields, src/IOfunctions.f90:360-402"""
+        x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+        dp = L.dp
+        check(lib().o3d_s_save_fields(self._h, os.fsencode(filename), C.c_double(time),
+                                      x.ctypes.data_as(dp), y.ctypes.data_as(dp),
+                                      z.ctypes.data_as(dp)))
+
+    def read_fields(self, filename):
+        """IOfunctions.read_fields, src/IOfunctions.f90:404-470 -> (time, x, y, z)"""
+        c = self.cfg
+        x, y, z = np.zeros(c.nx), np.zeros(c.ny), np.zeros(c.nz)
+        t = C.c_double(0.0)
+        dp = L.dp
+        check(lib().o3d_s_read_fields(self._h, os.fsencode(filename), C.byref(t),
+                                      x.ctypes.data_as(dp), y.ctypes.data_as(dp),
+                                      z.ctypes.data_as(dp)))
+        return t.value, x, y, z
+
+    def write_binary(self, filename, name):
+        """visualization.write_binary, src/visualization.f90:224-241"""
+        check(lib().o3d_s_write_binary(self._h, os.fsencode(filename), L.FIELD_ID[name]))
+
+    def write_all_data(self, directory, num):
+        """visualization.write_all_data, src/visualization.f90:243-276"""
+        check(lib().o3d_s_write_all_data(self._h, os.fsencode(directory), num))
+
+    def io_wait(self):
+        check(lib().o3d_s_io_wait(self._h))
 
     @property
     def omega(self):

@@ -12,6 +12,7 @@ and red-black SOR iterates alike (identical dmax -> identical exit decisions on 
 Prints one line per case and exits non-zero on any mismatch.  tests/test_gpu_multi.py wraps it.
 """
 import os
+import shutil
 import sys
 
 import numpy as np
@@ -104,6 +105,20 @@ def main():
         stats = ses.statistics()
         red = ses.reduce("ux", o3d.RED_ABSMAX)
         out = {k: ses.download(k) for k in ("ux", "uy", "uz", "pp", "phi", "ux_pred", "rhs")}
+        # shared-file output: every rank writes its own byte range (src/IOfunctions.f90:360-402,
+        # src/visualization.f90:243-276); compared below with the files of the 1-GPU session
+        io_dir = None
+        if name in ("freeslip_les_scalar_dynomega", "mixed_0011_ragged"):
+            io_dir = "/tmp/o3d_mgpu_io_%s_x%d" % (name, world)
+            if rank == 0:
+                shutil.rmtree(io_dir, ignore_errors=True)
+                os.makedirs(io_dir)
+            dist.barrier()
+            xyz = [d * np.arange(m) for m in (n, n, nz)]
+            ses.save_fields(io_dir + "/fields.bin", 0.5, *xyz)
+            ses.write_all_data(io_dir + "/outputs", 3)
+            ses.io_wait()
+            dist.barrier()
         ses.close()
         ok = True
         msg = ""
@@ -114,6 +129,18 @@ def main():
             st1 = one.statistics()
             red1 = one.reduce("ux", o3d.RED_ABSMAX)
             ref = {k: one.download(k) for k in out}
+            if io_dir:
+                one.save_fields(io_dir + "/fields_1gpu.bin", 0.5, *xyz)
+                one.write_all_data(io_dir + "/outputs_1gpu", 3)
+                one.io_wait()
+                pairs = [("fields.bin", "fields_1gpu.bin")] + [
+                    ("outputs/" + f, "outputs_1gpu/" + f)
+                    for f in sorted(os.listdir(io_dir + "/outputs_1gpu"))]
+                for a, b in pairs:
+                    if open(io_dir + "/" + a, "rb").read() != open(io_dir + "/" + b, "rb").read():
+                        ok, msg = False, msg + " file %s differs from the 1-GPU file;" % a
+                msg += " [%d output files byte-identical]" % len(pairs) if ok else ""
+                shutil.rmtree(io_dir, ignore_errors=True)
             one.close()
             if it1 != iters:
                 ok, msg = False, "iterations %s vs single-GPU %s" % (iters, it1)
