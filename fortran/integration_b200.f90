@@ -24,6 +24,12 @@ module integration
 
 contains
 
+  !> the resident session, for the output shims of fortran/output_b200.f90
+  function o3d_session_handle() result(h)
+    type(c_ptr) :: h
+    h = ses
+  end function o3d_session_handle
+
   subroutine o3d_open_session(ux, uy, uz, fux, fuy, fuz, re, adt, bdt, cdt, itscheme, &
        dx, dy, dz, nx, ny, nz, iles, cs, delta)
     real(kind=8), intent(in) :: ux(:,:,:), uy(:,:,:), uz(:,:,:)

@@ -335,6 +335,53 @@ module o3d_b200_c
        real(c_double), value :: omega
        integer(c_int) :: rc
      end function o3d_set_omega
+     function o3d_s_vorticity_magnitude(ses, dst) &
+          bind(C, name="o3d_s_vorticity_magnitude") result(rc)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ses
+       integer(c_int), value :: dst
+       integer(c_int) :: rc
+     end function o3d_s_vorticity_magnitude
+     !--- field output in the reference's binary formats (asynchronous; o3d_s_io_wait drains) ---
+     function o3d_s_save_fields(ses, filename, time, x, y, z) &
+          bind(C, name="o3d_s_save_fields") result(rc)
+       import :: c_int, c_ptr, c_double, c_char
+       type(c_ptr), value :: ses
+       character(kind=c_char), intent(in) :: filename(*)
+       real(c_double), value :: time
+       real(c_double), intent(in) :: x(*), y(*), z(*)
+       integer(c_int) :: rc
+     end function o3d_s_save_fields
+     function o3d_s_read_fields(ses, filename, time, x, y, z) &
+          bind(C, name="o3d_s_read_fields") result(rc)
+       import :: c_int, c_ptr, c_double, c_char
+       type(c_ptr), value :: ses
+       character(kind=c_char), intent(in) :: filename(*)
+       real(c_double), intent(inout) :: time
+       real(c_double), intent(inout) :: x(*), y(*), z(*)
+       integer(c_int) :: rc
+     end function o3d_s_read_fields
+     function o3d_s_write_binary(ses, filename, field) &
+          bind(C, name="o3d_s_write_binary") result(rc)
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: ses
+       character(kind=c_char), intent(in) :: filename(*)
+       integer(c_int), value :: field
+       integer(c_int) :: rc
+     end function o3d_s_write_binary
+     function o3d_s_write_all_data(ses, dir, num) &
+          bind(C, name="o3d_s_write_all_data") result(rc)
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: ses
+       character(kind=c_char), intent(in) :: dir(*)
+       integer(c_int), value :: num
+       integer(c_int) :: rc
+     end function o3d_s_write_all_data
+     function o3d_s_io_wait(ses) bind(C, name="o3d_s_io_wait") result(rc)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ses
+       integer(c_int) :: rc
+     end function o3d_s_io_wait
   end interface
 
 contains
