@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "o3d_common.cuh"
 
 namespace o3d {
@@ -15,18 +17,30 @@ struct FieldRef {
 };
 
 // z-chunking shared by the z-marching kernels.  A CTA marches over one chunk of `zchunk` planes
-// and pays `extra` additional plane loads (stencil window / pipeline prologue) per chunk.  CTAs
-// are scheduled dynamically on `slots` resident positions (148 SMs x CTAs per SM), so in units of
-// one plane per slot the run time is about
+// and pays per chunk the equivalent of `extra` additional planes of its normal per-plane cost
+// (the stencil window / pipeline prologue is loaded but not computed on: for a kernel that moves
+// `streams` values per point of which `nfz` carry a z window, 6 * nfz / streams planes).  CTAs are
+// scheduled dynamically on `slots` resident positions (148 SMs x CTAs per SM), so in units of one
+// plane per slot the run time is about
 //     tiles * nch * (zchunk + extra) / slots   +   (zchunk + extra) / 2
 // (throughput term + half a chunk of tail): more chunks shorten the tail and balance the SMs,
-// fewer chunks save overhead planes.  The number of chunks minimises that estimate.
-inline int pick_zchunk_slots(int tiles_xy, int nz, int slots, int extra) {
+// fewer chunks save overhead planes.  The number of chunks minimises that estimate; measured
+// sweeps over the chunk count at 256^3 and 512^3 (profiles/r1o_nch_sweep.txt) follow it.
+inline int pick_zchunk_slots(int tiles_xy, int nz, int slots, double extra) {
+    {   // tuning override: O3D_NCH_S (SOR pass), O3D_NCH_2 / O3D_NCH_3 (march kernels with 2 / 3
+        // resident CTAs per SM) = number of z chunks
+        const char* e = getenv(extra > 3.0 ? "O3D_NCH_S" : (slots == 148 * 2 ? "O3D_NCH_2" : "O3D_NCH_3"));
+        if (e && atoi(e) > 0) {
+            int nch = atoi(e);
+            if (nch > nz / 8) nch = nz / 8 > 0 ? nz / 8 : 1;
+            return (nz + nch - 1) / nch;
+        }
+    }
     int best = nz;
     double best_cost = 1e300;
-    int max_chunks = nz / 16;
+    int max_chunks = nz / 8;
     if (max_chunks < 1) max_chunks = 1;
-    if (max_chunks > 64) max_chunks = 64;
+    if (max_chunks > 128) max_chunks = 128;
     for (int nch = 1; nch <= max_chunks; ++nch) {
         const int zc = (nz + nch - 1) / nch;
         const int real = (nz + zc - 1) / zc;
@@ -36,8 +50,9 @@ inline int pick_zchunk_slots(int tiles_xy, int nz, int slots, int extra) {
     }
     return best;
 }
-inline int pick_zchunk(int tiles_xy, int nz, int ctas_per_sm = 2) {
-    return pick_zchunk_slots(tiles_xy, nz, 148 * ctas_per_sm, 6);
+// march kernels: nfz fields with a 7-plane z window out of `streams` values moved per point
+inline int pick_zchunk(int tiles_xy, int nz, int ctas_per_sm, int nfz, int streams) {
+    return pick_zchunk_slots(tiles_xy, nz, 148 * ctas_per_sm, 6.0 * nfz / streams);
 }
 
 // ---- padded-layout maintenance (ghost_kernels.cu) ----

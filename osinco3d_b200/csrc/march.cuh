@@ -106,12 +106,17 @@ struct Ring {
 };
 
 // Epilogue concept:
+//   static constexpr int STREAMS;                 values moved per point (reads + writes): sizes
+//                                                 the z chunks (pick_zchunk)
 //   void setup(const MarchGeom&, int i, int j);   per-thread constants, before the march
 //   struct Pre;                                   streamed operands of one point (register path)
 //   Pre  prefetch(long long m, bool ok) const;    issue their loads (m = element offset)
 //   void apply(const Ring<NFZ,NFC>&, long long m, int i, int j, int k, const Pre&);
 //   void finish(int tid, double* smem);           after the march (block reductions)
-template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0>
+// UNR > 1: the plane loop is unrolled UNR times, UNR a common multiple of the ring lengths, so
+// that every ring position is a compile-time constant inside the body: shared-memory operands
+// become [base + immediate] and the per-plane ring-pointer arithmetic disappears.
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0, int UNR = 1>
 __global__ void __launch_bounds__(MNT, MINB)
     march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC + NFS + NALT> maps, const MarchGeom g,
                  Epi epi) {
@@ -196,11 +201,38 @@ __global__ void __launch_bounds__(MNT, MINB)
     typename Epi::Pre cur = epi.prefetch(m0 + (long long)kb * g.sz, in_dom);
     const int cell = (ty + R) * MBX + tx + MXO;
 
+    long long m = m0 + (long long)kb * g.sz;
+    if constexpr (UNR > 1) {
+        static_assert(UNR % NZS == 0 && UNR % NCS == 0 && UNR % NB == 0 && (UNR / NB) % 2 == 0,
+                      "UNR must be a common multiple of the ring lengths (even in barrier rounds)");
+        for (int k0 = kb; k0 < ke; k0 += UNR) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int k = k0 + u;
+                if (k < ke) {  // uniform over the CTA
+                    const int it = k - kb;
+                    typename Epi::Pre nxt = epi.prefetch(m + g.sz, in_dom && (k + 1 < ke));
+                    __syncthreads();
+                    if (tid == 0 && it + P < niter) issue_group(it + P);
+                    mbar_wait(bars_s + 8 * (u % NB), (uint32_t)((u / NB) & 1));
+                    if (in_dom) {
+                        Ring<NFZ, NFC> r;
+#pragma unroll
+                        for (int w = 0; w < 7; ++w) r.p[w] = zring + ((u + w) % NZS) * ZSTAGE + cell;
+                        r.q = cring + (u % NCS) * CSTAGE + cell;
+                        r.s = sring + (u % NCS) * SSTAGE + tid;
+                        epi.apply(r, m, i, j, k, cur);
+                    }
+                    cur = nxt;
+                    m += g.sz;
+                }
+            }
+        }
+    } else {
     // ring positions of the plane being computed, advanced incrementally (no modulo in the loop):
     // zb = stage of plane k-3, cb = stage of plane k, bi / bpar = barrier index and phase
     int zb = 0, cb = 0, bi = 0;
     uint32_t bpar = 0;
-    long long m = m0 + (long long)kb * g.sz;
     for (int k = kb; k < ke; ++k) {
         const int it = k - kb;
         // streamed operands of the next plane (register path)
@@ -228,6 +260,7 @@ __global__ void __launch_bounds__(MNT, MINB)
         cb = (cb + 1 == NCS) ? 0 : cb + 1;
         if (++bi == NB) bi = 0, bpar ^= 1u;
     }
+    }
     __syncthreads();
     epi.finish(tid, zring);
 }
@@ -235,11 +268,11 @@ __global__ void __launch_bounds__(MNT, MINB)
 // zmode: ZFULL whole slab | ZINTERIOR planes [zedge, nz - zedge) | ZBOUNDARY the two end chunks
 enum { ZFULL = 0, ZINTERIOR = 1, ZBOUNDARY = 2 };
 
-template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0>
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0, int UNR = 1>
 int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS + NALT>& maps,
                  const Epi& epi, int zmode = ZFULL, int zedge = 0, const SorCtrl* gate = nullptr) {
     static bool attr_set = false;
-    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB, NFS, NALT>;
+    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB, NFS, NALT, UNR>;
     constexpr int smem = march_smem_bytes<NFZ, NFC, P, NFS>();
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
@@ -264,7 +297,7 @@ int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS
     } else {
         const int span = mg.zhi - mg.zlo;
         if (span <= 0) return 0;
-        mg.zchunk = pick_zchunk(gx * gy, span, MINB);
+        mg.zchunk = pick_zchunk(gx * gy, span, MINB, NFZ, Epi::STREAMS);
         gz = (span + mg.zchunk - 1) / mg.zchunk;
     }
     kern<<<dim3(gx, gy, gz), dim3(MNT, 1, 1), smem, st>>>(maps, mg, epi);

@@ -18,6 +18,7 @@ struct NoPre {};
 // S2 = sim2d resolved at compile time (no basic-block break in the common 3-D case)
 template <bool S2>
 struct DivEpi {
+    static constexpr int STREAMS = 4;
     double* out;
     Coef cx, cy, cz;
     double dt;
@@ -58,6 +59,7 @@ struct DivEpi {
 
 template <bool S2>
 struct CorrEpi {
+    static constexpr int STREAMS = 7;
     double* u[3];
     Coef cx, cy, cz;
     double dt;

@@ -408,7 +408,7 @@ int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class,
     if (seam_class == 0) {
         const int half = (a.nx + 1) / 2;
         const int gx = (half + SBX - 1) / SBX, gy = (a.ny + SBY - 1) / SBY;
-        const int zchunk = pick_zchunk(gx * gy, a.nz);
+        const int zchunk = pick_zchunk_slots(gx * gy, a.nz, 148 * 2, 0.5);
         sor_rb_kernel<<<dim3(gx, gy, (a.nz + zchunk - 1) / zchunk), dim3(SBX, SBY, 1), 0, st>>>(
             a, colour, ctrl, zchunk);
     } else {

@@ -313,8 +313,8 @@ int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_m
     } else {
         const int span = f.zhi - f.zlo;
         if (span <= 0) return 0;
-        // 5 extra planes per chunk (pipeline prologue), 3 CTAs per SM
-        f.zchunk = pick_zchunk_slots(gx * gy, span, 148 * 3, 5);
+        // per chunk: 5 prologue planes of 2 of the 3 streams (+ their red updates), 3 CTAs per SM
+        f.zchunk = pick_zchunk_slots(gx * gy, span, 148 * 3, 3.3);
         gz = (span + f.zchunk - 1) / f.zchunk;
     }
     if (f.opx || f.opy || f.opz)

@@ -12,6 +12,7 @@ namespace o3d {
 namespace {
 
 struct TranseqEpi {
+    static constexpr int STREAMS = 9;
     const double* u[3];
     const double* nu_t;
     const double* src;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) transeq_clip_kernel(const Geom g,
 
 int transeq_blocks(const Geom& g) {
     const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
-    const int zc = pick_zchunk(gx * gy, g.nz, 3);  // same chunking as launch_march<..., MINB = 3>
+    const int zc = pick_zchunk(gx * gy, g.nz, 3, 1, TranseqEpi::STREAMS);  // as launch_march<1,0,1,TranseqEpi,3>
     return gx * gy * ((g.nz + zc - 1) / zc);
 }
 

@@ -57,6 +57,7 @@ __device__ __forceinline__ double smagorinsky(const Grad& G, double csd2) {
 // the live ranges of the LES instantiation inside 128 registers (no spills).
 template <bool FAST>
 struct RhsEpi {
+    static constexpr int STREAMS = 15;
     const double* f2[3];
     const double* f3[3];
     double* f1[3];
@@ -71,6 +72,10 @@ struct RhsEpi {
     int nz, bz_lo, bz_hi;
     long long sy_, sz_;
     double sgx, sgy, sgz_lo, sgz_hi;
+    // image stores are the exception (points within 3 cells of a boundary): one flag per thread
+    // for x/y and one plane test for z keep them out of the instruction stream of interior warps
+    bool edge_xy;
+    int zimg_lo, zimg_hi;
     __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j) {
         ix = image_offsets(i, g.nx, g.bx, g.bx);
         iy = image_offsets(j, g.ny, g.by, g.by);
@@ -80,6 +85,10 @@ struct RhsEpi {
         sgy = (g.by == BM_MIRROR) ? -1.0 : 1.0;
         sgz_lo = (g.bz_lo == BM_MIRROR) ? -1.0 : 1.0;
         sgz_hi = (g.bz_hi == BM_MIRROR) ? -1.0 : 1.0;
+        edge_xy = (ix.lo | ix.hi | iy.lo | iy.hi) != 0;
+        // planes whose points have z images on this rank (walls / local periodic wrap)
+        zimg_lo = (g.bz_lo == BM_MIRROR || g.bz_hi == BM_WRAP) ? R : -1;
+        zimg_hi = (g.bz_hi == BM_MIRROR || g.bz_lo == BM_WRAP) ? g.nz - 1 - R : g.nz;
     }
     struct Pre {
         double f2v[3], f3v[3];
@@ -103,6 +112,7 @@ struct RhsEpi {
         }
         const double nu_eff = onere + nut;  // src/integration.f90:114
         const double u0 = r.c(0), u1 = r.c(1), u2 = r.c(2);
+        double ups[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double lx = r.d2x(c, q.x), ly = r.d2y(c, q.y);
@@ -114,17 +124,16 @@ struct RhsEpi {
             const double upv = uc + adu * f + bdu * pre.f2v[c] + cdu * pre.f3v[c];
             f1[c][m] = f;
             up[c][m] = upv;
-            if (c == 0) {
-                if (ix.lo) up[0][m + ix.lo] = sgx * upv;
-                if (ix.hi) up[0][m + ix.hi] = sgx * upv;
-            } else if (c == 1) {
-                if (iy.lo) up[1][m + iy.lo * sy_] = sgy * upv;
-                if (iy.hi) up[1][m + iy.hi * sy_] = sgy * upv;
-            } else {
-                const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
-                if (iz.lo) up[2][m + iz.lo * sz_] = sgz_lo * upv;
-                if (iz.hi) up[2][m + iz.hi * sz_] = sgz_hi * upv;
-            }
+            ups[c] = upv;
+        }
+        if (edge_xy || k <= zimg_lo || k >= zimg_hi) {  // boundary-adjacent points only
+            if (ix.lo) up[0][m + ix.lo] = sgx * ups[0];
+            if (ix.hi) up[0][m + ix.hi] = sgx * ups[0];
+            if (iy.lo) up[1][m + iy.lo * sy_] = sgy * ups[1];
+            if (iy.hi) up[1][m + iy.hi * sy_] = sgy * ups[1];
+            const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
+            if (iz.lo) up[2][m + iz.lo * sz_] = sgz_lo * ups[2];
+            if (iz.hi) up[2][m + iz.hi * sz_] = sgz_hi * ups[2];
         }
     }
     __device__ __forceinline__ void finish(int, double*) {}
@@ -224,6 +233,7 @@ struct RhsRoleEpi {
 struct NoPre {};
 
 struct NutEpi {
+    static constexpr int STREAMS = 4;
     double* nu_t;
     Coefs3 q;
     double csd2;
@@ -240,6 +250,7 @@ struct NutEpi {
 // rotational: every term uses the even closure (src/differential_operators.f90:64-74); the
 // caller fills the ghost cells with even parity before the launch
 struct RotEpi {
+    static constexpr int STREAMS = 6;
     double *rx, *ry, *rz;
     Coefs3 q;
     int sim2d;
@@ -259,6 +270,7 @@ struct RotEpi {
 // sqrt(rotx**2 + roty**2 + rotz**2) of the curl above, fused -- 32 B/pt instead of curl (48) + a
 // 32 B/pt magnitude pass; same even closure as RotEpi
 struct VortEpi {
+    static constexpr int STREAMS = 4;
     double* vm;
     Coefs3 q;
     int sim2d;
@@ -276,6 +288,7 @@ struct VortEpi {
 };
 
 struct QEpi {
+    static constexpr int STREAMS = 4;
     double* qc;
     Coefs3 q;
     int sim2d;
@@ -294,6 +307,7 @@ struct QEpi {
 // statistics_calc: 16 sums (columns 2..17 of stats.dat), src/utils.f90:277-361
 constexpr int NSTAT = 16;
 struct StatsEpi {
+    static constexpr int STREAMS = 3;
     double* partial;  // [NSTAT][nblocks]
     Coefs3 q;
     double xnu;
@@ -370,8 +384,15 @@ static int launch_rhs_t(cudaStream_t st, const Geom& g, const RhsArgs& r, int zm
     e.q = coefs(r.cx, r.cy, r.cz);
     e.onere = r.onere, e.adu = r.adu, e.bdu = r.bdu, e.cdu = r.cdu, e.csd2 = r.csd2;
     e.iles = r.iles, e.sim2d = g.sim2d;
-    return launch_march<3, 0, 1, RhsEpi<FAST>, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e,
-                                                          zmode, zedge);
+    // O3D_RHS_UNROLL=1: plane loop unrolled over the 8-stage ring (march.cuh, UNR = 8: ring
+    // positions become immediates).  Measured equal at 256^3 and 1-2 % slower at 512^3 than the
+    // rolled loop (the kernel is not instruction-bound), so the rolled loop is the default.
+    static const bool unrolled = getenv("O3D_RHS_UNROLL") && atoi(getenv("O3D_RHS_UNROLL")) == 1;
+    if (unrolled)
+        return launch_march<3, 0, 1, RhsEpi<FAST>, 2, 0, 0, 8>(st, g, maps3(r.u[0], r.u[1], r.u[2]),
+                                                               e, zmode, zedge);
+    return launch_march<3, 0, 1, RhsEpi<FAST>, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e, zmode,
+                                                  zedge);
 }
 
 int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int zedge) {
@@ -420,7 +441,7 @@ int launch_qcrit(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& 
 
 int stats_blocks(const Geom& g) {
     const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
-    const int zc = pick_zchunk(gx * gy, g.nz);
+    const int zc = pick_zchunk(gx * gy, g.nz, 2, 3, StatsEpi::STREAMS);  // as launch_march<3,0,1,StatsEpi,2>
     return gx * gy * ((g.nz + zc - 1) / zc);
 }
 
