@@ -322,6 +322,37 @@ def run_e2e_resident(o3d, ses, steps):
                     "step (resident integration mode), wall clock"}
 
 
+def run_e2e_slabs(o3d, ses, steps, dist):
+    """N > 1: the host-pointer module procedures are single-device (the reference has no domain
+    decomposition to drop into), so the end-to-end figure of a z-slab run goes through the public
+    session API instead: every step each rank uploads its slab of the flow state (ux, uy, uz, pp)
+    from pinned host memory, runs o3d_step, and reads the new state back into pinned host memory.
+    Wall clock between barriers, max over ranks."""
+    import torch
+    pool = o3d.PinnedPool()
+    names = ("ux", "uy", "uz", "pp")
+    host = {k: pool.empty(ses.shape) for k in names}
+    for k in names:
+        ses.download_ptr(k, host[k].ctypes.data)
+    ses.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for k in names:
+            ses.upload_ptr(k, host[k].ctypes.data)
+        ses.step()
+        for k in names:
+            ses.download_ptr(k, host[k].ctypes.data)
+    ses.sync()
+    dt_wall = time.perf_counter() - t0
+    t = torch.tensor([dt_wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pool.close()
+    nloc = float(np.prod(ses.shape))
+    return float(t.item()) / steps, int(4 * nloc * 8)
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -453,6 +484,16 @@ def main():
     e2e_res = None
     if rank == 0 and world == 1 and not args.no_e2e:
         e2e_res = run_e2e_resident(o3d, ses, max(3, K // 2))
+    e2e_slabs = None
+    if world > 1 and not args.no_e2e:
+        sec, nbytes = run_e2e_slabs(o3d, ses, max(3, K // 4), dist)
+        e2e_slabs = {"value": npts / 1e6 / sec, "unit": "Mpts*steps/s", "ms_per_step": 1e3 * sec,
+                     "steps": max(3, K // 4), "h2d_bytes_per_step": nbytes * world,
+                     "d2h_bytes_per_step": nbytes * world,
+                     "path": "per rank and step: o3d_upload of ux, uy, uz, pp from pinned host slabs "
+                             "+ o3d_step + o3d_download of the same four fields (session API; the "
+                             "host-pointer module procedures are single-device), wall clock, max "
+                             "over ranks; bytes are totals over all ranks"}
     ses.close()
     line = None
     if rank == 0:
@@ -486,7 +527,7 @@ def main():
                           "iters/step %s; oracle = C restatement of the serial Fortran reference "
                           "(gfortran absent)" % (len(tt), ncpu, its[1:] if len(its) > 1 else its)}
     elif rank == 0:
-        line["e2e"] = None
+        line["e2e"] = e2e_slabs
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -335,6 +335,19 @@ module o3d_b200_c
        real(c_double), value :: omega
        integer(c_int) :: rc
      end function o3d_set_omega
+     function o3d_s_old_values(ses) bind(C, name="o3d_s_old_values") result(rc)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ses
+       integer(c_int) :: rc
+     end function o3d_s_old_values
+     function o3d_s_calculate_residuals(ses, dt, t_ref, u_ref, out15) &
+          bind(C, name="o3d_s_calculate_residuals") result(rc)
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ses
+       real(c_double), value :: dt, t_ref, u_ref
+       real(c_double), intent(out) :: out15(15)
+       integer(c_int) :: rc
+     end function o3d_s_calculate_residuals
      function o3d_s_vorticity_magnitude(ses, dst) &
           bind(C, name="o3d_s_vorticity_magnitude") result(rc)
        import :: c_int, c_ptr

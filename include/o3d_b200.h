@@ -238,6 +238,7 @@ enum {
     O3D_F_FUZ1, O3D_F_FUZ2, O3D_F_FUZ3, O3D_F_FPHI1, O3D_F_FPHI2, O3D_F_FPHI3,
     O3D_F_DIVU, O3D_F_SCRATCH0, O3D_F_SCRATCH1, O3D_F_SCRATCH2,
     O3D_F_PP2, /* ping-pong partner of pp inside the fused red-black SOR (internal) */
+    O3D_F_OLD_UX, O3D_F_OLD_UY, O3D_F_OLD_UZ, /* old_ux, old_uy, old_uz (src/utils.f90:165) */
     O3D_F_COUNT
 };
 
@@ -279,6 +280,15 @@ int o3d_s_divergence(o3d_session* s, int fx, int fy, int fz, int dst, int odd);
 int o3d_s_reduce(o3d_session* s, int field, int op, double* out);
 int o3d_s_function_stats(o3d_session* s, int field, double* stats6);
 int o3d_s_statistics(o3d_session* s, double t, double* out17);
+/* old_values, src/utils.f90:165-176: old_u? = u? (device copies; only needed on the steps whose
+ * residual is evaluated, src/osinco3d_main.f90:104,167) */
+int o3d_s_old_values(o3d_session* s);
+/* calculate_residuals, src/utils.f90:93-160, over old_u? and u?: out15 = res_u res_v res_w |
+ * aa bb cc (= t_ref/u_ref * Linf) | (ia ja ka) (ib jb kb) (ic jc kc), 1-based GLOBAL indices of
+ * the LAST interior point attaining each maximum, as the reference's loop leaves them.  The
+ * "residue too high" stop (:155-158) is the caller's: res_u > 1e6. */
+int o3d_s_calculate_residuals(o3d_session* s, double dt, double t_ref, double u_ref,
+                              double* out15);
 int o3d_s_rotational(o3d_session* s, int rotx, int roty, int rotz);
 int o3d_s_q_criterion(o3d_session* s, int dst);
 /* sqrt(rotx**2 + roty**2 + rotz**2), the "vort" array of write_all_data

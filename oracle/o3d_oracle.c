@@ -560,6 +560,39 @@ void orc_function_stats(const double* f, int nx, int ny, int nz, double* out) {
     out[3] = im, out[4] = jm, out[5] = km;
 }
 
+void orc_calculate_residuals(const double* u, const double* v, const double* w,
+                             const double* old_u, const double* old_v, const double* old_w,
+                             double dt, double t_ref, double u_ref, int nx, int ny, int nz,
+                             double* out15) {
+    /* utils.f90:93-160: out = res_u res_v res_w | aa bb cc | ia ja ka ib jb kb ic jc kc */
+    const double* nw[3] = {u, v, w};
+    const double* od[3] = {old_u, old_v, old_w};
+    for (int c = 0; c < 3; ++c) {
+        double res = 0.0, linf = 0.0;
+        /* :109-124 interior points 2 .. n-1 */
+        for (int k = 1; k < nz - 1; ++k)
+            for (int j = 1; j < ny - 1; ++j)
+                for (int i = 1; i < nx - 1; ++i) {
+                    const double a = fabs(od[c][IDX(i, j, k)] - nw[c][IDX(i, j, k)]) / (2.0 * dt);
+                    res = res + a * a; /* (...)**2.d0 */
+                    linf = a > linf ? a : linf;
+                }
+        /* :125-145: the LAST point whose value equals the maximum */
+        int ia = 0, ja = 0, ka = 0;
+        for (int k = 1; k < nz - 1; ++k)
+            for (int j = 1; j < ny - 1; ++j)
+                for (int i = 1; i < nx - 1; ++i) {
+                    const double a = fabs(od[c][IDX(i, j, k)] - nw[c][IDX(i, j, k)]) / (2.0 * dt);
+                    if (fabs(linf - a) <= 2.2250738585072014e-308) ia = i + 1, ja = j + 1, ka = k + 1;
+                }
+        /* :147-152; real(nx*ny*nz) is a default (single precision) real */
+        const double cnt = (double)(float)(nx * ny * nz);
+        out15[c] = (t_ref / u_ref) * sqrt((1.0 / cnt) * res);
+        out15[3 + c] = (t_ref / u_ref) * linf;
+        out15[6 + 3 * c] = ia, out15[7 + 3 * c] = ja, out15[8 + 3 * c] = ka;
+    }
+}
+
 void orc_ab_coefficients(double dt, double* adt, double* bdt, double* cdt) {
     /* initialization.f90:194-202 */
     adt[0] = dt, bdt[0] = 0.0, cdt[0] = 0.0;

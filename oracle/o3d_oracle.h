@@ -101,6 +101,11 @@ void orc_statistics_calc(const orc_grid* g, const double* ux, const double* uy, 
 void orc_function_stats(const double* f, int nx, int ny, int nz, double* out);
 
 /* src/initialization.f90:194-202 */
+/* utils.f90:93-160: res_u res_v res_w | aa bb cc | (ia ja ka) (ib jb kb) (ic jc kc) */
+void orc_calculate_residuals(const double* u, const double* v, const double* w,
+                             const double* old_u, const double* old_v, const double* old_w,
+                             double dt, double t_ref, double u_ref, int nx, int ny, int nz,
+                             double* out15);
 void orc_ab_coefficients(double dt, double* adt, double* bdt, double* cdt);
 
 /* initial conditions, src/initial_conditions.f90:103-175 (TGV). x0,y0,z0 origin. */

@@ -88,6 +88,16 @@ def q_criterion(g, ux, uy, uz):
     return q
 
 
+def calculate_residuals(u, v, w, old_u, old_v, old_w, dt, t_ref, u_ref):
+    """utils.calculate_residuals, src/utils.f90:93-160 -> 15 values (see o3d_oracle.h)"""
+    out = (C.c_double * 15)()
+    nx, ny, nz = u.shape
+    lib().orc_calculate_residuals(_p(u), _p(v), _p(w), _p(old_u), _p(old_v), _p(old_w),
+                                  C.c_double(dt), C.c_double(t_ref), C.c_double(u_ref), nx, ny, nz,
+                                  out)
+    return np.array(list(out))
+
+
 def calculate_nu_t(g, ux, uy, uz, cs, delta):
     out = np.empty_like(ux, order="F")
     lib().orc_calculate_nu_t(C.byref(g), _p(out), _p(ux), _p(uy), _p(uz), C.c_double(cs),

@@ -25,7 +25,8 @@ RED_MIN, RED_MAX, RED_SUM, RED_ABSMAX = 0, 1, 2, 3
 
 FIELDS = ["ux", "uy", "uz", "pp", "phi", "ux_pred", "uy_pred", "uz_pred", "nu_t", "rhs",
           "fux1", "fux2", "fux3", "fuy1", "fuy2", "fuy3", "fuz1", "fuz2", "fuz3",
-          "fphi1", "fphi2", "fphi3", "divu", "scratch0", "scratch1", "scratch2", "pp2"]
+          "fphi1", "fphi2", "fphi3", "divu", "scratch0", "scratch1", "scratch2", "pp2",
+          "old_ux", "old_uy", "old_uz"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 
 
@@ -90,6 +91,9 @@ def lib():
         _lib.o3d_s_rotational.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.o3d_s_q_criterion.argtypes = [C.c_void_p, C.c_int]
         _lib.o3d_s_vorticity_magnitude.argtypes = [C.c_void_p, C.c_int]
+        _lib.o3d_s_old_values.argtypes = [C.c_void_p]
+        _lib.o3d_s_calculate_residuals.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                                   dp]
         _lib.o3d_s_save_fields.argtypes = [C.c_void_p, C.c_char_p, C.c_double, dp, dp, dp]
         _lib.o3d_s_read_fields.argtypes = [C.c_void_p, C.c_char_p, dp, dp, dp, dp]
         _lib.o3d_s_write_binary.argtypes = [C.c_void_p, C.c_char_p, C.c_int]

@@ -526,6 +526,8 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     if (e == cudaSuccess) e = cudaMalloc(&s->ctrl_d, sizeof(SorCtrl));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_h, sizeof(SorCtrl), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&s->flag_d, sizeof(int));
+    // the NaN / >1000 flag is sticky (only cleared when reported): it must start clean
+    if (e == cudaSuccess) e = cudaMemset(s->flag_d, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->flag_h, sizeof(int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&s->scal_d, 64 * sizeof(double));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->scal_h, 64 * sizeof(double), cudaHostAllocDefault);
@@ -1074,6 +1076,72 @@ int o3d_s_statistics(o3d_session* s, double t, double* out17) {
     out17[3] = a[2] / cnt;
     out17[4] = a[3] / cnt;
     for (int q = 0; q < 12; ++q) out17[5 + q] = a[4 + q] / cnt;
+    return O3D_OK;
+}
+
+int o3d_s_old_values(o3d_session* s) {
+    if (!s) return O3D_ERR_INVALID;
+    // src/utils.f90:165-176; whole padded allocations (ghost cells included), device to device
+    for (int c = 0; c < 3; ++c) {
+        double* src = field(s, O3D_F_UX + c);
+        double* dst = field(s, O3D_F_OLD_UX + c);
+        if (!src || !dst) return O3D_ERR_CUDA;
+        const long long off = interior_offset(s->g);
+        O3D_CUDA_CHECK(cudaMemcpyAsync(dst - off, src - off, (size_t)s->felems * sizeof(double),
+                                       cudaMemcpyDeviceToDevice, s->st));
+        s->gaxes[O3D_F_OLD_UX + c] = s->gaxes[O3D_F_UX + c];
+        s->gpar[O3D_F_OLD_UX + c] = s->gpar[O3D_F_UX + c];
+    }
+    return O3D_OK;
+}
+
+int o3d_s_calculate_residuals(o3d_session* s, double dt, double t_ref, double u_ref,
+                              double* out15) {
+    if (!s || !out15) return O3D_ERR_INVALID;
+    const o3d_config& c = s->cfg;
+    const double* un[3];
+    const double* uo[3];
+    for (int q = 0; q < 3; ++q) {
+        un[q] = field(s, O3D_F_UX + q);
+        uo[q] = field(s, O3D_F_OLD_UX + q);
+        if (!un[q] || !uo[q]) return O3D_ERR_CUDA;
+    }
+    int rc;
+    if ((rc = ensure_partial(s, 9ll * 296))) return rc;
+    double* out9 = s->scal_d + 48;
+    if (launch_residuals(s->st, s->g, un, uo, 2.0 * dt, s->partial, out9)) return O3D_ERR_CUDA;
+    double* h = s->scal_h + 48;
+    auto fetch = [&]() -> int {
+        O3D_CUDA_CHECK(
+            cudaMemcpyAsync(h, out9, 9 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+        return O3D_OK;
+    };
+    if (c.nranks > 1) {
+        // sums add up, maxima are global; a rank whose maximum is below the global one withdraws
+        // its index, the largest remaining (= last in array order) index wins
+        if ((rc = fetch())) return rc;
+        const double local_mx[3] = {h[3], h[4], h[5]};
+        if ((rc = comm_allreduce(s, out9, 3, RED_SUM))) return rc;
+        if ((rc = comm_allreduce(s, out9 + 3, 3, RED_MAX))) return rc;
+        if ((rc = fetch())) return rc;
+        for (int q = 0; q < 3; ++q)
+            if (local_mx[q] < h[3 + q]) h[6 + q] = -1.0;
+        O3D_CUDA_CHECK(cudaMemcpyAsync(out9 + 6, h + 6, 3 * sizeof(double),
+                                       cudaMemcpyHostToDevice, s->st));
+        if ((rc = comm_allreduce(s, out9 + 6, 3, RED_MAX))) return rc;
+    }
+    if ((rc = fetch())) return rc;
+    // src/utils.f90:147-152; real(nx*ny*nz) is a default (single precision) real
+    const double cnt = (double)(float)(c.nx * c.ny * c.nz);
+    for (int q = 0; q < 3; ++q) {
+        out15[q] = (t_ref / u_ref) * sqrt((1.0 / cnt) * h[q]);
+        out15[3 + q] = (t_ref / u_ref) * h[3 + q];
+        const long long m = (long long)h[6 + q];
+        out15[6 + 3 * q] = (m < 0) ? 0.0 : (double)(m % c.nx + 1);
+        out15[7 + 3 * q] = (m < 0) ? 0.0 : (double)((m / c.nx) % c.ny + 1);
+        out15[8 + 3 * q] = (m < 0) ? 0.0 : (double)(m / ((long long)c.nx * c.ny) + 1);
+    }
     return O3D_OK;
 }
 

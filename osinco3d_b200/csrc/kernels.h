@@ -222,6 +222,11 @@ int launch_reduce(cudaStream_t st, const Geom& g, const double* f, int op, doubl
 // function_stats (src/functions.f90:27): out6 device doubles; partial >= 4 * 296 doubles
 int launch_function_stats(cudaStream_t st, const Geom& g, const double* f, double* partial,
                           double* out6);
+// calculate_residuals (src/utils.f90:93-160) over the interior points of the GLOBAL grid that
+// this rank owns: out9 device doubles = 3 sums of squares | 3 maxima | 3 global linear indices
+// (as doubles, -1 if none) of the last point attaining the maximum; partial >= 9 * 296 doubles
+int launch_residuals(cudaStream_t st, const Geom& g, const double* const* unew,
+                     const double* const* uold, double two_dt, double* partial, double* out9);
 // sum `nparts` partial triples deterministically: out[c] = sum_b partial[c*nparts + b]
 int launch_sum_partials(cudaStream_t st, const double* partial, int nparts, int ncomp,
                         double* out);

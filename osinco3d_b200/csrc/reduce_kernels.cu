@@ -168,7 +168,118 @@ __global__ void __launch_bounds__(RB) fstats_stage2(const double* partial, int n
     }
 }
 
+// ---- calculate_residuals, src/utils.f90:93-160 ---------------------------------------------
+struct ResAcc {
+    double s[3], mx[3];
+    long long im[3];
+};
+__device__ __forceinline__ void res_merge(ResAcc& a, const ResAcc& b) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        a.s[c] += b.s[c];
+        // the reference's second loop (:125-145) keeps the LAST point equal to the maximum
+        if (b.mx[c] > a.mx[c] || (b.mx[c] == a.mx[c] && b.im[c] > a.im[c]))
+            a.mx[c] = b.mx[c], a.im[c] = b.im[c];
+    }
+}
+__device__ __forceinline__ ResAcc res_block(ResAcc v, ResAcc* red) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ResAcc b;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            b.s[c] = __shfl_xor_sync(0xffffffffu, v.s[c], o);
+            b.mx[c] = __shfl_xor_sync(0xffffffffu, v.mx[c], o);
+            b.im[c] = __shfl_xor_sync(0xffffffffu, v.im[c], o);
+        }
+        // xor butterflies must merge symmetrically to stay deterministic: order by lane
+        if (tid & o) {
+            ResAcc t = b;
+            res_merge(t, v);
+            v = t;
+        } else {
+            res_merge(v, b);
+        }
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0)
+        for (int q = 1; q < RB / 32; ++q) res_merge(v, red[q]);
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(RB)
+    resid_stage1(const Geom g, const double* __restrict__ u0, const double* __restrict__ u1,
+                 const double* __restrict__ u2, const double* __restrict__ o0,
+                 const double* __restrict__ o1, const double* __restrict__ o2, double two_dt,
+                 double* partial) {
+    __shared__ ResAcc red[RB / 32];
+    ResAcc v;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.s[c] = 0.0, v.mx[c] = 0.0, v.im[c] = -1;  // linf_? = 0.d0, :104
+    const double* un[3] = {u0, u1, u2};
+    const double* uo[3] = {o0, o1, o2};
+    const long long rows = (long long)g.ny * g.nz;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int j = (int)(row % g.ny), k = (int)(row / g.ny);
+        const int gk = g.gz0 + k;
+        if (j < 1 || j > g.ny - 2 || gk < 1 || gk > g.gnz - 2) continue;  // do k = 2, nz-1 ...
+        const long long base = (long long)k * g.sz + (long long)j * g.sy;
+        for (int i = 1 + threadIdx.x; i < g.nx - 1; i += RB) {
+            const long long lin = ((long long)gk * g.ny + j) * g.nx + i;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double a = fabs(__ldg(uo[c] + base + i) - __ldg(un[c] + base + i)) / two_dt;
+                v.s[c] += a * a;
+                if (a >= v.mx[c]) v.mx[c] = a, v.im[c] = lin;  // lin ascending within a thread
+            }
+        }
+    }
+    v = res_block(v, red);
+    if (threadIdx.x == 0) {
+        double* p = partial + 9ll * blockIdx.x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            p[c] = v.s[c], p[3 + c] = v.mx[c], p[6 + c] = (double)v.im[c];
+    }
+}
+
+__global__ void __launch_bounds__(RB) resid_stage2(const double* partial, int nparts,
+                                                    double* out9) {
+    __shared__ ResAcc red[RB / 32];
+    ResAcc v;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.s[c] = 0.0, v.mx[c] = 0.0, v.im[c] = -1;
+    for (int b = threadIdx.x; b < nparts; b += RB) {
+        ResAcc t;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            t.s[c] = partial[9ll * b + c], t.mx[c] = partial[9ll * b + 3 + c],
+            t.im[c] = (long long)partial[9ll * b + 6 + c];
+        res_merge(v, t);
+    }
+    v = res_block(v, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out9[c] = v.s[c], out9[3 + c] = v.mx[c], out9[6 + c] = (double)v.im[c];
+    }
+}
+
 }  // namespace
+
+int launch_residuals(cudaStream_t st, const Geom& g, const double* const* unew,
+                     const double* const* uold, double two_dt, double* partial, double* out9) {
+    int nb = reduce_blocks(g);
+    if (nb > 296) nb = 296;
+    resid_stage1<<<nb, RB, 0, st>>>(g, unew[0], unew[1], unew[2], uold[0], uold[1], uold[2],
+                                    two_dt, partial);
+    resid_stage2<<<1, RB, 0, st>>>(partial, nb, out9);
+    count_launch(2);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
 
 int reduce_blocks(const Geom& g) {
     long long b = (long long)g.ny * g.nz;

@@ -139,6 +139,17 @@ class Session:
     def q_criterion(self, dst="scratch0"):
         check(lib().o3d_s_q_criterion(self._h, L.FIELD_ID[dst]))
 
+    def old_values(self):
+        """utils.old_values, src/utils.f90:165-176"""
+        check(lib().o3d_s_old_values(self._h))
+
+    def calculate_residuals(self, dt=None, t_ref=1.0, u_ref=1.0):
+        """utils.calculate_residuals, src/utils.f90:93-160 -> 15 values (include/o3d_b200.h)"""
+        out = (C.c_double * 15)()
+        check(lib().o3d_s_calculate_residuals(self._h, C.c_double(self.cfg.dt if dt is None else dt),
+                                              C.c_double(t_ref), C.c_double(u_ref), out))
+        return np.array(list(out))
+
     def vorticity_magnitude(self, dst="scratch0"):
         check(lib().o3d_s_vorticity_magnitude(self._h, L.FIELD_ID[dst]))
 

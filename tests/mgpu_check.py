@@ -101,7 +101,10 @@ def main():
         ses = o3d.Session(cfg)
         assert (ses.z0, ses.nz_local) == slab.slab_range(nz, rank, world)
         ses.set(**{k: slab.take_slab(v, rank, world) for k, v in fields.items()})
-        iters = [ses.step() for _ in range(steps)]
+        iters = [ses.step() for _ in range(steps - 1)]
+        ses.old_values()
+        iters.append(ses.step())
+        resid = ses.calculate_residuals(0.02 * d, 1.0, 1.0)   # src/utils.f90:93-160
         stats = ses.statistics()
         red = ses.reduce("ux", o3d.RED_ABSMAX)
         out = {k: ses.download(k) for k in ("ux", "uy", "uz", "pp", "phi", "ux_pred", "rhs")}
@@ -125,7 +128,14 @@ def main():
         if rank == 0:
             one = o3d.Session(o3d.make_config(n, n, nz, d, d, d, **kw))
             one.set(**fields)
-            it1 = [one.step() for _ in range(steps)]
+            it1 = [one.step() for _ in range(steps - 1)]
+            one.old_values()
+            it1.append(one.step())
+            resid1 = one.calculate_residuals(0.02 * d, 1.0, 1.0)
+            # Linf values and their indices are exact, the sums differ in association only
+            if not (np.array_equal(resid[3:], resid1[3:]) and
+                    np.allclose(resid[:3], resid1[:3], rtol=1e-12, atol=0)):
+                ok, msg = False, "residuals %s vs single-GPU %s" % (resid, resid1)
             st1 = one.statistics()
             red1 = one.reduce("ux", o3d.RED_ABSMAX)
             ref = {k: one.download(k) for k in out}
@@ -143,7 +153,7 @@ def main():
                 shutil.rmtree(io_dir, ignore_errors=True)
             one.close()
             if it1 != iters:
-                ok, msg = False, "iterations %s vs single-GPU %s" % (iters, it1)
+                ok, msg = False, msg + " iterations %s vs single-GPU %s" % (iters, it1)
             if red1 != red:
                 ok, msg = False, msg + " absmax differs"
             # sums are reduced in a different association across ranks: round-off only
