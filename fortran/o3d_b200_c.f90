@@ -335,6 +335,12 @@ module o3d_b200_c
        real(c_double), value :: omega
        integer(c_int) :: rc
      end function o3d_set_omega
+     function o3d_s_step_diagnostics(ses, out23) bind(C, name="o3d_s_step_diagnostics") result(rc)
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ses
+       real(c_double), intent(out) :: out23(23)
+       integer(c_int) :: rc
+     end function o3d_s_step_diagnostics
      function o3d_s_old_values(ses) bind(C, name="o3d_s_old_values") result(rc)
        import :: c_int, c_ptr
        type(c_ptr), value :: ses

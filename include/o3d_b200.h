@@ -280,6 +280,15 @@ int o3d_s_divergence(o3d_session* s, int fx, int fy, int fz, int dst, int odd);
 int o3d_s_reduce(o3d_session* s, int field, int op, double* out);
 int o3d_s_function_stats(o3d_session* s, int field, double* stats6);
 int o3d_s_statistics(o3d_session* s, double t, double* out17);
+/* Everything src/osinco3d_main.f90:116-128 prints per step, in two fused passes (one over u*,
+ * one over u; 24 B/pt each) instead of 2 divergences + 2 function_stats + 9 reductions:
+ *   out23[0..5]   function_stats(divergence(u*, odd=1)): min, max, mean, i, j, k of the max
+ *   out23[6..11]  function_stats(divergence(u,  odd=1))          (src/functions.f90:27-63)
+ *   out23[12..14] minval(ux, uy, uz)  out23[15..17] maxval   (print_velocity_values,
+ *                                                             src/IOfunctions.f90:322)
+ *   out23[18..20] cflx, cfly, cflz                           (compute_cfl, src/utils.f90:178)
+ *   out23[21..22] minval(phi), maxval(phi) if nscr == 1      (print_scalar_values, :332) */
+int o3d_s_step_diagnostics(o3d_session* s, double* out23);
 /* old_values, src/utils.f90:165-176: old_u? = u? (device copies; only needed on the steps whose
  * residual is evaluated, src/osinco3d_main.f90:104,167) */
 int o3d_s_old_values(o3d_session* s);

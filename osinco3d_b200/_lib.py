@@ -92,6 +92,7 @@ def lib():
         _lib.o3d_s_q_criterion.argtypes = [C.c_void_p, C.c_int]
         _lib.o3d_s_vorticity_magnitude.argtypes = [C.c_void_p, C.c_int]
         _lib.o3d_s_old_values.argtypes = [C.c_void_p]
+        _lib.o3d_s_step_diagnostics.argtypes = [C.c_void_p, dp]
         _lib.o3d_s_calculate_residuals.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double,
                                                    dp]
         _lib.o3d_s_save_fields.argtypes = [C.c_void_p, C.c_char_p, C.c_double, dp, dp, dp]

@@ -529,8 +529,8 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     // the NaN / >1000 flag is sticky (only cleared when reported): it must start clean
     if (e == cudaSuccess) e = cudaMemset(s->flag_d, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->flag_h, sizeof(int), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaMalloc(&s->scal_d, 64 * sizeof(double));
-    if (e == cudaSuccess) e = cudaHostAlloc(&s->scal_h, 64 * sizeof(double), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&s->scal_d, 128 * sizeof(double));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->scal_h, 128 * sizeof(double), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         set_error("session allocation failed: %s", cudaGetErrorString(e));
         o3d_session_destroy(s);
@@ -1076,6 +1076,103 @@ int o3d_s_statistics(o3d_session* s, double t, double* out17) {
     out17[3] = a[2] / cnt;
     out17[4] = a[3] / cnt;
     for (int q = 0; q < 12; ++q) out17[5 + q] = a[4 + q] / cnt;
+    return O3D_OK;
+}
+
+int o3d_s_step_diagnostics(o3d_session* s, double* out23) {
+    if (!s || !out23) return O3D_ERR_INVALID;
+    const o3d_config& c = s->cfg;
+    int rc;
+    const int nb = diag_blocks(s->g);
+    if ((rc = ensure_partial(s, 13ll * nb))) return rc;
+    // divergence(..., 1) of u* and of u: own-axis odd ghosts (src/differential_operators.f90:30-32)
+    FieldRef up[3] = {fref(s, O3D_F_UX_PRED), fref(s, O3D_F_UY_PRED), fref(s, O3D_F_UZ_PRED)};
+    FieldRef u[3] = {fref(s, O3D_F_UX), fref(s, O3D_F_UY), fref(s, O3D_F_UZ)};
+    for (int q = 0; q < 3; ++q)
+        if (!up[q].p || !u[q].p) return O3D_ERR_CUDA;
+    double* d0 = s->scal_d + 64;  // 13 values of u*, 13 of u, then phi min / max
+    if ((rc = ensure_ghosts_own_axis(s, PRED_IDS, NAT3))) return rc;
+    if (launch_diag(s->st, s->g, up, s->cx, s->cy, s->cz, s->partial, d0)) return O3D_ERR_CUDA;
+    if ((rc = ensure_ghosts_own_axis(s, VEL_IDS, NAT3))) return rc;
+    if (launch_diag(s->st, s->g, u, s->cx, s->cy, s->cz, s->partial, d0 + 13)) return O3D_ERR_CUDA;
+    if (c.nscr == 1) {
+        double* phi = field(s, O3D_F_PHI);
+        if (!phi) return O3D_ERR_CUDA;
+        if ((rc = ensure_partial(s, reduce_blocks(s->g)))) return rc;
+        if (launch_reduce(s->st, s->g, phi, RED_MIN, s->partial, d0 + 26)) return O3D_ERR_CUDA;
+        if (launch_reduce(s->st, s->g, phi, RED_MAX, s->partial, d0 + 27)) return O3D_ERR_CUDA;
+    }
+    double* h = s->scal_h + 64;
+    auto fetch = [&]() -> int {
+        O3D_CUDA_CHECK(cudaMemcpyAsync(h, d0, 28 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+        poll_flag(s);
+        return O3D_OK;
+    };
+    if ((rc = fetch())) return rc;
+    if (c.nranks > 1) {
+        // regroup by reduction type, reduce across the slabs, withdraw the arg-max position of a
+        // rank whose maximum is below the global one (the smallest remaining position wins)
+        double mn[10], mx[14], sm[2], loc_max[2] = {h[1], h[14]};
+        for (int t = 0; t < 2; ++t) {
+            const double* x = h + 13 * t;
+            mn[4 * t] = x[0];
+            for (int q = 0; q < 3; ++q) mn[4 * t + 1 + q] = x[4 + q];
+            mx[7 * t] = x[1];
+            for (int q = 0; q < 3; ++q) mx[7 * t + 1 + q] = x[7 + q], mx[7 * t + 4 + q] = x[10 + q];
+            sm[t] = x[2];
+        }
+        mn[8] = h[26];
+        double* w = s->scal_d + 96;  // 10 min | 14 max | 2 sum   (mn[8] = phi min, mn[9] spare)
+        double stage[28];
+        for (int q = 0; q < 10; ++q) stage[q] = (q < 9) ? mn[q] : 0.0;
+        for (int q = 0; q < 14; ++q) stage[10 + q] = mx[q];
+        stage[24] = h[27];  // phi max rides with the maxima
+        stage[25] = sm[0], stage[26] = sm[1];
+        O3D_CUDA_CHECK(cudaMemcpyAsync(w, stage, 27 * sizeof(double), cudaMemcpyHostToDevice, s->st));
+        if ((rc = comm_allreduce(s, w, 10, RED_MIN))) return rc;
+        if ((rc = comm_allreduce(s, w + 10, 15, RED_MAX))) return rc;
+        if ((rc = comm_allreduce(s, w + 25, 2, RED_SUM))) return rc;
+        double r[27];
+        O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h + 96, w, 27 * sizeof(double),
+                                       cudaMemcpyDeviceToHost, s->st));
+        O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+        for (int q = 0; q < 27; ++q) r[q] = s->scal_h[96 + q];
+        double pos[2] = {h[3], h[16]};
+        for (int t = 0; t < 2; ++t)
+            if (loc_max[t] < r[10 + 7 * t]) pos[t] = 9.0e18;
+        O3D_CUDA_CHECK(cudaMemcpyAsync(w, pos, 2 * sizeof(double), cudaMemcpyHostToDevice, s->st));
+        if ((rc = comm_allreduce(s, w, 2, RED_MIN))) return rc;
+        O3D_CUDA_CHECK(cudaMemcpyAsync(s->scal_h + 96, w, 2 * sizeof(double),
+                                       cudaMemcpyDeviceToHost, s->st));
+        O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+        for (int t = 0; t < 2; ++t) {
+            double* x = h + 13 * t;
+            x[0] = r[4 * t], x[1] = r[10 + 7 * t], x[2] = r[25 + t], x[3] = s->scal_h[96 + t];
+            for (int q = 0; q < 3; ++q)
+                x[4 + q] = r[4 * t + 1 + q], x[7 + q] = r[10 + 7 * t + 1 + q],
+                x[10 + q] = r[10 + 7 * t + 4 + q];
+        }
+        h[26] = r[8], h[27] = r[24];
+    }
+    const double cnt = (double)((long long)c.nx * c.ny * c.nz);
+    for (int t = 0; t < 2; ++t) {  // function_stats layout, src/functions.f90:27-63
+        const double* x = h + 13 * t;
+        double* o = out23 + 6 * t;
+        o[0] = x[0], o[1] = x[1], o[2] = x[2] / cnt;
+        long long m = (x[3] > 8.9e18) ? 0 : (long long)x[3];
+        o[3] = (double)(m % c.nx + 1);
+        o[4] = (double)((m / c.nx) % c.ny + 1);
+        o[5] = (double)(m / ((long long)c.nx * c.ny) + 1);
+    }
+    const double* xu = h + 13;
+    for (int q = 0; q < 3; ++q) out23[12 + q] = xu[4 + q], out23[15 + q] = xu[7 + q];
+    // src/utils.f90:199-201
+    out23[18] = xu[10] * c.dt / c.dx;
+    out23[19] = xu[11] * c.dt / c.dy;
+    out23[20] = xu[12] * c.dt / c.dz;
+    out23[21] = (c.nscr == 1) ? h[26] : 0.0;
+    out23[22] = (c.nscr == 1) ? h[27] : 0.0;
     return O3D_OK;
 }
 

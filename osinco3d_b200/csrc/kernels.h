@@ -230,6 +230,13 @@ int launch_residuals(cudaStream_t st, const Geom& g, const double* const* unew,
 // sum `nparts` partial triples deterministically: out[c] = sum_b partial[c*nparts + b]
 int launch_sum_partials(cudaStream_t st, const double* partial, int nparts, int ncomp,
                         double* out);
+// per-step driver diagnostics of one velocity triple in one pass (vel_kernels.cu, DiagEpi):
+// out13 = min, max, sum, first arg-max position (global array order, as a double) of
+// divergence(odd = 1) | minval u[3] | maxval u[3] | maxval |u|[3]; u needs own-axis odd ghosts;
+// partial >= 13 * diag_blocks(g) doubles
+int diag_blocks(const Geom& g);
+int launch_diag(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx, const Coef& cy,
+                const Coef& cz, double* partial, double* out13);
 // statistics_calc (src/utils.f90:243): 16 sums
 int stats_blocks(const Geom& g);
 int launch_stats(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,

@@ -361,6 +361,126 @@ struct StatsEpi {
     }
 };
 
+// Per-step diagnostics of the driver in ONE pass over a velocity triple:
+// divergence(odd = 1) (src/differential_operators.f90:25-35) fed straight into function_stats
+// (src/functions.f90:27-63: min, max with first-occurrence position, sum), plus minval / maxval
+// of each component (print_velocity_values, src/IOfunctions.f90:322) and maxval(abs())
+// (compute_cfl, src/utils.f90:199-201).  24 B/pt instead of divergence (32) + function_stats (8)
+// + nine reductions (72).
+constexpr int NDIAG = 13;  // dmin dmax dsum dlin | umin[3] | umax[3] | uabs[3]
+struct DiagEpi {
+    static constexpr int STREAMS = 3;
+    double* partial;  // [NDIAG][nblocks]
+    Coefs3 q;
+    int sim2d, nx, ny, gz0;
+    double dmin, dmax, dsum, umin[3], umax[3], uabs[3];
+    long long dlin;
+    typedef NoPre Pre;
+    __device__ __forceinline__ void setup(const MarchGeom& g, int, int) { nx = g.nx, ny = g.ny; }
+    __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
+    // z-field 0 = uz (7-plane window); centre-only fields 0, 1 = ux, uy (x / y halo of the plane
+    // being computed): the ring layout of the divergence kernel, 3 CTAs per SM
+    __device__ __forceinline__ void apply(const Ring<1, 2>& r, long long, int i, int j, int k,
+                                          const Pre&) {
+        const double dfx = r.c_d1x(0, q.x), dfy = r.c_d1y(1, q.y);
+        const double dfz = sim2d ? 0.0 : r.d1z(0, q.z);
+        const double dv = dfx + dfy + dfz;  // src/differential_operators.f90:35
+        const long long lin = ((long long)(gz0 + k) * ny + j) * nx + i;  // array-order position
+        dmin = fmin(dmin, dv);
+        dsum += dv;
+        if (dv > dmax) dmax = dv, dlin = lin;  // k ascending per thread: first occurrence
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double u = (c == 2) ? r.c(0) : r.cx(c, 0);
+            umin[c] = fmin(umin[c], u);
+            umax[c] = fmax(umax[c], u);
+            uabs[c] = fmax(uabs[c], fabs(u));
+        }
+    }
+    __device__ __forceinline__ void finish(int tid, double* smem) {
+        const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+        const int b = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        // warp level: min / max / sum by shuffles; the arg-max keeps the smaller position on ties
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+            const double om = __shfl_xor_sync(0xffffffffu, dmax, o);
+            const long long ol = __shfl_xor_sync(0xffffffffu, dlin, o);
+            if (om > dmax || (om == dmax && ol < dlin)) dmax = om, dlin = ol;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                umin[c] = fmin(umin[c], __shfl_xor_sync(0xffffffffu, umin[c], o));
+                umax[c] = fmax(umax[c], __shfl_xor_sync(0xffffffffu, umax[c], o));
+                uabs[c] = fmax(uabs[c], __shfl_xor_sync(0xffffffffu, uabs[c], o));
+            }
+        }
+        dsum = warp_sum(dsum);
+        if ((tid & 31) == 0) {
+            double* w = smem + (tid >> 5) * NDIAG;
+            w[0] = dmin, w[1] = dmax, w[2] = dsum, w[3] = (double)dlin;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) w[4 + c] = umin[c], w[7 + c] = umax[c], w[10 + c] = uabs[c];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double v[NDIAG];
+            for (int s = 0; s < NDIAG; ++s) v[s] = smem[s];
+            for (int w = 1; w < MNT / 32; ++w) {  // fixed order: deterministic
+                const double* x = smem + w * NDIAG;
+                v[0] = fmin(v[0], x[0]);
+                if (x[1] > v[1] || (x[1] == v[1] && x[3] < v[3])) v[1] = x[1], v[3] = x[3];
+                v[2] += x[2];
+                for (int c = 0; c < 3; ++c) {
+                    v[4 + c] = fmin(v[4 + c], x[4 + c]);
+                    v[7 + c] = fmax(v[7 + c], x[7 + c]);
+                    v[10 + c] = fmax(v[10 + c], x[10 + c]);
+                }
+            }
+            for (int s = 0; s < NDIAG; ++s) partial[(long long)s * nblocks + b] = v[s];
+        }
+    }
+};
+
+// merge the per-CTA partials of DiagEpi in a fixed order -> out[NDIAG]
+__global__ void __launch_bounds__(256) diag_stage2(const double* partial, int nblocks,
+                                                   double* out) {
+    __shared__ double red[8][NDIAG];
+    const int tid = threadIdx.x;
+    double v[NDIAG];
+    v[0] = 1.7976931348623157e308, v[1] = -1.7976931348623157e308, v[2] = 0.0;
+    v[3] = 9.0e18;
+    for (int c = 0; c < 3; ++c)
+        v[4 + c] = 1.7976931348623157e308, v[7 + c] = -1.7976931348623157e308, v[10 + c] = 0.0;
+    auto merge = [&](const double* x) {
+        v[0] = fmin(v[0], x[0]);
+        if (x[1] > v[1] || (x[1] == v[1] && x[3] < v[3])) v[1] = x[1], v[3] = x[3];
+        v[2] += x[2];
+        for (int c = 0; c < 3; ++c) {
+            v[4 + c] = fmin(v[4 + c], x[4 + c]);
+            v[7 + c] = fmax(v[7 + c], x[7 + c]);
+            v[10 + c] = fmax(v[10 + c], x[10 + c]);
+        }
+    };
+    for (int b = tid; b < nblocks; b += 256) {
+        double x[NDIAG];
+        for (int s = 0; s < NDIAG; ++s) x[s] = partial[(long long)s * nblocks + b];
+        merge(x);
+    }
+    // warp merge through shared memory (13 values per lane is too wide for shuffles to pay)
+    __shared__ double lane[256][NDIAG];
+    for (int s = 0; s < NDIAG; ++s) lane[tid][s] = v[s];
+    __syncthreads();
+    if ((tid & 31) == 0) {
+        for (int l = 1; l < 32; ++l) merge(lane[tid + l]);
+        for (int s = 0; s < NDIAG; ++s) red[tid >> 5][s] = v[s];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) merge(red[w]);
+        for (int s = 0; s < NDIAG; ++s) out[s] = v[s];
+    }
+}
+
 MarchMaps<3> maps3(const FieldRef& a, const FieldRef& b, const FieldRef& c) {
     MarchMaps<3> m;
     m.m[0] = *a.tm, m.m[1] = *b.tm, m.m[2] = *c.tm;
@@ -437,6 +557,26 @@ int launch_qcrit(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& 
     QEpi e;
     e.qc = q, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d;
     return launch_march<3, 0, 1, QEpi, 2>(st, g, maps3(u[0], u[1], u[2]), e);
+}
+
+int diag_blocks(const Geom& g) {
+    const int gx = (g.nx + MTX - 1) / MTX, gy = (g.ny + MTY - 1) / MTY;
+    const int zc = pick_zchunk(gx * gy, g.nz, 3, 1, DiagEpi::STREAMS);  // as launch_march below
+    return gx * gy * ((g.nz + zc - 1) / zc);
+}
+
+int launch_diag(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx, const Coef& cy,
+                const Coef& cz, double* partial, double* out13) {
+    DiagEpi e;
+    e.partial = partial, e.q = coefs(cx, cy, cz), e.sim2d = g.sim2d, e.gz0 = g.gz0;
+    e.dmin = 1.7976931348623157e308, e.dmax = -1.7976931348623157e308, e.dsum = 0.0;
+    e.dlin = 0x7fffffffffffffffLL;
+    for (int c = 0; c < 3; ++c)
+        e.umin[c] = 1.7976931348623157e308, e.umax[c] = -1.7976931348623157e308, e.uabs[c] = 0.0;
+    if (launch_march<1, 2, 2, DiagEpi, 3>(st, g, maps3(u[2], u[0], u[1]), e)) return 1;
+    diag_stage2<<<1, 256, 0, st>>>(partial, diag_blocks(g), out13);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 int stats_blocks(const Geom& g) {

@@ -139,6 +139,14 @@ class Session:
     def q_criterion(self, dst="scratch0"):
         check(lib().o3d_s_q_criterion(self._h, L.FIELD_ID[dst]))
 
+    def step_diagnostics(self):
+        """the per-step prints of src/osinco3d_main.f90:116-128 in two fused passes -> dict"""
+        o = (C.c_double * 23)()
+        check(lib().o3d_s_step_diagnostics(self._h, o))
+        o = list(o)
+        return {"divu_pred": o[0:6], "divu": o[6:12], "umin": o[12:15], "umax": o[15:18],
+                "cfl": o[18:21], "phi": o[21:23]}
+
     def old_values(self):
         """utils.old_values, src/utils.f90:165-176"""
         check(lib().o3d_s_old_values(self._h))

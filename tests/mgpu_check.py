@@ -105,6 +105,7 @@ def main():
         ses.old_values()
         iters.append(ses.step())
         resid = ses.calculate_residuals(0.02 * d, 1.0, 1.0)   # src/utils.f90:93-160
+        diag = ses.step_diagnostics()
         stats = ses.statistics()
         red = ses.reduce("ux", o3d.RED_ABSMAX)
         out = {k: ses.download(k) for k in ("ux", "uy", "uz", "pp", "phi", "ux_pred", "rhs")}
@@ -136,6 +137,16 @@ def main():
             if not (np.array_equal(resid[3:], resid1[3:]) and
                     np.allclose(resid[:3], resid1[:3], rtol=1e-12, atol=0)):
                 ok, msg = False, "residuals %s vs single-GPU %s" % (resid, resid1)
+            diag1 = one.step_diagnostics()
+            for key in diag:
+                a, b = np.array(diag[key]), np.array(diag1[key])
+                if key.startswith("divu"):   # the mean (index 2) is a differently associated sum
+                    same = np.array_equal(np.delete(a, 2), np.delete(b, 2)) and \
+                        abs(a[2] - b[2]) <= 1e-12 * max(abs(b[0]), abs(b[1]))
+                else:
+                    same = np.array_equal(a, b)
+                if not same:
+                    ok, msg = False, msg + " diagnostics[%s] %s vs %s;" % (key, a, b)
             st1 = one.statistics()
             red1 = one.reduce("ux", o3d.RED_ABSMAX)
             ref = {k: one.download(k) for k in out}

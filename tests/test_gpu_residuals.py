@@ -58,3 +58,44 @@ def test_residuals_tie_keeps_last_point_and_excludes_boundary(gpu, O):
     assert list(got[6:9]) == [8, 3, 7] and list(got[9:12]) == [6, 6, 2]
     assert list(got[12:15]) == [n[0] - 1, n[1] - 1, n[2] - 1] and got[5] == 0.0
     ses.close()
+
+
+@pytest.mark.parametrize("bc,n,nscr", [((1, 1, 1), (40, 33, 29), 1), ((0, 0, 0), (33, 32, 36), 0),
+                                       ((0, 1, 0), (64, 20, 41), 1)])
+def test_step_diagnostics_match_oracle(gpu, O, bc, n, nscr):
+    """o3d_s_step_diagnostics = divergence + function_stats of u* and u, minval/maxval, CFL
+    (src/osinco3d_main.f90:116-128) in two fused passes.  Divergence values are bit-identical to
+    the oracle's, so min / max / position are exact; the mean is a differently associated sum."""
+    d = tuple((PI if b else 2 * PI) / (m - 1) for b, m in zip(bc, n))
+    g = O.grid(*n, *d, bc)
+    ux, uy, uz, pp, phi = O.init_tgv(g, nscr=1)
+    dt = 0.02 * d[0]
+    cfg = gpu.make_config(*n, *d, bc=bc, re=400.0, dt=dt, itscheme=3, nscr=nscr, omega=1.7,
+                          eps=1e-7, kmax=2000)
+    ses = gpu.Session(cfg)
+    ses.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+    for _ in range(3):
+        ses.step()
+    got = ses.step_diagnostics()
+    f = {k: ses.download(k) for k in ("ux", "uy", "uz", "ux_pred", "uy_pred", "uz_pred", "phi")}
+    for key, names in (("divu_pred", ("ux_pred", "uy_pred", "uz_pred")), ("divu", ("ux", "uy", "uz"))):
+        div = O.divergence(g, *[f[k] for k in names], 1)
+        exp = O.function_stats(div)
+        assert got[key][0] == exp[0] and got[key][1] == exp[1], (key, got[key], exp)
+        assert list(got[key][3:]) == list(exp[3:]), (key, got[key], exp)
+        assert abs(got[key][2] - exp[2]) <= 1e-12 * np.max(np.abs(div)), (key, got[key][2], exp[2])
+    for q, k in enumerate(("ux", "uy", "uz")):
+        assert got["umin"][q] == f[k].min() and got["umax"][q] == f[k].max()
+        assert got["cfl"][q] == np.abs(f[k]).max() * dt / d[q]        # src/utils.f90:199-201
+    if nscr:
+        assert got["phi"] == [f["phi"].min(), f["phi"].max()]
+    # the diagnostics must not disturb the state: the next steps equal an undisturbed run
+    ref = gpu.Session(cfg)
+    ref.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+    for _ in range(4):
+        ref.step()
+    ses.step()
+    for k in ("ux", "uy", "uz", "pp"):
+        assert np.array_equal(ses.download(k), ref.download(k)), k
+    ref.close()
+    ses.close()
