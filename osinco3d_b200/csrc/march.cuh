@@ -203,9 +203,12 @@ __global__ void __launch_bounds__(MNT, MINB)
 
     long long m = m0 + (long long)kb * g.sz;
     if constexpr (UNR > 1) {
-        static_assert(UNR % NZS == 0 && UNR % NCS == 0 && UNR % NB == 0 && (UNR / NB) % 2 == 0,
-                      "UNR must be a common multiple of the ring lengths (even in barrier rounds)");
-        for (int k0 = kb; k0 < ke; k0 += UNR) {
+        static_assert(UNR % NZS == 0 && UNR % NCS == 0 && UNR % NB == 0,
+                      "UNR must be a common multiple of the ring lengths");
+        // barrier phase of the first round of an unrolled block: flips from block to block when a
+        // block holds an odd number of barrier rounds
+        uint32_t bp = 0;
+        for (int k0 = kb; k0 < ke; k0 += UNR, bp ^= (uint32_t)((UNR / NB) & 1)) {
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 const int k = k0 + u;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(MNT, MINB)
                     typename Epi::Pre nxt = epi.prefetch(m + g.sz, in_dom && (k + 1 < ke));
                     __syncthreads();
                     if (tid == 0 && it + P < niter) issue_group(it + P);
-                    mbar_wait(bars_s + 8 * (u % NB), (uint32_t)((u / NB) & 1));
+                    mbar_wait(bars_s + 8 * (u % NB), bp ^ (uint32_t)((u / NB) & 1));
                     if (in_dom) {
                         Ring<NFZ, NFC> r;
 #pragma unroll

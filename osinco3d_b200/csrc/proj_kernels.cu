@@ -5,6 +5,8 @@
 //   CorrEpi (march engine): u = u* - dt grad p with the NaN / >1000 guard fused in
 //             (src/integration.f90:298-325).  pp(1)+u*(3) reads, u(3) writes = 56 B/pt.
 //             u* arrives through TMA stream fields (32 x 8 boxes, 3 planes ahead).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "march.cuh"
 
@@ -28,12 +30,18 @@ struct DivEpi {
     Img2 ix, iy;
     int nz, bz_lo, bz_hi;
     long long sy_, sz_;
+    // image stores are the exception: one flag per thread for x/y, one plane test for z
+    bool edge_xy;
+    int zimg_lo, zimg_hi;
     typedef NoPre Pre;
     __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j) {
         ix = image_offsets(i, g.nx, g.bx, g.bx);
         iy = image_offsets(j, g.ny, g.by, g.by);
         nz = g.nz, bz_lo = g.bz_lo, bz_hi = g.bz_hi;
         sy_ = g.sy, sz_ = g.sz;
+        edge_xy = (ix.lo | ix.hi | iy.lo | iy.hi) != 0;
+        zimg_lo = (g.bz_lo == BM_MIRROR || g.bz_hi == BM_WRAP) ? R : -1;
+        zimg_hi = (g.bz_hi == BM_MIRROR || g.bz_lo == BM_WRAP) ? g.nz - 1 - R : g.nz;
     }
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     __device__ __forceinline__ void apply(const Ring<1, 2>& r, long long m, int, int, int k,
@@ -44,8 +52,8 @@ struct DivEpi {
         double v = dfx + dfy + dfz;  // src/differential_operators.f90:35
         if (divide) v = v / dt;      // src/integration.f90:239
         out[m] = v;
-        const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
-        if (ix.lo | ix.hi | iy.lo | iy.hi | iz.lo | iz.hi) {  // boundary-adjacent threads only
+        if (edge_xy || k <= zimg_lo || k >= zimg_hi) {  // boundary-adjacent points only
+            const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
             if (ix.lo) out[m + ix.lo] = v;
             if (ix.hi) out[m + ix.hi] = v;
             if (iy.lo) out[m + iy.lo * sy_] = v;
@@ -72,6 +80,8 @@ struct CorrEpi {
     int nz, bz_lo, bz_hi;
     long long sy_, sz_;
     bool mx, my, mz_lo, mz_hi;  // mirrored sides
+    bool edge_xy;
+    int zimg_lo, zimg_hi;
     typedef NoPre Pre;
     __device__ __forceinline__ void setup(const MarchGeom& g, int i, int j) {
         ix = image_offsets(i, g.nx, g.bx, g.bx);
@@ -80,6 +90,9 @@ struct CorrEpi {
         sy_ = g.sy, sz_ = g.sz;
         mx = g.bx == BM_MIRROR, my = g.by == BM_MIRROR;
         mz_lo = g.bz_lo == BM_MIRROR, mz_hi = g.bz_hi == BM_MIRROR;
+        edge_xy = (ix.lo | ix.hi | iy.lo | iy.hi) != 0;
+        zimg_lo = (g.bz_lo == BM_MIRROR || g.bz_hi == BM_WRAP) ? R : -1;
+        zimg_hi = (g.bz_hi == BM_MIRROR || g.bz_lo == BM_WRAP) ? g.nz - 1 - R : g.nz;
     }
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     // z-field 0 = pp (7-plane window); stream fields 0..2 = u* (TMA, 3 planes ahead)
@@ -96,8 +109,8 @@ struct CorrEpi {
         u[0][m] = u0;
         u[1][m] = u1;
         u[2][m] = u2;
-        const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
-        if (ix.lo | ix.hi | iy.lo | iy.hi | iz.lo | iz.hi) {  // boundary-adjacent threads only
+        if (edge_xy || k <= zimg_lo || k >= zimg_hi) {  // boundary-adjacent points only
+            const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
             const double v[3] = {u0, u1, u2};
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -134,6 +147,9 @@ static int launch_div_t(cudaStream_t st, const Geom& g, const FieldRef* f, const
     m.m[0] = *f[2].tm;  // z-window field first
     m.m[1] = *f[0].tm;
     m.m[2] = *f[1].tm;
+    // O3D_DIV_UNROLL=1: plane loop unrolled over the 9-stage ring (march.cuh UNR)
+    static const bool unr = getenv("O3D_DIV_UNROLL") && atoi(getenv("O3D_DIV_UNROLL")) == 1;
+    if (unr) return launch_march<1, 2, 2, DivEpi<S2>, 3, 0, 0, 9>(st, g, m, e, zmode, zedge);
     return launch_march<1, 2, 2, DivEpi<S2>, 3>(st, g, m, e, zmode, zedge);
 }
 
@@ -162,6 +178,14 @@ static int launch_corr_t(cudaStream_t st, const Geom& g, const FieldRef& pp, con
     MarchMaps<4> m;
     m.m[0] = *pp.tm;
     for (int c = 0; c < 3; ++c) m.m[1 + c] = *up[c].tms;
+    // O3D_CORR_VARIANT: 0 = 3 planes ahead, rolled loop (default); 1 = same, unrolled over the
+    // rings (20 planes); 2 = 2 planes ahead, unrolled (9 planes); 3 = 2 planes ahead, rolled
+    static const int variant = getenv("O3D_CORR_VARIANT") ? atoi(getenv("O3D_CORR_VARIANT")) : 0;
+    if (variant == 1)
+        return launch_march<1, 0, 3, CorrEpi<S2>, 3, 3, 0, 20>(st, g, m, e, zmode, zedge);
+    if (variant == 2)
+        return launch_march<1, 0, 2, CorrEpi<S2>, 3, 3, 0, 9>(st, g, m, e, zmode, zedge);
+    if (variant == 3) return launch_march<1, 0, 2, CorrEpi<S2>, 3, 3>(st, g, m, e, zmode, zedge);
     return launch_march<1, 0, 3, CorrEpi<S2>, 3, 3>(st, g, m, e, zmode, zedge);
 }
 
