@@ -140,3 +140,60 @@ def test_mixing_layer_full_size_multigrid_vs_sor(gpu, O):
     assert np.max(np.abs(a - b)) / np.max(np.abs(b)) < 5e-3, np.max(np.abs(a - b)) / np.max(np.abs(b))
     assert it_mg <= 15
     print("241x241x81 mixing layer: multigrid %d V-cycles vs red-black SOR %d iterations" % (it_mg, it_rb))
+
+
+@pytest.mark.parametrize("example,solver", [("mixing_layer", "sor"), ("coplanar_jet", "sor"),
+                                            ("mixing_layer", "multigrid")])
+def test_shipped_examples_full_size_steps_and_timing(gpu, O, example, solver):
+    """BASELINE.json configs[3] / [4] at the SHIPPED sizes (241 x 241 x 81 LES + scalar;
+    257 x 513 x 129, odd periodic extents) with the shipped Poisson settings through the
+    device-resident session: size-independent properties (finite fields, max|div u| below
+    max|div u*|, scalar stays in [0, 1], kinetic energy changes slowly) and the measured stage
+    times, written to $O3D_TIMING_OUT (JSON lines) when set -- profiles/ keeps a copy."""
+    import json
+    import os
+    if example == "mixing_layer":
+        g, d, f, kw = mixing_layer(O, 241, 241, 81)
+    else:
+        g, d, f, kw = coplanar_jet(O, 257, 513, 129)
+    ux, uy, uz, pp, phi = f
+    cfg = gpu.make_config(g.nx, g.ny, g.nz, *d, bc=tuple(g.bc), re=kw["re"], sc=kw.get("sc", 1.0),
+                          cs=kw.get("cs", 0.0), dt=kw["dt"], itscheme=kw["itscheme"],
+                          iles=kw["iles"], nscr=kw["nscr"], omega=kw["omega"], eps=kw["eps"],
+                          kmax=kw["kmax"], idyn=kw["idyn"], multigrid=1 if solver == "multigrid" else 0)
+    ses = gpu.Session(cfg)
+    ses.set(ux=ux, uy=uy, uz=uz, pp=pp)
+    if kw["nscr"]:
+        ses.set(phi=phi)
+    e0 = ses.statistics()[1]
+    warm, timed = 4, 8
+    for _ in range(warm):
+        ses.step()
+    ses.enable_timers(True)
+    ses.timers(reset=True)
+    ses.stopwatch_start()
+    iters = [ses.step() for _ in range(timed)]
+    ms = ses.stopwatch_stop() / timed
+    tm = ses.timers(reset=True)
+    ses.enable_timers(False)
+    diag = ses.step_diagnostics()
+    e1 = ses.statistics()[1]
+    assert all(np.isfinite(v) for v in diag["umin"] + diag["umax"] + diag["divu"][:3])
+    # the projection reduces the divergence (at the shipped, loose eps only by a modest factor)
+    assert max(abs(diag["divu"][0]), abs(diag["divu"][1])) < \
+        max(abs(diag["divu_pred"][0]), abs(diag["divu_pred"][1]))
+    assert abs(e1 - e0) < 0.05 * e0
+    if kw["nscr"]:
+        assert -1e-12 <= diag["phi"][0] and diag["phi"][1] <= 1.0 + 1e-12
+    npts = g.nx * g.ny * g.nz
+    rec = {"example": example, "solver": solver, "grid": [g.nx, g.ny, g.nz],
+           "ms_per_step": ms, "Mpts_steps_per_s": npts / 1e6 / (ms / 1e3),
+           "poisson_iterations_per_step": float(np.mean(iters)),
+           "stage_ms_per_step": {k: v[0] / timed for k, v in tm.items() if v[0] > 0},
+           "settings": {k: kw[k] for k in ("re", "dt", "omega", "eps", "kmax", "idyn", "iles", "nscr")}}
+    print(json.dumps(rec))
+    out = os.environ.get("O3D_TIMING_OUT")
+    if out:
+        with open(out, "a") as fh:
+            fh.write(json.dumps(rec) + "\n")
+    ses.close()
