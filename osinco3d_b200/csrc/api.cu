@@ -511,6 +511,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->trace_step = getenv("O3D_TRACE") ? atoi(getenv("O3D_TRACE")) : -1;
     s->sw_a = nullptr, s->sw_b = nullptr;
     s->ctrl_d = nullptr, s->ctrl_h = nullptr, s->flag_d = nullptr, s->flag_h = nullptr;
+    s->seam_sync_d = nullptr;
     s->scal_d = nullptr, s->scal_h = nullptr;
     fill_geom(s);
     cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
@@ -525,6 +526,8 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->ctrl_d, sizeof(SorCtrl));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_h, sizeof(SorCtrl), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&s->seam_sync_d, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(s->seam_sync_d, 0, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&s->flag_d, sizeof(int));
     // the NaN / >1000 flag is sticky (only cleared when reported): it must start clean
     if (e == cudaSuccess) e = cudaMemset(s->flag_d, 0, sizeof(int));
@@ -557,6 +560,7 @@ int o3d_session_destroy(o3d_session* s) {
     if (s->partial) cudaFree(s->partial);
     if (s->stage_d) cudaFree(s->stage_d);
     if (s->ctrl_d) cudaFree(s->ctrl_d);
+    if (s->seam_sync_d) cudaFree(s->seam_sync_d);
     if (s->ctrl_h) cudaFreeHost(s->ctrl_h);
     if (s->flag_d) cudaFree(s->flag_d);
     if (s->flag_h) cudaFreeHost(s->flag_h);

@@ -167,6 +167,10 @@ struct SorArgs {
 // sweep can follow the fused TMA pass on its output buffer
 int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class, SorCtrl* ctrl,
                   int images = 0);
+// single rank: both odd seam classes (with ghost images) and the end-of-iteration control in one
+// cooperative launch; sync = 2 zero-initialised device counters that persist across launches
+int launch_sor_seam_fused(cudaStream_t st, const SorArgs& a, SorCtrl* ctrl,
+                          unsigned long long* sync, double eps, int kmax, int idyn, double factor);
 // fused red+black iteration (one pass, ping-pong p_old -> p_new); needs a 2-colourable grid
 // zmode / zedge: split launch as for the march kernels (0 = whole slab)
 int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,

@@ -77,7 +77,9 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     const char* e_seam = getenv("O3D_SOR_SEAM");
     const bool legacy = e_fused && !strcmp(e_fused, "legacy");
     const bool seam_inplace = e_seam && !strcmp(e_seam, "inplace");
-    const bool fused = !wavefront && (!seams || (!legacy && !seam_inplace));
+    const bool seam_split = e_seam && !strcmp(e_seam, "split");  // seam classes as 2 launches
+    const bool fused_off = e_fused && !strcmp(e_fused, "off");  // in-place half-sweeps always
+    const bool fused = !wavefront && !fused_off && (!seams || (!legacy && !seam_inplace));
     const bool tma = fused && !legacy;
     double* alt = nullptr;
     if (fused) {
@@ -165,6 +167,13 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                     // rewrite the ghost images of the points they touch
                     SorArgs sa = a;
                     sa.pp = dst;
+                    if (!multi && !seam_split) {
+                        // one cooperative launch: both classes + the end-of-iteration control
+                        if (launch_sor_seam_fused(s->st, sa, s->ctrl_d, s->seam_sync_d, c.eps,
+                                                  c.kmax, c.idyn, factor))
+                            return O3D_ERR_CUDA;
+                        continue;
+                    }
                     double* dstf[1] = {dst - ioff};
                     for (int colour = 0; colour < 2; ++colour) {
                         if (multi && comm_exchange(s, dstf, 1, 1, zwrap)) return O3D_ERR_COMM;

@@ -44,6 +44,7 @@ struct o3d_session {
     // SOR
     o3d::SorCtrl* ctrl_d;
     o3d::SorCtrl* ctrl_h;  // pinned
+    unsigned long long* seam_sync_d;  // grid-barrier / finish counters of sor_seam_fused_kernel
     int sor_variant;       // 0: _0000, 1: _0011, 2: _111111
     int last_iters;
     double omega;

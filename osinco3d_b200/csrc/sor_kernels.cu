@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(256) sor_wavefront_kernel(const SorArgs a, int
 }
 
 // src/poisson.f90:110-122, evaluated once per completed sweep
-__global__ void sor_control_kernel(SorCtrl* c, double eps, int kmax, int idyn, double factor) {
+__device__ __forceinline__ void sor_control_step(SorCtrl* c, double eps, int kmax, int idyn,
+                                                 double factor) {
     if (c->done) return;
     const double dmax = __longlong_as_double((long long)c->dmax_bits);
     c->dmax_bits = 0ull;
@@ -399,6 +400,94 @@ __global__ void sor_control_kernel(SorCtrl* c, double eps, int kmax, int idyn, d
     }
     c->dmax_old = dmax;
     if (iter >= kmax) c->done = 3;  // loop exhausted
+}
+__global__ void sor_control_kernel(SorCtrl* c, double eps, int kmax, int idyn, double factor) {
+    sor_control_step(c, eps, kmax, idyn, factor);
+}
+
+// ------------------------------------------------------------------------------------------
+// Both odd seam classes AND the end-of-iteration control in ONE launch (single rank): the seam
+// sets are thin (~3/n of the grid), so three separate launches cost mostly launch latency --
+// on the shipped 241 x 241 x 81 mixing layer (84 iterations per step) that is a third of the
+// solve.  Cooperative launch (all CTAs co-resident), grid-stride loops, one hand-rolled grid
+// barrier between the red and the black class; the last CTA to finish evaluates the exit tests
+// and the dynamic omega (threadfence-reduction pattern).  sync[0]: barrier arrivals (monotone),
+// sync[1]: finish arrivals (monotone).
+__device__ __forceinline__ void seam_point_of(const SorArgs& a, long long t, long long nxf,
+                                              long long nyf, long long nzf, int& i, int& j,
+                                              int& k, bool& ok) {
+    ok = false;
+    i = j = k = -1;
+    if (t < nxf) {  // x seam plane: (nx-1, j, k)
+        i = a.nx - 1;
+        j = (int)(t % a.ny);
+        k = (int)(t / a.ny);
+        ok = true;
+    } else if ((t -= nxf) < nyf) {  // y seam plane, excluding points on the x seam
+        j = a.ny - 1;
+        i = (int)(t % a.nx);
+        k = (int)(t / a.nx);
+        ok = !(a.seam_x && i == a.nx - 1);
+    } else if ((t -= nyf) < nzf) {  // z seam plane
+        k = a.nz - 1;
+        i = (int)(t % a.nx);
+        j = (int)(t / a.nx);
+        ok = !(a.seam_x && i == a.nx - 1) && !(a.seam_y && j == a.ny - 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    sor_seam_fused_kernel(const SorArgs a, SorCtrl* ctrl, long long nxf, long long nyf,
+                          long long nzf, unsigned long long* sync, double eps, int kmax, int idyn,
+                          double factor) {
+    __shared__ double red[32];
+    __shared__ int last_s;
+    if (*((volatile int*)&ctrl->done)) return;  // uniform over the grid: no CTA reaches a barrier
+    const bool active = true;
+    const double omega = *((volatile double*)&ctrl->omega);
+    const long long tot = nxf + nyf + nzf;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double dmax = 0.0;
+    for (int colour = 0; colour < 2; ++colour) {
+        if (active) {
+            for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot;
+                 t += stride) {
+                int i, j, k;
+                bool ok;
+                seam_point_of(a, t, nxf, nyf, nzf, i, j, k, ok);
+                if (ok) {
+                    const int gk = a.gz0 + k;
+                    if (((i + j + gk) & 1) == colour && (seam_pop(a, i, j, gk) & 1))
+                        dmax = fmax(dmax, sor_point<true>(a, i, j, k, omega));
+                }
+            }
+        }
+        if (colour == 0) {
+            // grid barrier: the black class reads what the red class of other CTAs wrote
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                const unsigned long long t = atomicAdd(&sync[0], 1ull);
+                const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
+                while (*((volatile unsigned long long*)&sync[0]) < target) {
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+    const double bm = block_max(dmax, red);
+    if (threadIdx.x == 0) {
+        if (bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+        __threadfence();
+        const unsigned long long t = atomicAdd(&sync[1], 1ull);
+        last_s = (t % gridDim.x) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_s && threadIdx.x == 0) {
+        __threadfence();
+        sor_control_step(ctrl, eps, kmax, idyn, factor);
+    }
 }
 
 }  // namespace
@@ -427,6 +516,36 @@ int launch_sor_rb(cudaStream_t st, const SorArgs& a, int colour, int seam_class,
     }
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_sor_seam_fused(cudaStream_t st, const SorArgs& a, SorCtrl* ctrl,
+                          unsigned long long* sync, double eps, int kmax, int idyn,
+                          double factor) {
+    long long nxf = a.seam_x ? (long long)a.ny * a.nz : 0;
+    long long nyf = a.seam_y ? (long long)a.nx * a.nz : 0;
+    long long nzf = a.seam_z ? (long long)a.nx * a.ny : 0;
+    const long long tot = nxf + nyf + nzf;
+    // co-resident grid: at most 4 CTAs of 256 threads per SM
+    static int max_ctas = 0;
+    if (!max_ctas) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_seam_fused_kernel, 256, 0);
+        if (per_sm > 4) per_sm = 4;
+        max_ctas = per_sm * sms;
+        if (max_ctas < 1) return 1;
+    }
+    long long nb = (tot + 255) / 256;
+    if (nb > max_ctas) nb = max_ctas;
+    if (nb < 1) nb = 1;
+    SorArgs aa = a;
+    void* args[] = {(void*)&aa,  (void*)&ctrl, (void*)&nxf,  (void*)&nyf,  (void*)&nzf,
+                    (void*)&sync, (void*)&eps,  (void*)&kmax, (void*)&idyn, (void*)&factor};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)sor_seam_fused_kernel,
+                                                      dim3((unsigned)nb), dim3(256), args, 0, st);
+    count_launch();
+    return e == cudaSuccess ? 0 : 1;
 }
 
 int launch_sor_fused(cudaStream_t st, const SorArgs& a, const double* p_old, double* p_new,

@@ -60,6 +60,17 @@ struct alignas(64) TmaSorMaps {
     CUtensorMap p, rhs;
 };
 
+// shared-memory accesses as [register + immediate] through the 32-bit shared window
+template <int OFF>
+__device__ __forceinline__ double lds(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
 template <bool SEAM>
 __global__ void __launch_bounds__(GNT, 3)
     sor_tma_kernel(const __grid_constant__ TmaSorMaps maps, const TmaSorArgs a, SorCtrl* ctrl) {
@@ -178,59 +189,80 @@ __global__ void __launch_bounds__(GNT, 3)
     const int zimg_hi = (a.bz_hi == BM_MIRROR || a.bz_lo == BM_WRAP) ? a.nz - 1 - R : a.nz;
 
     double dmax = 0.0;
-    // SOR update of cell c of plane S0 (src/poisson.f90:95-102, "/ A" as "* (1/A)": this ordering
-    // is not the bit-parity one); returns the relaxed value, d = |p_new - p_old|
-    auto update = [&](const double* Sm, const double* S0, const double* Sp, const double* Rr,
-                      int c, double& d) -> double {
-        const double pc = S0[c];
-        const double p_new = (-(a.ox * (S0[c - 1] + S0[c + 1])) -
-                              a.oy * (S0[c - GBX] + S0[c + GBX]) - a.oz * (Sm[c] + Sp[c]) + Rr[c]) *
-                             a.invA;
-        d = fabs(p_new - pc);                      // :100
-        return one_m_omega * pc + omega * p_new;   // :102
+    // ---- hot loop -------------------------------------------------------------------------
+    // The pass is issue-bound (64 % of the issue slots at 3 CTAs/SM), so the loop is written for
+    // instruction count: staged planes are addressed through 32-bit shared-window byte addresses
+    // kept in registers and rotated (no index -> pointer arithmetic per access), every load is
+    // ld.shared [reg + immediate], and the colour of the pair's members alternates from plane to
+    // plane by XOR-ing precomputed offsets.
+    constexpr uint32_t PLB = GPL * 8;  // bytes per staged plane
+    const uint32_t p_end = sp_s + GNP * PLB, r_end = sr_s + GNR * PLB;
+    auto nextp = [&](uint32_t x) { return x + PLB == p_end ? sp_s : x + PLB; };
+    auto nextr = [&](uint32_t x) { return x + PLB == r_end ? sr_s : x + PLB; };
+    // SOR update of the cell at byte offset c of the plane at a0 (am / ap = planes below / above,
+    // ar = rhs plane): src/poisson.f90:95-102 with "/ A" as "* (1/A)" (this ordering is not the
+    // bit-parity one); returns the relaxed value, d = |p_new - p_old|, pc = the old value
+    auto update = [&](uint32_t am, uint32_t a0, uint32_t ap, uint32_t ar, uint32_t c, double& d,
+                      double& pc) -> double {
+        const uint32_t c0 = a0 + c;
+        pc = lds<0>(c0);
+        const double w = lds<-8>(c0), e = lds<8>(c0);
+        const double sn = lds<-GBX * 8>(c0), nn = lds<GBX * 8>(c0);
+        const double bb = lds<0>(am + c), tt = lds<0>(ap + c), rr = lds<0>(ar + c);
+        const double p_new =
+            (-(a.ox * (w + e)) - a.oy * (sn + nn) - a.oz * (bb + tt) + rr) * a.invA;
+        d = fabs(p_new - pc);                     // :100
+        return one_m_omega * pc + omega * p_new;  // :102
     };
-    // Stage of p plane q: (q - (kb-2)) mod GNP; of rhs plane q: (q - (kb-1)) mod GNR.  The march
-    // keeps the stage indices of planes k-1 .. k+3 (p) and k .. k+2 (rhs) in registers and rotates
-    // them, so the hot loop has no modulo arithmetic.
-    auto nextp = [](int st) { return st + 1 == GNP ? 0 : st + 1; };
-    auto nextr = [](int st) { return st + 1 == GNR ? 0 : st + 1; };
-    // red half-sweep of plane q (stages sm, s0, s1 = planes q-1, q, q+1; rs = rhs plane q) over
-    // the own pair and the ring pair; counted: the plane is owned by this chunk
-    auto red_plane = [&](int q, int sm, int s0, int s1, int rs, bool counted) {
-        double* S0 = sp + s0 * GPL;
-        const double *Sm = sp + sm * GPL, *Sp = sp + s1 * GPL, *Rr = sr + rs * GPL;
-        const int r = (pe + q) & 1;  // 0: member A is red in plane q, 1: member B
-        double d;
-        const int c = own + r * GBX;
-        double v = update(Sm, S0, Sp, Rr, c, d);
-        bool ring_on = rcell >= 0;  // warps 0 and 1 only
-        const int rm = (rpar + q) & 1;
+    const uint32_t ownA8 = own * 8, ownB8 = (own + GBX) * 8, cxor = ownA8 ^ ownB8;
+    const bool has_ring = rcell >= 0;  // warps 0 and 1 only
+    const uint32_t ring0 = has_ring ? rcell * 8 : 0, ring1 = has_ring ? (rcell + rstep) * 8 : 0;
+    const uint32_t rxor = ring0 ^ ring1;
+    // r = 1: member B of the pair is the red one in the current plane (member A otherwise);
+    // c_red / c_blk = byte offsets of the red / black member; rc = the red cell of the ring pair,
+    // rmm = which of its two cells that is.  All flip from plane to plane.
+    int r = (pe + kb) & 1, rmm = (rpar + kb) & 1;
+    uint32_t c_red = r ? ownB8 : ownA8, c_blk = r ? ownA8 : ownB8;
+    uint32_t rc = rmm ? ring1 : ring0;
+    auto flip = [&]() { r ^= 1, rmm ^= 1, c_red ^= cxor, c_blk ^= cxor, rc ^= rxor; };
+    // red half-sweep of the plane at a0 (global plane q) over the own pair and the ring pair;
+    // counted: the plane is owned by this chunk
+    auto red_plane = [&](int q, uint32_t am, uint32_t a0, uint32_t ap, uint32_t ar, bool counted) {
+        double d, pc;
+        double v = update(am, a0, ap, ar, c_red, d, pc);
+        bool ring_on = has_ring;
         if (SEAM) {
             const int zs = zseam(q);
-            if (zs == 2 || (((own_par >> r) ^ zs) & 1)) v = S0[c], d = 0.0;  // odd class: keep
-            const int code = (ring_code >> (2 * rm)) & 3;
+            if (zs == 2 || (((own_par >> r) ^ zs) & 1)) v = pc, d = 0.0;  // odd class: keep
+            const int code = (ring_code >> (2 * rmm)) & 3;
             ring_on = ring_on && zs != 2 && code != 2 && !((code ^ zs) & 1);
         }
         if (ring_on) {
-            double dr;
-            const int rc = rcell + (rm ? rstep : 0);
-            S0[rc] = update(Sm, S0, Sp, Rr, rc, dr);
+            double dr, pr;
+            const double vr = update(am, a0, ap, ar, rc, dr, pr);
+            sts(a0 + rc, vr);
         }
         // (a red cell has no red neighbour: every read above is of a black cell or of the cell's
-        // own centre, every write below of a red cell owned by exactly one thread)
-        S0[c] = v;
-        dmax = fmax(dmax, (counted && (r ? inB : inA)) ? d : 0.0);
+        // own centre, every write of a red cell owned by exactly one thread)
+        sts(a0 + c_red, v);
+        if (counted && (r ? inB : inA)) dmax = fmax(dmax, d);
     };
 
     mbar_wait(bars_s, 0);  // group 0: p planes kb-2 .. kb+3 in stages 0 .. 5, rhs kb-1 .. kb+2 in 0 .. 3
-    red_plane(kb - 1, 0, 1, 2, 0, false);
-    red_plane(kb, 1, 2, 3, 1, true);
-    red_plane(kb + 1, 2, 3, 4, 2, kb + 1 < ke);
+    flip();  // plane kb-1 has the other parity
+    red_plane(kb - 1, sp_s, sp_s + PLB, sp_s + 2 * PLB, sr_s, false);
+    flip();
+    red_plane(kb, sp_s + PLB, sp_s + 2 * PLB, sp_s + 3 * PLB, sr_s + PLB, true);
+    flip();
+    red_plane(kb + 1, sp_s + 2 * PLB, sp_s + 3 * PLB, sp_s + 4 * PLB, sr_s + 2 * PLB, kb + 1 < ke);
+    flip();  // back to the parity of plane kb
 
-    int p_m1 = 1, p_0 = 2, p_1 = 3, p_2 = 4, p_3 = 5;  // stages of planes k-1 .. k+3 (k = kb)
-    int r_0 = 1, r_2 = 3;                              // stages of rhs planes k, k+2
+    // addresses of the staged planes k-1 .. k+3 (p) and k, k+2 (rhs) for k = kb
+    uint32_t a_m1 = sp_s + PLB, a_0 = sp_s + 2 * PLB, a_1 = sp_s + 3 * PLB, a_2 = sp_s + 4 * PLB,
+             a_3 = sp_s + 5 * PLB;
+    uint32_t ar_0 = sr_s + PLB, ar_2 = sr_s + 3 * PLB;
     double* outp = a.p_new + (long long)kb * a.sz + (long long)gj * a.sy + gi;
-    int bi = 1 % GNB;          // barrier index / phase of group n = 1
+    int bi = 1 % GNB;  // barrier index / phase of group n = 1
     uint32_t bpar = 0;
     for (int k = kb; k < ke; ++k) {
         const int n = k - kb;
@@ -240,18 +272,16 @@ __global__ void __launch_bounds__(GNT, 3)
             if (n < ngroups) mbar_wait(bars_s + 8 * bi, bpar);
             if (++bi == GNB) bi = 0, bpar ^= 1u;
         }
-        if (k + 2 <= ke) red_plane(k + 2, p_1, p_2, p_3, r_2, k + 2 < ke);
+        // planes k+2 and k have the same parity: the same member is red in both
+        if (k + 2 <= ke) red_plane(k + 2, a_1, a_2, a_3, ar_2, k + 2 < ke);
         {
             // black member of the own pair in plane k: all six neighbours hold new red values
-            const int r = (pe + k) & 1;  // member r is red, member 1-r black
-            const double* S0 = sp + p_0 * GPL;
-            double d;
-            double vb = update(sp + p_m1 * GPL, S0, sp + p_1 * GPL, sr + r_0 * GPL,
-                               own + (1 - r) * GBX, d);
+            double d, pcb;
+            double vb = update(a_m1, a_0, a_1, ar_0, c_blk, d, pcb);
             if (SEAM && (((own_par >> (1 - r)) ^ zseam(k)) & 1))
-                vb = S0[own + (1 - r) * GBX], d = 0.0;  // odd class: swept by sor_seam_kernel
-            const double vred = S0[own + r * GBX];
-            dmax = fmax(dmax, (r ? inA : inB) ? d : 0.0);
+                vb = pcb, d = 0.0;  // odd class: swept by sor_seam_kernel
+            const double vred = lds<0>(a_0 + c_red);
+            if (r ? inA : inB) dmax = fmax(dmax, d);
             const double vA = r ? vb : vred, vB = r ? vred : vb;
             if (inA) outp[0] = vA;
             if (inB) outp[a.sy] = vB;
@@ -266,8 +296,9 @@ __global__ void __launch_bounds__(GNT, 3)
             }
         }
         outp += a.sz;
-        p_m1 = p_0, p_0 = p_1, p_1 = p_2, p_2 = p_3, p_3 = nextp(p_3);
-        r_0 = nextr(r_0), r_2 = nextr(r_2);
+        flip();
+        a_m1 = a_0, a_0 = a_1, a_1 = a_2, a_2 = a_3, a_3 = nextp(a_3);
+        ar_0 = nextr(ar_0), ar_2 = nextr(ar_2);
     }
     const double bm = block_max(dmax, red);
     if (tid == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);

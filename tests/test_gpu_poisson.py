@@ -178,16 +178,52 @@ def test_fused_seam_pass_equals_inplace_class_sweeps_bitwise(gpu, variant, shape
     p0 = rand_field(shape, 12, 0.1)
     fn = getattr(M, "poisson_solver_" + variant)
     out = {}
-    for mode in ("inplace", "fused"):
-        if mode == "inplace":
-            monkeypatch.setenv("O3D_SOR_SEAM", "inplace")
-        else:
+    for mode in ("inplace", "split", "fused"):
+        # inplace: four in-place half-sweeps; split: fused pass + the two odd classes as separate
+        # launches + control kernel; fused (default): pass + ONE cooperative launch that sweeps
+        # both odd classes behind a grid barrier and evaluates the exit tests / dynamic omega
+        if mode == "fused":
             monkeypatch.delenv("O3D_SOR_SEAM", raising=False)
+        else:
+            monkeypatch.setenv("O3D_SOR_SEAM", mode)
         for kmax in (1, 2, 7, 400):
             p = p0.copy(order="F")
             out[mode, kmax] = (fn(p, rhs, *d, 1.8, 1e-9, kmax, idyn), p)
     for kmax in (1, 2, 7, 400):
-        (ra, pa), (rb, pb) = out["inplace", kmax], out["fused", kmax]
+        for mode in ("split", "fused"):
+            (ra, pa), (rb, pb) = out["inplace", kmax], out[mode, kmax]
+            assert ra == rb, (mode, kmax, ra, rb)
+            assert np.array_equal(pa, pb), (mode, kmax, rel_max(pa, pb))
+    assert out["fused", 400][0][2] < out["fused", 7][0][2]   # dmax keeps falling
+
+
+@pytest.mark.parametrize("variant,shape", [
+    ("111111", (40, 33, 29)), ("111111", (64, 48, 40)), ("111111", (21, 17, 15)),
+    ("0000", (32, 48, 20)), ("0000", (66, 34, 38)), ("0011", (64, 37, 24)), ("0011", (34, 20, 36)),
+])
+@pytest.mark.parametrize("idyn", [0, 1])
+def test_fused_pass_equals_inplace_half_sweeps_bitwise(gpu, variant, shape, idyn, monkeypatch):
+    """2-colourable grids: one fused TMA pass (red update of plane k+2, black update of plane k,
+    ping-pong buffers, ghost-cell closures) == a red in-place half-sweep followed by a black one
+    (sor_rb_kernel with the reference's neighbour-index rule, O3D_SOR_FUSED=off): identical
+    iterates, iteration counts, dmax and omega history, for mirrored, periodic and mixed axes,
+    full and partial tiles, several z chunks."""
+    from osinco3d_b200 import modules as M
+    bc = VARIANTS[variant]
+    d = (0.11, 0.13, 0.17)
+    rhs, _ = consistent_problem(shape, d, bc, 21)
+    p0 = rand_field(shape, 22, 0.1)
+    fn = getattr(M, "poisson_solver_" + variant)
+    out = {}
+    for mode in ("off", "fused"):
+        if mode == "fused":
+            monkeypatch.delenv("O3D_SOR_FUSED", raising=False)
+        else:
+            monkeypatch.setenv("O3D_SOR_FUSED", "off")
+        for kmax in (1, 2, 5, 300):
+            p = p0.copy(order="F")
+            out[mode, kmax] = (fn(p, rhs, *d, 1.8, 1e-9, kmax, idyn), p)
+    for kmax in (1, 2, 5, 300):
+        (ra, pa), (rb, pb) = out["off", kmax], out["fused", kmax]
         assert ra == rb, (kmax, ra, rb)
         assert np.array_equal(pa, pb), (kmax, rel_max(pa, pb))
-    assert out["fused", 400][0][2] < out["fused", 7][0][2]   # dmax keeps falling
