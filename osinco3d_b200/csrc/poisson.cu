@@ -242,4 +242,68 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     return O3D_OK;
 }
 
+// `sweeps` red-black Gauss-Seidel / SOR iterations with the relaxation factor held in `ctrl`
+// (never "done"), no exit tests: the multigrid smoother on level 0 of a single-rank run, through
+// the same fused TMA pass (+ split odd seam classes) as sor_solve.  pp must be the session's
+// O3D_F_PP field, rhs a session field; on return O3D_F_PP holds the result (the two ping-pong
+// buffers are swapped when the number of passes was odd).  Returns O3D_ERR_UNSUPPORTED when the
+// fused path does not apply (the caller then uses the in-place half-sweeps: same bits).
+int sor_fixed_sweeps(o3d_session* s, const double* rhs, int sweeps, SorCtrl* ctrl) {
+    if (sweeps <= 0) return O3D_OK;
+    if (s->cfg.nranks > 1) return O3D_ERR_UNSUPPORTED;
+    const char* e_fused = getenv("O3D_SOR_FUSED");
+    if (e_fused && (!strcmp(e_fused, "off") || !strcmp(e_fused, "legacy"))) return O3D_ERR_UNSUPPORTED;
+    double* pp = field(s, O3D_F_PP);
+    double* alt = field(s, O3D_F_PP2);
+    if (!pp || !alt) return O3D_ERR_CUDA;
+    int id_rhs = -1;
+    for (int f = 0; f < O3D_F_COUNT; ++f)
+        if (s->base[f] && s->base[f] + interior_offset(s->g) == rhs) id_rhs = f;
+    if (id_rhs < 0) return O3D_ERR_UNSUPPORTED;
+    SorArgs a = make_sor_args(s, pp, rhs);
+    if (!sor_tmap(s, O3D_F_PP) || !sor_tmap(s, O3D_F_PP2) || !sor_tmap(s, id_rhs))
+        return O3D_ERR_CUDA;
+    const bool same_bc = (a.mx == s->g.bx && a.my == s->g.by && a.mz_lo == s->g.bz_lo &&
+                          a.mz_hi == s->g.bz_hi);
+    int rc;
+    if (same_bc) {
+        if ((rc = ensure_local_ghosts(s, O3D_F_PP, 0u, true))) return rc;
+        if ((rc = ensure_local_ghosts(s, id_rhs, 0u, false))) return rc;
+    } else {
+        Geom gs = s->g;
+        gs.bx = a.mx, gs.by = a.my, gs.bz_lo = a.mz_lo, gs.bz_hi = a.mz_hi;
+        if (launch_fill_ghosts_full(s->st, gs, pp, 0u)) return O3D_ERR_CUDA;
+        if (launch_fill_ghosts_full(s->st, gs, const_cast<double*>(rhs), 0u)) return O3D_ERR_CUDA;
+        touch(s, O3D_F_PP), touch(s, id_rhs);
+    }
+    const bool seams = a.seam_x || a.seam_y || a.seam_z;
+    for (int t = 0; t < sweeps; ++t) {
+        double* dst = (t & 1) ? pp : alt;
+        const int id_src = (t & 1) ? O3D_F_PP2 : O3D_F_PP;
+        if (launch_sor_tma(s->st, a, sor_tmap(s, id_src), sor_tmap(s, id_rhs), dst, a.mx, a.my,
+                           a.mz_lo, a.mz_hi, ctrl, 0, 0))
+            return O3D_ERR_CUDA;
+        if (seams) {
+            SorArgs sa = a;
+            sa.pp = dst;
+            for (int colour = 0; colour < 2; ++colour)
+                if (launch_sor_rb(s->st, sa, colour, 1, ctrl, 1)) return O3D_ERR_CUDA;
+        }
+    }
+    if (sweeps & 1) {
+        std::swap(s->base[O3D_F_PP], s->base[O3D_F_PP2]);
+        std::swap(s->tmap[O3D_F_PP], s->tmap[O3D_F_PP2]);
+        std::swap(s->tmap_sor[O3D_F_PP], s->tmap_sor[O3D_F_PP2]);
+        std::swap(s->tmap_st[O3D_F_PP], s->tmap_st[O3D_F_PP2]);
+        std::swap(s->tmap_sor_ok[O3D_F_PP], s->tmap_sor_ok[O3D_F_PP2]);
+    }
+    touch(s, O3D_F_PP);
+    touch(s, O3D_F_PP2);
+    if (same_bc) {  // the last pass (and the seam sweeps) wrote the ghost images of what they stored
+        s->gaxes[O3D_F_PP] = 0x1u | 0x2u | 0x4u | 0x8u | 0x10u;
+        s->gpar[O3D_F_PP] = 0u;
+    }
+    return O3D_OK;
+}
+
 }  // namespace o3d

@@ -137,6 +137,9 @@ int spec_correct_launch(o3d_session* s);
 
 // Poisson solvers (poisson.cu)
 int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double* dmax);
+// fixed number of fused red-black sweeps on O3D_F_PP with the relaxation factor of `ctrl` and no
+// exit tests (multigrid smoother, single rank); O3D_ERR_UNSUPPORTED: use the in-place sweeps
+int sor_fixed_sweeps(o3d_session* s, const double* rhs, int sweeps, SorCtrl* ctrl);
 int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npre, int npost,
              double tol, int* cycles, double* dmax);
 void mg_destroy(o3d_session* s);

@@ -367,13 +367,13 @@ struct StatsEpi {
 // of each component (print_velocity_values, src/IOfunctions.f90:322) and maxval(abs())
 // (compute_cfl, src/utils.f90:199-201).  24 B/pt instead of divergence (32) + function_stats (8)
 // + nine reductions (72).
-constexpr int NDIAG = 13;  // dmin dmax dsum dlin | umin[3] | umax[3] | uabs[3]
+constexpr int NDIAG = 10;  // dmin dmax dsum dlin | umin[3] | umax[3]   (max|u| = max(-min, max))
 struct DiagEpi {
     static constexpr int STREAMS = 3;
     double* partial;  // [NDIAG][nblocks]
     Coefs3 q;
     int sim2d, nx, ny, gz0;
-    double dmin, dmax, dsum, umin[3], umax[3], uabs[3];
+    double dmin, dmax, dsum, umin[3], umax[3];
     long long dlin;
     typedef NoPre Pre;
     __device__ __forceinline__ void setup(const MarchGeom& g, int, int) { nx = g.nx, ny = g.ny; }
@@ -394,7 +394,6 @@ struct DiagEpi {
             const double u = (c == 2) ? r.c(0) : r.cx(c, 0);
             umin[c] = fmin(umin[c], u);
             umax[c] = fmax(umax[c], u);
-            uabs[c] = fmax(uabs[c], fabs(u));
         }
     }
     __device__ __forceinline__ void finish(int tid, double* smem) {
@@ -411,7 +410,6 @@ struct DiagEpi {
             for (int c = 0; c < 3; ++c) {
                 umin[c] = fmin(umin[c], __shfl_xor_sync(0xffffffffu, umin[c], o));
                 umax[c] = fmax(umax[c], __shfl_xor_sync(0xffffffffu, umax[c], o));
-                uabs[c] = fmax(uabs[c], __shfl_xor_sync(0xffffffffu, uabs[c], o));
             }
         }
         dsum = warp_sum(dsum);
@@ -419,7 +417,7 @@ struct DiagEpi {
             double* w = smem + (tid >> 5) * NDIAG;
             w[0] = dmin, w[1] = dmax, w[2] = dsum, w[3] = (double)dlin;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) w[4 + c] = umin[c], w[7 + c] = umax[c], w[10 + c] = uabs[c];
+            for (int c = 0; c < 3; ++c) w[4 + c] = umin[c], w[7 + c] = umax[c];
         }
         __syncthreads();
         if (tid == 0) {
@@ -433,7 +431,6 @@ struct DiagEpi {
                 for (int c = 0; c < 3; ++c) {
                     v[4 + c] = fmin(v[4 + c], x[4 + c]);
                     v[7 + c] = fmax(v[7 + c], x[7 + c]);
-                    v[10 + c] = fmax(v[10 + c], x[10 + c]);
                 }
             }
             for (int s = 0; s < NDIAG; ++s) partial[(long long)s * nblocks + b] = v[s];
@@ -441,7 +438,8 @@ struct DiagEpi {
     }
 };
 
-// merge the per-CTA partials of DiagEpi in a fixed order -> out[NDIAG]
+// merge the per-CTA partials of DiagEpi in a fixed order -> out13 = dmin dmax dsum dlin |
+// umin[3] | umax[3] | max|u|[3]
 __global__ void __launch_bounds__(256) diag_stage2(const double* partial, int nblocks,
                                                    double* out) {
     __shared__ double red[8][NDIAG];
@@ -449,8 +447,7 @@ __global__ void __launch_bounds__(256) diag_stage2(const double* partial, int nb
     double v[NDIAG];
     v[0] = 1.7976931348623157e308, v[1] = -1.7976931348623157e308, v[2] = 0.0;
     v[3] = 9.0e18;
-    for (int c = 0; c < 3; ++c)
-        v[4 + c] = 1.7976931348623157e308, v[7 + c] = -1.7976931348623157e308, v[10 + c] = 0.0;
+    for (int c = 0; c < 3; ++c) v[4 + c] = 1.7976931348623157e308, v[7 + c] = -1.7976931348623157e308;
     auto merge = [&](const double* x) {
         v[0] = fmin(v[0], x[0]);
         if (x[1] > v[1] || (x[1] == v[1] && x[3] < v[3])) v[1] = x[1], v[3] = x[3];
@@ -458,7 +455,6 @@ __global__ void __launch_bounds__(256) diag_stage2(const double* partial, int nb
         for (int c = 0; c < 3; ++c) {
             v[4 + c] = fmin(v[4 + c], x[4 + c]);
             v[7 + c] = fmax(v[7 + c], x[7 + c]);
-            v[10 + c] = fmax(v[10 + c], x[10 + c]);
         }
     };
     for (int b = tid; b < nblocks; b += 256) {
@@ -466,18 +462,27 @@ __global__ void __launch_bounds__(256) diag_stage2(const double* partial, int nb
         for (int s = 0; s < NDIAG; ++s) x[s] = partial[(long long)s * nblocks + b];
         merge(x);
     }
-    // warp merge through shared memory (13 values per lane is too wide for shuffles to pay)
-    __shared__ double lane[256][NDIAG];
-    for (int s = 0; s < NDIAG; ++s) lane[tid][s] = v[s];
-    __syncthreads();
-    if ((tid & 31) == 0) {
-        for (int l = 1; l < 32; ++l) merge(lane[tid + l]);
-        for (int s = 0; s < NDIAG; ++s) red[tid >> 5][s] = v[s];
+    // butterfly inside the warp (the lower lane of a pair merges first: fixed association)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double x[NDIAG];
+#pragma unroll
+        for (int s = 0; s < NDIAG; ++s) x[s] = __shfl_xor_sync(0xffffffffu, v[s], o);
+        if (tid & o) {  // keep "lower lane first" so that both partners compute the same sum
+            double t[NDIAG];
+            for (int s = 0; s < NDIAG; ++s) t[s] = v[s], v[s] = x[s];
+            merge(t);
+        } else {
+            merge(x);
+        }
     }
+    if ((tid & 31) == 0)
+        for (int s = 0; s < NDIAG; ++s) red[tid >> 5][s] = v[s];
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < 8; ++w) merge(red[w]);
         for (int s = 0; s < NDIAG; ++s) out[s] = v[s];
+        for (int c = 0; c < 3; ++c) out[10 + c] = fmax(-v[4 + c], v[7 + c]);  // maxval(abs(u))
     }
 }
 
@@ -572,7 +577,7 @@ int launch_diag(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& c
     e.dmin = 1.7976931348623157e308, e.dmax = -1.7976931348623157e308, e.dsum = 0.0;
     e.dlin = 0x7fffffffffffffffLL;
     for (int c = 0; c < 3; ++c)
-        e.umin[c] = 1.7976931348623157e308, e.umax[c] = -1.7976931348623157e308, e.uabs[c] = 0.0;
+        e.umin[c] = 1.7976931348623157e308, e.umax[c] = -1.7976931348623157e308;
     if (launch_march<1, 2, 2, DiagEpi, 3>(st, g, maps3(u[2], u[0], u[1]), e)) return 1;
     diag_stage2<<<1, 256, 0, st>>>(partial, diag_blocks(g), out13);
     count_launch();
