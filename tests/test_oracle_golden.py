@@ -68,3 +68,30 @@ def test_les_row1_25_steps(O):
     for c in (1, 2, 4):
         assert abs(st[c] - ref[c]) / ref[c] < 1e-6, (c, st[c], ref[c])
     s.close()
+
+
+def test_calculate_residuals_restatement_against_numpy():
+    """orc_calculate_residuals (src/utils.f90:93-160) against an independent numpy evaluation:
+    interior points only, L2 with the single-precision real(nx*ny*nz) divisor, Linf, and the
+    LAST point (array order) attaining each maximum."""
+    import numpy as np
+    from oracle import oracle_py as O
+    O.build()
+    rng = np.random.default_rng(7)
+    n = (13, 11, 9)
+    new = [np.asfortranarray(rng.standard_normal(n)) for _ in range(3)]
+    old = [np.asfortranarray(rng.standard_normal(n)) for _ in range(3)]
+    old[1][5, 5, 5], new[1][5, 5, 5] = 40.0, 0.0      # the maximum, twice: the later one is kept
+    old[1][7, 6, 5], new[1][7, 6, 5] = 0.0, 40.0
+    old[2][0, 3, 3] = 1e3                              # boundary point: not scanned
+    dt, t_ref, u_ref = 0.25, 2.0, 4.0
+    got = O.calculate_residuals(*new, *old, dt, t_ref, u_ref)
+    cnt = float(np.float32(n[0] * n[1] * n[2]))
+    for c in range(3):
+        a = np.abs(old[c] - new[c])[1:-1, 1:-1, 1:-1] / (2.0 * dt)
+        assert abs(got[c] - (t_ref / u_ref) * np.sqrt(np.sum(a * a) / cnt)) < 1e-13 * got[c]
+        assert got[3 + c] == (t_ref / u_ref) * a.max()
+        where = np.argwhere(a == a.max())
+        last = max(where, key=lambda q: (q[2], q[1], q[0]))    # k slowest, i fastest
+        assert list(got[6 + 3 * c: 9 + 3 * c]) == [last[0] + 2, last[1] + 2, last[2] + 2]
+    assert list(got[9:12]) == [8, 7, 6]
