@@ -258,3 +258,103 @@ def test_gated_correction_behind_sor_equals_host_polled_step_bitwise(gpu, O, bc,
     assert len(set(res["1"][0])) > 1, res["1"][0]     # iteration counts did vary
     for k, a in res["0"][2].items():
         assert np.array_equal(a, res["1"][2][k]), (k, rel_max(a, res["1"][2][k]))
+
+
+@pytest.mark.parametrize("itscheme", [1, 2])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 1, 0)])
+def test_euler_and_ab2_schemes_match_oracle_bitwise(gpu, O, itscheme, bc):
+    """itscheme = 1 (Euler) / 2 (AB2): src/integration.f90:84-105 selects the coefficients and
+    :176-188 shifts only the history levels that scheme uses -- on the device a different
+    rotation of the three physical history buffers than AB3.  Wavefront SOR -> bit parity,
+    LES + scalar on, 5 steps."""
+    n = 25
+    d = tuple((PI if b else 2 * PI) / (n - 1) for b in bc)
+    kw = dict(re=500.0, dt=3e-3, omega=1.7, eps=1e-6, idyn=1, iles=1, cs=0.17, sc=0.7,
+              itscheme=itscheme, kmax=400)
+    sim, ses = make_pair(gpu, O, (n, n, n), d, bc, tgv(O), nscr=1,
+                         sor_order=gpu.SOR_LEXI_WAVEFRONT, **kw)
+    for step in range(5):
+        assert sim.step() == ses.step()
+        assert ses.omega == sim.omega and ses.last_dmax == sim.last_dmax
+    for k in ("ux", "uy", "uz", "pp", "phi", "nu_t"):
+        assert np.array_equal(ses.download(k), sim.field(k)), k
+    ses.close()
+    sim.close()
+
+
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("iles", [0, 1])
+def test_sim2d_steps_match_oracle_bitwise(gpu, O, bc, iles):
+    """sim2d = 1 binds derz / derzz to the *_2dsim routines (zeros, src/derivation.f90:481,934;
+    src/initialization.f90:226-281): every z derivative of the step vanishes -- in the RHS, the
+    Smagorinsky strain, the divergence and the pressure gradient (compile-time variants of the
+    CUDA epilogues) -- while the Poisson operator keeps its z coupling."""
+    n = 24
+    d = tuple((PI if b else 2 * PI) / (n - 1) for b in bc)
+    g = O.grid(n, n, n, *d, bc, sim2d=1)
+    ux, uy, uz, pp, phi = O.init_tgv(g, nscr=1)
+    kw = dict(re=300.0, dt=4e-3, omega=1.6, eps=1e-6, iles=iles, cs=0.17, nscr=1, kmax=300)
+    sim = O.Sim(g, itscheme=3, idyn=0, sc=1.0, **kw)
+    sim.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+    cfg = gpu.make_config(n, n, n, *d, bc=bc, sim2d=1, itscheme=3, idyn=0, sc=1.0,
+                          sor_order=gpu.SOR_LEXI_WAVEFRONT, **kw)
+    ses = gpu.Session(cfg)
+    ses.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+    for step in range(4):
+        assert sim.step() == ses.step()
+    for k in ("ux", "uy", "uz", "pp", "phi") + (("nu_t",) if iles else ()):
+        assert np.array_equal(ses.download(k), sim.field(k)), k
+    # and the fast path (red-black, gated correction) agrees with it to solver tolerance
+    cfg2 = gpu.make_config(n, n, n, *d, bc=bc, sim2d=1, itscheme=3, idyn=0, sc=1.0,
+                           **dict(kw, eps=1e-11, kmax=20000))
+    fast = gpu.Session(cfg2)
+    fast.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+    conv = gpu.Session(gpu.make_config(n, n, n, *d, bc=bc, sim2d=1, itscheme=3, idyn=0, sc=1.0,
+                                       sor_order=gpu.SOR_LEXI_WAVEFRONT,
+                                       **dict(kw, eps=1e-11, kmax=20000)))
+    conv.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+    for step in range(3):
+        fast.step(), conv.step()
+    for k in ("ux", "uy", "uz"):
+        assert np.max(np.abs(fast.download(k) - conv.download(k))) < 1e-8, k
+    for s in (ses, fast, conv):
+        s.close()
+    sim.close()
+
+
+@pytest.mark.parametrize("shape", [(7, 7, 7), (8, 9, 7), (33, 7, 70), (130, 9, 8), (9, 70, 11)])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0), (0, 1, 0)])
+def test_extreme_grid_shapes_match_oracle_bitwise(gpu, O, shape, bc):
+    """the smallest grid the stencils admit (7 points: every point is within 3 of both walls, the
+    ghost images overlap), pencils and slabs thinner than one tile / one z chunk, rows longer
+    than four tiles: whole steps with LES + scalar in the reference's sweep order -> bit parity;
+    the red-black fast path is checked against it to solver tolerance."""
+    L = [(PI if b else 2 * PI) for b in bc]
+    d = tuple(L[a] / (shape[a] - 1) for a in range(3))
+    kw = dict(re=200.0, dt=0.02 * min(d), omega=1.5, eps=1e-7, idyn=1, iles=1, cs=0.17, sc=1.0,
+              kmax=2000)
+    sim, ses = make_pair(gpu, O, shape, d, bc, tgv(O), nscr=1,
+                         sor_order=gpu.SOR_LEXI_WAVEFRONT, **kw)
+    for step in range(4):
+        assert sim.step() == ses.step()
+    for k in ("ux", "uy", "uz", "pp", "nu_t"):
+        assert np.array_equal(ses.download(k), sim.field(k)), k
+    # the conservative clipping of the scalar divides by three global sums whose association
+    # differs on the device (tree vs sequential): round-off only (tests/test_gpu_operators.py)
+    assert np.max(np.abs(ses.download("phi") - sim.field("phi"))) < 1e-13
+    diag = ses.step_diagnostics()
+    div = O.divergence(sim.g, sim.field("ux"), sim.field("uy"), sim.field("uz"), 1)
+    assert diag["divu"][0] == div.min() and diag["divu"][1] == div.max()
+    ses.close()
+    kw2 = dict(kw, eps=1e-12, idyn=0, kmax=50000)
+    sim2, rb = make_pair(gpu, O, shape, d, bc, tgv(O), nscr=1, **kw2)
+    _, wf = make_pair(gpu, O, shape, d, bc, tgv(O), nscr=1, sor_order=gpu.SOR_LEXI_WAVEFRONT, **kw2)
+    for step in range(3):
+        rb.step(), wf.step()
+    scale = max(np.max(np.abs(wf.download(k))) for k in ("ux", "uy", "uz"))
+    for k in ("ux", "uy", "uz"):
+        assert np.max(np.abs(rb.download(k) - wf.download(k))) < 1e-8 * scale, k
+    for s in (rb, wf):
+        s.close()
+    sim.close()
+    sim2.close()
