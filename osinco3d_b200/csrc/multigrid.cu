@@ -40,6 +40,10 @@ struct MgHierarchy {
     // ranks.  A rank restricts the level-1 planes [ck0, ck0 + nck) whose centre tap it owns --
     // its residual carries 2 exchanged ghost planes per side, which covers every tap -- and the
     // planes are then replicated with grouped broadcasts.  Same taps, same order as on one GPU.
+    // The coarse part of a V-cycle (levels >= 1: ~40 small launches per level, launch-latency
+    // bound) is a fixed launch sequence: captured once into a CUDA graph, replayed per cycle.
+    cudaGraphExec_t coarse_exec = nullptr;
+    int graph_npre = -1, graph_npost = -1, graph_launches = 0;
     int ck0 = 0, nck = 0;
     const int* ridx_z_local = nullptr;        // z restriction taps as local plane offsets
     std::vector<long long> gfirst, gcount;    // element ranges of the ranks' level-1 chunks
@@ -336,6 +340,7 @@ void mg_destroy(o3d_session* s) {
     if (!H) return;
     for (auto& L : H->lv)
         for (void* p : L.owned) cudaFree(p);
+    if (H->coarse_exec) cudaGraphExecDestroy(H->coarse_exec);
     if (H->ctrl) cudaFree(H->ctrl);
     if (H->res0_base) cudaFree(H->res0_base);
     delete H;
@@ -398,15 +403,18 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
         if (last < tol || cyc >= MG_MAX_CYCLES) break;
         if (cyc >= 2 && last > 0.9 * prev) break;  // stalled at the round-off / compatibility floor
         prev = last;
-        // one V-cycle
-        for (int l = 0; l < nl - 1; ++l) {
-            MgLevel& F = H->lv[l];
-            MgLevel& C = H->lv[l + 1];
-            const bool dist = multi && l == 0;
-            if (smooth(s, F, npre, dist)) return O3D_ERR_CUDA;
-            if (dist && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
+        // one V-cycle.  Level 0 (session fields; distributed over the z slabs when multi) ...
+        if (nl == 1) {
+            if (smooth(s, H->lv[0], npre + npost, multi)) return O3D_ERR_CUDA;
+            continue;
+        }
+        {
+            MgLevel& F = H->lv[0];
+            MgLevel& C = H->lv[1];
+            if (smooth(s, F, npre, multi)) return O3D_ERR_CUDA;
+            if (multi && comm_exchange(s, ppf, 1, 1, zwrap)) return O3D_ERR_COMM;
             if (launch_mg_residual(s->st, F.g, F.p, F.rhs, F.res, nullptr)) return O3D_ERR_CUDA;
-            if (dist) {
+            if (multi) {
                 // 2 ghost planes of the residual, restrict the owned level-1 planes, replicate
                 if (comm_exchange(s, resf, 1, 2, zwrap)) return O3D_ERR_COMM;
                 MgTables tl = F.t;
@@ -421,20 +429,66 @@ int mg_solve(o3d_session* s, double* pp, const double* rhs, int nlevels, int npr
                 return O3D_ERR_CUDA;
             }
         }
-        if (nl == 1) {
-            if (smooth(s, H->lv[0], npre + npost, multi)) return O3D_ERR_CUDA;
-        } else {
+        // ... levels >= 1 (local / replicated buffers, no communication): fixed launch sequence
+        auto coarse_part = [&]() -> int {
+            for (int l = 1; l < nl - 1; ++l) {
+                MgLevel& F = H->lv[l];
+                MgLevel& C = H->lv[l + 1];
+                if (smooth(s, F, npre, false)) return 1;
+                if (launch_mg_residual(s->st, F.g, F.p, F.rhs, F.res, nullptr)) return 1;
+                if (launch_mg_restrict(s->st, F.g, C.g, F.t, F.res, C.rhs, C.p, 0, C.g.nz)) return 1;
+            }
             MgLevel& B = H->lv[nl - 1];
-            if (launch_mg_coarse(s->st, B.g, B.p, B.rhs, MG_COARSE_SWEEPS)) return O3D_ERR_CUDA;
+            if (launch_mg_coarse(s->st, B.g, B.p, B.rhs, MG_COARSE_SWEEPS)) return 1;
+            for (int l = nl - 2; l >= 1; --l) {
+                MgLevel& F = H->lv[l];
+                MgLevel& C = H->lv[l + 1];
+                if (launch_mg_prolong(s->st, F.g, C.g, F.t, C.p, F.p, 0)) return 1;
+                if (smooth(s, F, npost, false)) return 1;
+            }
+            return 0;
+        };
+        const bool use_graph = !(getenv("O3D_MG_GRAPH") && atoi(getenv("O3D_MG_GRAPH")) == 0);
+        if (use_graph && nl > 2) {
+            if (H->coarse_exec && (H->graph_npre != npre || H->graph_npost != npost)) {
+                cudaGraphExecDestroy(H->coarse_exec);
+                H->coarse_exec = nullptr;
+            }
+            if (!H->coarse_exec) {
+                const long long before = o3d_kernel_launches();
+                cudaGraph_t graph = nullptr;
+                O3D_CUDA_CHECK(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeRelaxed));
+                const int crc = coarse_part();
+                const cudaError_t ce = cudaStreamEndCapture(s->st, &graph);
+                if (crc || ce != cudaSuccess || !graph) {
+                    if (graph) cudaGraphDestroy(graph);
+                    set_error("multigrid: capture of the coarse V-cycle failed: %s",
+                              cudaGetErrorString(ce));
+                    return O3D_ERR_CUDA;
+                }
+                H->graph_launches = (int)(o3d_kernel_launches() - before);
+                count_launch(-H->graph_launches);  // captured, not run
+                const cudaError_t ie = cudaGraphInstantiate(&H->coarse_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) {
+                    H->coarse_exec = nullptr;
+                    set_error("multigrid: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+                    return O3D_ERR_CUDA;
+                }
+                H->graph_npre = npre, H->graph_npost = npost;
+            }
+            O3D_CUDA_CHECK(cudaGraphLaunch(H->coarse_exec, s->st));
+            count_launch(H->graph_launches);
+        } else if (coarse_part()) {
+            return O3D_ERR_CUDA;
         }
-        for (int l = nl - 2; l >= 0; --l) {
-            MgLevel& F = H->lv[l];
-            MgLevel& C = H->lv[l + 1];
-            const bool dist = multi && l == 0;
-            if (launch_mg_prolong(s->st, F.g, C.g, F.t, C.p, F.p, dist ? s->z0 : 0))
+        {   // ... and back up to level 0
+            MgLevel& F = H->lv[0];
+            MgLevel& C = H->lv[1];
+            if (launch_mg_prolong(s->st, F.g, C.g, F.t, C.p, F.p, multi ? s->z0 : 0))
                 return O3D_ERR_CUDA;
-            if (l == 0) touch(s, O3D_F_PP);  // interior changed: ghost images are stale
-            if (smooth(s, F, npost, dist)) return O3D_ERR_CUDA;
+            touch(s, O3D_F_PP);  // interior changed: ghost images are stale
+            if (smooth(s, F, npost, multi)) return O3D_ERR_CUDA;
         }
     }
     span_end(s, ST_SOR, cyc);

@@ -156,10 +156,13 @@ def test_fused_level0_smoother_equals_inplace_smoother_bitwise(gpu, variant, sha
     rhs -= rhs.mean()
     out = {}
     for mode in ("inplace", "fused"):
+        # "inplace" also replays the coarse levels launch by launch instead of as a CUDA graph
         if mode == "inplace":
             monkeypatch.setenv("O3D_MG_SMOOTHER", "inplace")
+            monkeypatch.setenv("O3D_MG_GRAPH", "0")
         else:
             monkeypatch.delenv("O3D_MG_SMOOTHER", raising=False)
+            monkeypatch.delenv("O3D_MG_GRAPH", raising=False)
         for npre, npost, tol in ((5, 4, 1e-9), (2, 1, 1e-6), (1, 0, 1e-3)):
             p = np.asfortranarray(np.zeros(shape))
             out[mode, npre] = (M.solve_poisson_multigrid(p, rhs, *d, 10000, npre, npost, tol), p)
