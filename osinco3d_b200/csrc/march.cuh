@@ -55,9 +55,10 @@ struct MarchGeom {
 // by TMA P planes ahead instead of through registers).  P = prefetch distance in planes.
 // Fields are ordered z-fields, c-fields, s-fields in MarchMaps.
 constexpr int MSFIELD = MTX * MTY;  // doubles per staged stream-field plane (2 KB)
-template <int NFZ, int NFC, int P, int NFS = 0>
+template <int NFZ, int NFC, int P, int NFS = 0, int NFW = 0>
 constexpr int march_smem_bytes() {
-    return (NFZ * (7 + P) + NFC * (1 + P)) * MFIELD * 8 + NFS * (1 + P) * MSFIELD * 8 + (P + 1) * 8;
+    return (NFZ * (7 + P) + NFC * (1 + P)) * MFIELD * 8 + NFS * (1 + P) * MSFIELD * 8 +
+           NFW * (7 + P) * MSFIELD * 8 + (P + 1) * 8;
 }
 
 // The staged data seen by one thread: p[m] points at this thread's cell of z-field 0 in plane
@@ -105,6 +106,44 @@ struct Ring {
     }
 };
 
+// Split-ring view (NFW > 0): a field that is differentiated in all three directions is staged
+// twice -- plane k WITH its x/y halo (c-ring, 1+P stages of 40 x 14 boxes) and planes k-3 .. k+3
+// WITHOUT halo (w-ring, 7+P stages of 32 x 8 boxes) -- because the z stencil only ever reads the
+// thread's own column; a field that is only differentiated in z needs the w-ring alone.  x / y /
+// c index the c-fields, z the w-fields (RHS: the same three fields in both rings).  Per field the
+// ring costs (7+P) * 2 KB + (1+P) * 4.4 KB instead of (7+P) * 4.4 KB, which buys prefetch depth
+// (bytes in flight) inside the same shared-memory budget; the second read of a plane hits L2.
+struct RingCW {
+    const double* w[7];  // this thread's value in planes k-3 .. k+3 (field f is MSFIELD further)
+    const double* q;     // its cell in the halo'd plane k (field f is MFIELD further)
+    __device__ __forceinline__ double c(int f) const { return q[f * MFIELD]; }
+    __device__ __forceinline__ double x(int f, int d) const { return q[f * MFIELD + d]; }
+    __device__ __forceinline__ double y(int f, int d) const { return q[f * MFIELD + d * MBX]; }
+    __device__ __forceinline__ double z(int f, int d) const { return w[3 + d][f * MSFIELD]; }
+    __device__ __forceinline__ double d1x(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, x(f, -3), x(f, -2), x(f, -1), x(f, 1), x(f, 2), x(f, 3));
+    }
+    __device__ __forceinline__ double d1y(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, y(f, -3), y(f, -2), y(f, -1), y(f, 1), y(f, 2), y(f, 3));
+    }
+    __device__ __forceinline__ double d1z(int f, const Coef& k) const {
+        return d1_expr(k.a1, k.b1, k.c1, z(f, -3), z(f, -2), z(f, -1), z(f, 1), z(f, 2), z(f, 3));
+    }
+    __device__ __forceinline__ double d2x(int f, const Coef& k) const {
+        return d2_expr(k.a2, k.b2, k.c2, x(f, -2), x(f, -1), c(f), x(f, 1), x(f, 2));
+    }
+    __device__ __forceinline__ double d2y(int f, const Coef& k) const {
+        return d2_expr(k.a2, k.b2, k.c2, y(f, -2), y(f, -1), c(f), y(f, 1), y(f, 2));
+    }
+    __device__ __forceinline__ double d2z(int f, const Coef& k) const {
+        return d2_expr(k.a2, k.b2, k.c2, z(f, -2), z(f, -1), c(f), z(f, 1), z(f, 2));
+    }
+    // names of Ring<NFZ, NFC>'s centre-only accessors (c-field f)
+    __device__ __forceinline__ double cx(int f, int d) const { return x(f, d); }
+    __device__ __forceinline__ double c_d1x(int f, const Coef& k) const { return d1x(f, k); }
+    __device__ __forceinline__ double c_d1y(int f, const Coef& k) const { return d1y(f, k); }
+};
+
 // Epilogue concept:
 //   static constexpr int STREAMS;                 values moved per point (reads + writes): sizes
 //                                                 the z chunks (pick_zchunk)
@@ -116,10 +155,13 @@ struct Ring {
 // UNR > 1: the plane loop is unrolled UNR times, UNR a common multiple of the ring lengths, so
 // that every ring position is a compile-time constant inside the body: shared-memory operands
 // become [base + immediate] and the per-plane ring-pointer arithmetic disappears.
-template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0, int UNR = 1>
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0, int UNR = 1,
+          int NFW = 0>
 __global__ void __launch_bounds__(MNT, MINB)
-    march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC + NFS + NALT> maps, const MarchGeom g,
-                 Epi epi) {
+    march_kernel(const __grid_constant__ MarchMaps<NFZ + NFC + NFS + NALT + NFW> maps,
+                 const MarchGeom g, Epi epi) {
+    static_assert(NFW == 0 || (NFZ == 0 && NFS == 0 && NALT == 0 && UNR == 1),
+                  "split-ring mode: z windows live in the w-ring only");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const CUtensorMap* map0 = &maps.m[0];
     if (NALT) {
@@ -131,7 +173,9 @@ __global__ void __launch_bounds__(MNT, MINB)
     double* zring = reinterpret_cast<double*>(smem_raw);
     double* cring = zring + NZS * ZSTAGE;
     double* sring = cring + NCS * CSTAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sring + NCS * SSTAGE);
+    constexpr int WSTAGE = NFW * MSFIELD;
+    double* wring = sring + NCS * SSTAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + NZS * WSTAGE);
     constexpr uint32_t PLANE_BYTES = MFIELD * 8, SPLANE_BYTES = MSFIELD * 8;
 
     const int tid = threadIdx.x;
@@ -149,6 +193,7 @@ __global__ void __launch_bounds__(MNT, MINB)
     const bool in_dom = (i < g.nx) && (j < g.ny);
 
     const uint32_t zring_s = smem_u32(zring), cring_s = smem_u32(cring), sring_s = smem_u32(sring);
+    const uint32_t wring_s = smem_u32(wring);
     const uint32_t bars_s = smem_u32(bars);
     if (tid == 0) {
 #pragma unroll
@@ -167,6 +212,15 @@ __global__ void __launch_bounds__(MNT, MINB)
             tma_load_3d(zring_s + (uint32_t)(st * ZSTAGE + f * MFIELD) * 8,
                         (NALT && f == 0) ? map0 : &maps.m[f], bar, cx, cy, GH + plane);
     };
+    // w-plane `plane` (tile only) lives in w-stage (plane - (kb-3)) mod NZS; its tensor maps follow
+    // the c-field maps
+    auto issue_w = [&](int plane, uint32_t bar) {
+        const unsigned st = (unsigned)(plane - (kb - R)) % NZS;
+#pragma unroll
+        for (int f = 0; f < NFW; ++f)
+            tma_load_3d(wring_s + (uint32_t)(st * WSTAGE + f * MSFIELD) * 8,
+                        &maps.m[NFZ + NFC + NFS + NALT + f], bar, GX + i0, GH + j0, GH + plane);
+    };
     auto issue_c = [&](int plane, uint32_t bar) {
         const unsigned st = (unsigned)(plane - kb) % NCS;
 #pragma unroll
@@ -184,12 +238,17 @@ __global__ void __launch_bounds__(MNT, MINB)
     auto issue_group = [&](int n) {
         const uint32_t bar = bars_s + 8 * ((unsigned)n % NB);
         const int nz_planes = (n == 0) ? 7 : 1;
-        mbar_expect_tx(bar, (uint32_t)(nz_planes * NFZ + NFC) * PLANE_BYTES + NFS * SPLANE_BYTES);
+        mbar_expect_tx(bar, (uint32_t)(nz_planes * NFZ + NFC) * PLANE_BYTES +
+                                (uint32_t)(NFS + nz_planes * NFW) * SPLANE_BYTES);
         if (n == 0) {
 #pragma unroll
-            for (int s = 0; s < 6; ++s) issue_z(kb - R + s, bar);
+            for (int s = 0; s < 6; ++s) {
+                issue_z(kb - R + s, bar);
+                issue_w(kb - R + s, bar);
+            }
         }
         issue_z(kb + n + R, bar);
+        issue_w(kb + n + R, bar);
         issue_c(kb + n, bar);
     };
     if (tid == 0) {
@@ -246,16 +305,28 @@ __global__ void __launch_bounds__(MNT, MINB)
         // group `it` has landed?
         mbar_wait(bars_s + 8 * bi, bpar);
         if (in_dom) {
-            Ring<NFZ, NFC> r;
+            if constexpr (NFW > 0) {
+                RingCW r;
 #pragma unroll
-            for (int w = 0; w < 7; ++w) {
-                int st = zb + w;
-                st = (st >= NZS) ? st - NZS : st;
-                r.p[w] = zring + st * ZSTAGE + cell;
+                for (int w = 0; w < 7; ++w) {
+                    int st = zb + w;
+                    st = (st >= NZS) ? st - NZS : st;
+                    r.w[w] = wring + st * WSTAGE + tid;
+                }
+                r.q = cring + cb * CSTAGE + cell;
+                epi.apply(r, m, i, j, k, cur);
+            } else {
+                Ring<NFZ, NFC> r;
+#pragma unroll
+                for (int w = 0; w < 7; ++w) {
+                    int st = zb + w;
+                    st = (st >= NZS) ? st - NZS : st;
+                    r.p[w] = zring + st * ZSTAGE + cell;
+                }
+                r.q = cring + cb * CSTAGE + cell;
+                r.s = sring + cb * SSTAGE + tid;
+                epi.apply(r, m, i, j, k, cur);
             }
-            r.q = cring + cb * CSTAGE + cell;
-            r.s = sring + cb * SSTAGE + tid;
-            epi.apply(r, m, i, j, k, cur);
         }
         cur = nxt;
         m += g.sz;
@@ -271,12 +342,14 @@ __global__ void __launch_bounds__(MNT, MINB)
 // zmode: ZFULL whole slab | ZINTERIOR planes [zedge, nz - zedge) | ZBOUNDARY the two end chunks
 enum { ZFULL = 0, ZINTERIOR = 1, ZBOUNDARY = 2 };
 
-template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0, int UNR = 1>
-int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS + NALT>& maps,
-                 const Epi& epi, int zmode = ZFULL, int zedge = 0, const SorCtrl* gate = nullptr) {
+template <int NFZ, int NFC, int P, class Epi, int MINB, int NFS = 0, int NALT = 0, int UNR = 1,
+          int NFW = 0>
+int launch_march(cudaStream_t st, const Geom& g,
+                 const MarchMaps<NFZ + NFC + NFS + NALT + NFW>& maps, const Epi& epi,
+                 int zmode = ZFULL, int zedge = 0, const SorCtrl* gate = nullptr) {
     static bool attr_set = false;
-    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB, NFS, NALT, UNR>;
-    constexpr int smem = march_smem_bytes<NFZ, NFC, P, NFS>();
+    auto kern = march_kernel<NFZ, NFC, P, Epi, MINB, NFS, NALT, UNR, NFW>;
+    constexpr int smem = march_smem_bytes<NFZ, NFC, P, NFS, NFW>();
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
             cudaSuccess)
@@ -300,7 +373,7 @@ int launch_march(cudaStream_t st, const Geom& g, const MarchMaps<NFZ + NFC + NFS
     } else {
         const int span = mg.zhi - mg.zlo;
         if (span <= 0) return 0;
-        mg.zchunk = pick_zchunk(gx * gy, span, MINB, NFZ, Epi::STREAMS);
+        mg.zchunk = pick_zchunk(gx * gy, span, MINB, NFZ + NFW, Epi::STREAMS);
         gz = (span + mg.zchunk - 1) / mg.zchunk;
     }
     kern<<<dim3(gx, gy, gz), dim3(MNT, 1, 1), smem, st>>>(maps, mg, epi);

@@ -14,6 +14,7 @@
 //
 // HBM-bound FP64 stencils: no tensor cores (nothing here is a contraction).
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels.h"
 #include "march.cuh"
@@ -29,7 +30,8 @@ struct Coefs3 {
 struct Grad {
     double d[3][3];
 };
-__device__ __forceinline__ Grad gradient(const Ring<3>& r, const Coefs3& q, int sim2d) {
+template <class RG>
+__device__ __forceinline__ Grad gradient(const RG& r, const Coefs3& q, int sim2d) {
     Grad G;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -102,7 +104,8 @@ struct RhsEpi {
         }
         return p;
     }
-    __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int k,
+    template <class RG>
+    __device__ __forceinline__ void apply(const RG& r, long long m, int, int, int k,
                                           const Pre& pre) {
         const Grad G = gradient(r, q, FAST ? 0 : sim2d);
         double nut = 0.0;
@@ -380,7 +383,8 @@ struct DiagEpi {
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     // z-field 0 = uz (7-plane window); centre-only fields 0, 1 = ux, uy (x / y halo of the plane
     // being computed): the ring layout of the divergence kernel, 3 CTAs per SM
-    __device__ __forceinline__ void apply(const Ring<1, 2>& r, long long, int i, int j, int k,
+    template <class RG>
+    __device__ __forceinline__ void apply(const RG& r, long long, int i, int j, int k,
                                           const Pre&) {
         const double dfx = r.c_d1x(0, q.x), dfy = r.c_d1y(1, q.y);
         const double dfz = sim2d ? 0.0 : r.d1z(0, q.z);
@@ -391,7 +395,7 @@ struct DiagEpi {
         if (dv > dmax) dmax = dv, dlin = lin;  // k ascending per thread: first occurrence
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const double u = (c == 2) ? r.c(0) : r.cx(c, 0);
+            const double u = (c == 2) ? r.z(0, 0) : r.cx(c, 0);
             umin[c] = fmin(umin[c], u);
             umax[c] = fmax(umax[c], u);
         }
@@ -509,6 +513,20 @@ static int launch_rhs_t(cudaStream_t st, const Geom& g, const RhsArgs& r, int zm
     e.q = coefs(r.cx, r.cy, r.cz);
     e.onere = r.onere, e.adu = r.adu, e.bdu = r.bdu, e.cdu = r.cdu, e.csd2 = r.csd2;
     e.iles = r.iles, e.sim2d = g.sim2d;
+    // O3D_RHS_RING=split<P>: split-ring staging (march.cuh RingCW: halo'd box for plane k only,
+    // tile-only boxes for the z window), P = 2 or 3 planes of prefetch instead of 1
+    // Measured (profiles/r1r_variants.txt): split2 0.405 vs 0.435 ms at 256^3 and 3.13 vs 3.38 ms
+    // at 512^3 for the DNS instantiation (default there); the LES instantiation spills in the
+    // split layout and stays on the classic ring.  O3D_RHS_RING=classic | split2 | split3 forces.
+    static const char* ring = getenv("O3D_RHS_RING");
+    const bool split = ring ? !strncmp(ring, "split", 5) : FAST;
+    if (split) {
+        MarchMaps<6> m6;
+        for (int c = 0; c < 3; ++c) m6.m[c] = *r.u[c].tm, m6.m[3 + c] = *r.u[c].tms;
+        if (ring && ring[5] == '3')
+            return launch_march<0, 3, 3, RhsEpi<FAST>, 2, 0, 0, 1, 3>(st, g, m6, e, zmode, zedge);
+        return launch_march<0, 3, 2, RhsEpi<FAST>, 2, 0, 0, 1, 3>(st, g, m6, e, zmode, zedge);
+    }
     // O3D_RHS_UNROLL=1: plane loop unrolled over the 8-stage ring (march.cuh, UNR = 8: ring
     // positions become immediates).  Measured equal at 256^3 and 1-2 % slower at 512^3 than the
     // rolled loop (the kernel is not instruction-bound), so the rolled loop is the default.
@@ -578,7 +596,9 @@ int launch_diag(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& c
     e.dlin = 0x7fffffffffffffffLL;
     for (int c = 0; c < 3; ++c)
         e.umin[c] = 1.7976931348623157e308, e.umax[c] = -1.7976931348623157e308;
-    if (launch_march<1, 2, 2, DiagEpi, 3>(st, g, maps3(u[2], u[0], u[1]), e)) return 1;
+    MarchMaps<3> ms;  // ux, uy with halo (c-ring); uz tile-only (w-ring), as the divergence kernel
+    ms.m[0] = *u[0].tm, ms.m[1] = *u[1].tm, ms.m[2] = *u[2].tms;
+    if (launch_march<0, 2, 2, DiagEpi, 3, 0, 0, 1, 1>(st, g, ms, e)) return 1;
     diag_stage2<<<1, 256, 0, st>>>(partial, diag_blocks(g), out13);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
