@@ -476,7 +476,9 @@ def main():
     for k in stages:
         stages[k]["frac"] = stages[k]["gbs"] / peak
         stages[k]["share_of_step"] = stages[k]["ms_per_launch"] * stages[k]["launches"] / ms_dev
-    kernel_of = {"rhs": "march_kernel<3,0,1,RhsEpi>", "div": "march_kernel<1,2,2,DivEpi>",
+    kernel_of = {"rhs": ("march_kernel<3,0,1,RhsEpi<les>>" if ph["iles"] else
+                         "march_kernel<0,3,2,RhsEpi<dns>,split ring>"),
+                 "div": "march_kernel<0,2,2,DivEpi,split ring>",
                  "sor": "sor_tma_kernel" if fused else "sor_rb_kernel",
                  "corr": "march_kernel<1,0,3,CorrEpi,3 stream fields>"}
     dom = max(stages, key=lambda k: stages[k]["share_of_step"]) if stages else None
