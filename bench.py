@@ -46,6 +46,8 @@ B_SOR_HALF = 16.0     # in-place colour half-sweep (odd periodic grids): half of
 B_SOR_FUSED = 24.0    # fused red+black pass with ping-pong: read pp + read rhs + write pp
 B_CORR = 56.0
 B_TRANSEQ = 88.0
+# z chunks of the e2e leg (csrc/pipeline.cu: the library default); O3D_PIPELINE overrides
+E2E_PIPELINE_CHUNKS = int(os.environ.get("O3D_PIPELINE", "8"))
 
 
 def parse():
@@ -60,6 +62,12 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=0, help="grid of the CPU sample (0 = same n)")
+    ap.add_argument("--pipeline", type=int, default=E2E_PIPELINE_CHUNKS,
+                    help="z chunks of the pipelined host-pointer procedures in the e2e leg "
+                         "(o3d_set_pipeline; 0 = unpipelined)")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: keep the grid at n^3 (strong scaling) instead of replicating "
+                         "the box in z")
     return ap.parse_args()
 
 
@@ -68,7 +76,7 @@ def workload(args, nranks):
     bc = (1, 1, 1) if args.bc == "freeslip" else (0, 0, 0)
     L = PI if args.bc == "freeslip" else 2 * PI
     d = L / (n - 1)                       # dx = xlx/(nx-1), src/initialization.f90:182-184
-    nz = nranks * (n - 1) + 1 if nranks > 1 else n
+    nz = nranks * (n - 1) + 1 if (nranks > 1 and not args.strong) else n
     if args.les:   # examples/tgv_re2500_les, dt scaled with dx from 5e-4 @ 129^3
         phys = dict(re=2500.0, dt=5e-4 * 128.0 / (n - 1), omega=1.999, eps=1e-6, idyn=1, iles=1,
                     cs=0.17)
@@ -235,8 +243,10 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # end-to-end through the host-pointer module procedures
 # ----------------------------------------------------------------------------------------------
-def run_e2e(o3d, w, steps, warmup):
+def run_e2e(o3d, w, steps, warmup, chunks=0):
     from osinco3d_b200 import modules as M
+    chunks_before = M.get_pipeline()
+    M.set_pipeline(chunks)
     n, d, bc, ph = w["n"], w["d"], w["bc"], w["phys"]
     shape = (n, n, n)
     N = n ** 3
@@ -289,15 +299,18 @@ def run_e2e(o3d, w, steps, warmup):
         iters.append(step(itime))
     dt_wall = time.perf_counter() - t0      # every call returns after its D2H copies completed
     pool.close()
+    M.set_pipeline(chunks_before)
     # bytes per step, counted from the arrays the three calls copy (see modules.cu)
     h2d = (3 + 6) * N * 8 + 4 * N * 8 + 4 * N * 8
     d2h = (3 + 1 + 9) * N * 8 + 1 * N * 8 + 3 * N * 8
     ms = 1e3 * dt_wall / steps
     return {"value": N / 1e6 / (ms / 1e3), "unit": "Mpts*steps/s", "ms_per_step": ms,
             "steps": steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "sor_iters_per_step": float(np.mean(iters)),
+            "sor_iters_per_step": float(np.mean(iters)), "pipeline_chunks": chunks,
             "path": "o3d_predict_velocity + o3d_correct_pression + o3d_correct_velocity with "
-                    "pinned HOST arrays (stateless drop-in procedures), wall clock"}
+                    "pinned HOST arrays (stateless drop-in procedures), wall clock"
+                    + ("; predict / correct_velocity pipelined over %d z chunks (upload, kernel "
+                       "and download of successive chunks overlap)" % chunks if chunks else "")}
 
 
 def run_e2e_resident(o3d, ses, steps):
@@ -513,7 +526,8 @@ def main():
     if rank == 0:
         line = {"metric": "Mpts*steps/s (full AB3+SOR time step)", "value": value,
                 "unit": "Mpts*steps/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong" if (args.strong and world > 1) else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["name"], "grid": [n, n, nz], "dt": ph["dt"],
                            "re": ph["re"], "omega": ph["omega"], "eps": ph["eps"],
@@ -526,7 +540,7 @@ def main():
     if rank == 0 and world == 1:
         if not args.no_e2e:
             e2e_steps = max(3, K // 4)
-            line["e2e"] = run_e2e(o3d, w, e2e_steps, 3)
+            line["e2e"] = run_e2e(o3d, w, e2e_steps, 3, args.pipeline)
             line["e2e_resident"] = e2e_res
         if not args.no_cpu:
             ncpu = args.cpu_n or n

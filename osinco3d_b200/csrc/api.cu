@@ -375,6 +375,7 @@ void fill_geom(o3d_session* s) {
     g.sim2d = c.sim2d;
     g.gz0 = s->z0;
     g.gnz = c.nz;
+    g.zr_lo = g.zr_hi = 0;
     s->felems = field_elems(g);
     s->cx = make_coef(c.dx);
     s->cy = make_coef(c.dy);
@@ -499,6 +500,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->comm = nullptr;
     s->mg = nullptr;
     s->io = nullptr;
+    s->pipe = nullptr;
     s->timers_on = 0;
     s->use_src = 0;
     for (int q2 = 0; q2 < 6; ++q2) s->t_ms[q2] = 0.0, s->t_cnt[q2] = 0;
@@ -555,6 +557,7 @@ int o3d_session_destroy(o3d_session* s) {
     io_destroy(s);
     comm_destroy(s);
     mg_destroy(s);
+    pipe_destroy(s);
     for (int f = 0; f < O3D_F_COUNT; ++f)
         if (s->base[f]) cudaFree(s->base[f]);
     if (s->partial) cudaFree(s->partial);
@@ -755,14 +758,15 @@ static const int PRED_IDS[3] = {O3D_F_UX_PRED, O3D_F_UY_PRED, O3D_F_UZ_PRED};
 static const unsigned NAT3[3] = {0x1u, 0x2u, 0x4u};
 static const unsigned EVEN3[3] = {0u, 0u, 0u};
 
-int o3d_s_predict_velocity(o3d_session* s, int itime) {
-    if (!s) return O3D_ERR_INVALID;
+extern "C++" {
+namespace o3d {
+// arguments of the fused RHS + predictor launch for time step `itime` (tgt = physical history
+// buffer that receives the new f of each component) ...
+int rhs_prepare(o3d_session* s, int itime, RhsArgs& a, int* tgt) {
     const o3d_config& c = s->cfg;
     double adu, bdu, cdu;
     int rc = ab_select(c, itime, &adu, &bdu, &cdu);
     if (rc) return rc;
-    RhsArgs a;
-    int tgt[3];
     for (int k = 0; k < 3; ++k) {
         a.u[k] = fref(s, VEL_IDS[k]);
         tgt[k] = hist_target(s, k);
@@ -780,6 +784,31 @@ int o3d_s_predict_velocity(o3d_session* s, int itime) {
     const double csd = c.cs * c.delta;
     a.csd2 = csd * csd;  // (cs*delta)**2, src/les_turbulence.f90:87
     a.iles = (c.iles == 1);
+    return O3D_OK;
+}
+
+// ... and the bookkeeping after it: history rotation, ghost state of u* and nu_t
+void rhs_finish(o3d_session* s, const int* tgt, bool iles) {
+    const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+    for (int k = 0; k < 3; ++k) {
+        hist_rotate(s, k, tgt[k]);
+        // the RHS kernel wrote the own-axis ghost images of u* (odd closure) with the interior
+        // (k == 2: z images on the wall sides are in place, bit 0x8; a rank boundary still needs
+        // the exchange)
+        s->gaxes[PRED_IDS[k]] = (k == 2) ? (zhalo ? 0x8u : 0xCu) : (1u << k);
+        s->gpar[PRED_IDS[k]] = NAT3[k];
+    }
+    if (iles) touch(s, O3D_F_NU_T);
+}
+}  // namespace o3d
+}  // extern "C++"
+
+int o3d_s_predict_velocity(o3d_session* s, int itime) {
+    if (!s) return O3D_ERR_INVALID;
+    RhsArgs a;
+    int tgt[3];
+    int rc = rhs_prepare(s, itime, a, tgt);
+    if (rc) return rc;
     // parity table of src/integration.f90:118-165 = natural-parity ghosts of ux, uy, uz
     if ((rc = ensure_ghosts(s, VEL_IDS, 3, NAT3, 0x7u, true))) return rc;
     span_begin(s, ST_RHS);
@@ -790,16 +819,7 @@ int o3d_s_predict_velocity(o3d_session* s, int itime) {
         return rc;
     }
     span_end(s, ST_RHS, 1);
-    const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
-    for (int k = 0; k < 3; ++k) {
-        hist_rotate(s, k, tgt[k]);
-        // the RHS kernel wrote the own-axis ghost images of u* (odd closure) with the interior
-        // (k == 2: z images on the wall sides are in place, bit 0x8; a rank boundary still needs
-        // the exchange)
-        s->gaxes[PRED_IDS[k]] = (k == 2) ? (zhalo ? 0x8u : 0xCu) : (1u << k);
-        s->gpar[PRED_IDS[k]] = NAT3[k];
-    }
-    if (a.iles) touch(s, O3D_F_NU_T);
+    rhs_finish(s, tgt, a.iles != 0);
     return O3D_OK;
 }
 

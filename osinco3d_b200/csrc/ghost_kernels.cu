@@ -22,7 +22,10 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const Geom g, const Gh
     const int mhi = (axis == 0) ? g.bx : (axis == 1) ? g.by : g.bz_hi;
     // the two other extents (a = fast, b = slow)
     const int na = (axis == 0) ? g.ny : g.nx;
-    const int nb = (axis == 2) ? g.ny : g.nz;
+    // x / y ghosts of the planes [zr_lo, zr_hi) only, when the geometry carries a plane range
+    const bool ranged = (axis != 2) && (g.zr_hi > g.zr_lo);
+    const int b0 = ranged ? g.zr_lo : 0;
+    const int nb = (axis == 2) ? g.ny : (ranged ? g.zr_hi - g.zr_lo : g.nz);
     const long long sa = (axis == 0) ? g.sy : 1;
     const long long sb = (axis == 2) ? g.sy : g.sz;
     const long long total = (long long)na * nb * 6;
@@ -38,9 +41,12 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const Geom g, const Gh
             const long long rest = t / na;
             g6 = (int)(rest % 6), ib = (int)(rest / 6);
         }
+        ib += b0;
         const int side = g6 / 3, gg = g6 % 3 + 1;
         const int mode = side ? mhi : mlo;
         if (mode == BM_HALO) continue;  // filled by the z-slab halo exchange
+        // z ghosts of one side only (GHOST_Z_LO_ONLY / GHOST_Z_HI_ONLY)
+        if (axis == 2 && (jb.axes & (side ? GHOST_Z_LO_ONLY : GHOST_Z_HI_ONLY))) continue;
         const int q = side ? (n - 1 + gg) : -gg;
         bool refl;
         const int src = map_index(q, n, mlo, mhi, refl);
@@ -85,6 +91,22 @@ __global__ void __launch_bounds__(256) fill_axis_kernel(const Geom g, double* __
         const long long base = (long long)(ia - ea) * sa + (long long)(ib - eb) * sb;
         const double v = p[base + (long long)src * s];
         p[base + (long long)q * s] = (refl && odd) ? -v : v;
+    }
+}
+
+// planes [k0, k0 + nk) of a padded field <-> a contiguous (nx, ny, nk) chunk of a host array
+__global__ void __launch_bounds__(256) pack_planes_kernel(const Geom g, const double* __restrict__ src,
+                                                          double* __restrict__ dst, int k0, int nk,
+                                                          int to_padded) {
+    const long long rows = (long long)g.ny * nk;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int j = (int)(row % g.ny), kk = (int)(row / g.ny);
+        const long long mp = (long long)(k0 + kk) * g.sz + (long long)j * g.sy;
+        const long long mc = row * g.nx;
+        if (to_padded)
+            for (int i = threadIdx.x; i < g.nx; i += blockDim.x) dst[mp + i] = src[mc + i];
+        else
+            for (int i = threadIdx.x; i < g.nx; i += blockDim.x) dst[mc + i] = src[mp + i];
     }
 }
 
@@ -134,6 +156,26 @@ int launch_pack(cudaStream_t st, const Geom& g, const double* contiguous, double
     long long b = (long long)g.ny * g.nz;
     if (b > 148 * 16) b = 148 * 16;
     pack_kernel<<<(unsigned)b, 256, 0, st>>>(g, contiguous, padded, 1);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_pack_planes(cudaStream_t st, const Geom& g, const double* chunk, double* padded, int k0,
+                       int nk) {
+    long long b = (long long)g.ny * nk;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) return 0;
+    pack_planes_kernel<<<(unsigned)b, 256, 0, st>>>(g, chunk, padded, k0, nk, 1);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_unpack_planes(cudaStream_t st, const Geom& g, const double* padded, double* chunk,
+                         int k0, int nk) {
+    long long b = (long long)g.ny * nk;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) return 0;
+    pack_planes_kernel<<<(unsigned)b, 256, 0, st>>>(g, padded, chunk, k0, nk, 0);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -56,10 +56,13 @@ inline int pick_zchunk(int tiles_xy, int nz, int ctas_per_sm, int nfz, int strea
 }
 
 // ---- padded-layout maintenance (ghost_kernels.cu) ----
+// extra bits of GhostJob::axes: fill the z ghosts of one side only (pipeline.cu: the source planes
+// of the other side have not been uploaded yet)
+enum : unsigned { GHOST_Z_LO_ONLY = 0x10u, GHOST_Z_HI_ONLY = 0x20u };
 struct GhostJob {
     double* p;
     unsigned par;   // bit a set: odd along axis a (der?i_11), else even (der?p_11)
-    unsigned axes;  // bit a set: fill the ghosts of axis a
+    unsigned axes;  // bit a set: fill the ghosts of axis a (a = 0..2) | GHOST_Z_*_ONLY
 };
 struct GhostArgs {
     GhostJob job[6];
@@ -70,6 +73,11 @@ int launch_fill_ghosts(cudaStream_t st, const Geom& g, const GhostArgs& a);
 int launch_fill_ghosts_full(cudaStream_t st, const Geom& g, double* p, unsigned par);
 int launch_pack(cudaStream_t st, const Geom& g, const double* contiguous, double* padded);
 int launch_unpack(cudaStream_t st, const Geom& g, const double* padded, double* contiguous);
+// planes [k0, k0 + nk) only; `chunk` = contiguous (nx, ny, nk)
+int launch_pack_planes(cudaStream_t st, const Geom& g, const double* chunk, double* padded, int k0,
+                       int nk);
+int launch_unpack_planes(cudaStream_t st, const Geom& g, const double* padded, double* chunk,
+                         int k0, int nk);
 
 // ---- single-axis derivative, operator form (src/derivation.f90, der_type) ----
 // the closure is whatever the ghost cells of f hold; zero != 0 -> der?_2dsim

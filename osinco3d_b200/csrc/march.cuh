@@ -366,6 +366,10 @@ int launch_march(cudaStream_t st, const Geom& g,
     mg.zmode = zmode, mg.zedge = zedge;
     mg.zlo = (zmode == ZINTERIOR) ? zedge : 0;
     mg.zhi = (zmode == ZINTERIOR) ? g.nz - zedge : g.nz;
+    if (g.zr_hi > g.zr_lo) {  // explicit plane range (single rank: never combined with a split)
+        if (zmode != ZFULL) return 1;
+        mg.zlo = g.zr_lo, mg.zhi = g.zr_hi;
+    }
     int gz;
     if (zmode == ZBOUNDARY) {
         mg.zchunk = zedge;
@@ -493,6 +497,10 @@ int launch_march_roles(cudaStream_t st, const Geom& g, const MarchMaps<NFZ>& map
     mg.zmode = zmode, mg.zedge = zedge;
     mg.zlo = (zmode == ZINTERIOR) ? zedge : 0;
     mg.zhi = (zmode == ZINTERIOR) ? g.nz - zedge : g.nz;
+    if (g.zr_hi > g.zr_lo) {  // explicit plane range (single rank: never combined with a split)
+        if (zmode != ZFULL) return 1;
+        mg.zlo = g.zr_lo, mg.zhi = g.zr_hi;
+    }
     int gz;
     if (zmode == ZBOUNDARY) {
         mg.zchunk = zedge;

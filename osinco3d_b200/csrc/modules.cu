@@ -301,17 +301,22 @@ int o3d_predict_velocity(double* ux_pred, double* uy_pred, double* uz_pred, cons
     const size_t N = (size_t)nx * ny * nz;
     double* fh[3] = {fux, fuy, fuz};
     const int fb[3] = {O3D_F_FUX1, O3D_F_FUY1, O3D_F_FUZ1};
-    if ((rc = up(s, O3D_F_UX, ux)) || (rc = up(s, O3D_F_UY, uy)) || (rc = up(s, O3D_F_UZ, uz)))
-        return rc;
-    for (int c = 0; c < 3; ++c) {
-        // level 1 is overwritten before it is read (src/integration.f90:129); levels 2,3 are inputs
-        if ((rc = up(s, fb[c] + 1, fh[c] + N)) || (rc = up(s, fb[c] + 2, fh[c] + 2 * N))) return rc;
-    }
     if (iles != 1) {  // nu_t = 0.0d0, src/integration.f90:112
         double* nt = field(s, O3D_F_NU_T);
         if (!nt) return O3D_ERR_CUDA;
         O3D_CUDA_CHECK(cudaMemsetAsync(nt - interior_offset(s->g), 0,
                                        (size_t)s->felems * sizeof(double), s->st));
+    }
+    if (pipe_chunks(nz)) {  // z-chunk pipeline: both PCIe directions busy at once (pipeline.cu)
+        double* const up_h[3] = {ux_pred, uy_pred, uz_pred};
+        const double* const u_h[3] = {ux, uy, uz};
+        return pipe_predict_velocity(s, itime, up_h, u_h, fh, nu_t);
+    }
+    if ((rc = up(s, O3D_F_UX, ux)) || (rc = up(s, O3D_F_UY, uy)) || (rc = up(s, O3D_F_UZ, uz)))
+        return rc;
+    for (int c = 0; c < 3; ++c) {
+        // level 1 is overwritten before it is read (src/integration.f90:129); levels 2,3 are inputs
+        if ((rc = up(s, fb[c] + 1, fh[c] + N)) || (rc = up(s, fb[c] + 2, fh[c] + 2 * N))) return rc;
     }
     if ((rc = o3d_s_predict_velocity(s, itime))) return rc;
     if ((rc = down(s, O3D_F_UX_PRED, ux_pred)) || (rc = down(s, O3D_F_UY_PRED, uy_pred)) ||
@@ -392,6 +397,11 @@ int o3d_correct_velocity(double* ux, double* uy, double* uz, const double* ux_pr
     int rc = scratch(nx, ny, nz, dx, dy, dz, &s);
     if (rc) return rc;
     s->cfg.dt = dt;
+    if (pipe_chunks(nz)) {  // z-chunk pipeline (pipeline.cu)
+        double* const u_h[3] = {ux, uy, uz};
+        const double* const up_h[3] = {ux_pred, uy_pred, uz_pred};
+        return pipe_correct_velocity(s, u_h, up_h, pp);
+    }
     if ((rc = up(s, O3D_F_PP, pp)) || (rc = up(s, O3D_F_UX_PRED, ux_pred)) ||
         (rc = up(s, O3D_F_UY_PRED, uy_pred)) || (rc = up(s, O3D_F_UZ_PRED, uz_pred)))
         return rc;

@@ -43,6 +43,9 @@ struct Geom {
     int bz_lo, bz_hi;    // BM_WRAP | BM_MIRROR | BM_HALO
     int sim2d;           // derz_2dsim / derzz_2dsim: z derivatives are zero
     int gz0, gnz;        // first owned global plane, global nz (red-black colouring)
+    // zr_hi > zr_lo: restrict a z-marching launch / an x-y ghost fill to the planes [zr_lo, zr_hi)
+    // (the chunks of the pipelined host-pointer procedures, pipeline.cu); 0, 0 = whole slab
+    int zr_lo, zr_hi;
 };
 
 inline int pitch_for(int nx) { return ((GX + nx + R + 15) / 16) * 16; }

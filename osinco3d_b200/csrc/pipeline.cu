@@ -1,0 +1,409 @@
+// pipeline.cu -- z-chunk pipelining of the stateless HOST-pointer procedures (modules.cu).
+//
+// o3d_predict_velocity / o3d_correct_velocity move 22 / 7 fields over PCIe per call against
+// < 0.5 ms of kernel time, so their cost is the copy time.  The plain path runs upload ->
+// kernel -> download strictly one after the other: only one PCIe direction is ever busy.  Both
+// kernels are z-marching stencils whose output planes [za, zb) depend on the input planes
+// [za-3, zb+3) alone, so here the host arrays are cut into C z chunks and three kinds of work
+// overlap:
+//     upload streams   : H2D of chunk j+1 into a staging slot + pack into the padded field
+//     session stream   : ghost fill + kernel on chunk j (plane-range launch, Geom::zr_lo/zr_hi)
+//     download streams : unpack of chunk j-1 + D2H
+// i.e. both PCIe directions are busy at the same time.  A call costs about max(bytes up, bytes
+// down) instead of their sum; it still returns only when every output array is complete, so the
+// procedures stay drop-ins for the reference's (src/integration.f90:14, :257).
+//
+// The kernels, their arguments and the closure data are those of the plain path -- a plane-range
+// launch computes every point exactly as the whole-slab launch does (the same property the
+// interior / boundary split of the multi-GPU path relies on) -- so the results are bitwise equal
+// (tests/test_gpu_pipeline.py).
+//
+// Order constraints: chunk c needs upload chunk c+1 (3 planes beyond its end); with a periodic z
+// axis chunk 0 also needs the LAST planes (wrap ghosts), so it runs last.  Mirror z ghosts are
+// filled one side at a time, as soon as that side's source planes have landed.
+#include <cstdlib>
+#include <vector>
+
+#include "session.h"
+
+namespace o3d {
+
+struct Pipe {
+    cudaStream_t up[2], dn[2];
+    double* slot_up[2];
+    double* slot_dn[2];
+    long long slot_elems;
+    cudaEvent_t ev_start;
+    std::vector<cudaEvent_t> ev;
+};
+
+namespace {
+
+int g_pipe_setting = -1;  // -1: take O3D_PIPELINE from the environment at first use
+// Default number of chunks.  Measured end to end on the 256^3 TGV step (B200, PCIe Gen5, pinned
+// arrays; profiles/r1p_e2e_pipeline.jsonl): 86.8 ms unpipelined, 71.3 / 65.8 / 65.1 ms with
+// 4 / 8 / 16 chunks.
+constexpr int DEFAULT_CHUNKS = 8;
+
+constexpr int MAX_CHUNKS = 64;
+constexpr int MIN_PLANES = 8;  // per chunk: > stencil radius + mirror source planes
+
+const unsigned NAT3[3] = {0x1u, 0x2u, 0x4u};
+
+int ensure_pipe(o3d_session* s, long long slot_elems, int nev) {
+    Pipe* p = s->pipe;
+    if (!p) {
+        p = new (std::nothrow) Pipe();
+        if (!p) return O3D_ERR_INVALID;
+        for (int l = 0; l < 2; ++l) p->up[l] = p->dn[l] = nullptr, p->slot_up[l] = p->slot_dn[l] = nullptr;
+        p->slot_elems = 0;
+        p->ev_start = nullptr;
+        s->pipe = p;
+        for (int l = 0; l < 2; ++l) {
+            O3D_CUDA_CHECK(cudaStreamCreateWithFlags(&p->up[l], cudaStreamNonBlocking));
+            O3D_CUDA_CHECK(cudaStreamCreateWithFlags(&p->dn[l], cudaStreamNonBlocking));
+        }
+        O3D_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    }
+    if (slot_elems > p->slot_elems) {
+        for (int l = 0; l < 2; ++l) {
+            if (p->slot_up[l]) cudaFree(p->slot_up[l]);
+            if (p->slot_dn[l]) cudaFree(p->slot_dn[l]);
+            p->slot_up[l] = p->slot_dn[l] = nullptr;
+        }
+        p->slot_elems = 0;
+        for (int l = 0; l < 2; ++l) {
+            O3D_CUDA_CHECK(cudaMalloc(&p->slot_up[l], (size_t)slot_elems * sizeof(double)));
+            O3D_CUDA_CHECK(cudaMalloc(&p->slot_dn[l], (size_t)slot_elems * sizeof(double)));
+        }
+        p->slot_elems = slot_elems;
+    }
+    while ((int)p->ev.size() < nev) {
+        cudaEvent_t e;
+        O3D_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->ev.push_back(e);
+    }
+    return O3D_OK;
+}
+
+// One pipelined call: the chunk partition, the copy lanes and the order constraints.
+struct Run {
+    o3d_session* s;
+    Pipe* p;
+    int C;
+    int z[MAX_CHUNKS + 1];  // chunk c = planes [z[c], z[c+1])
+    long long plane;        // nx * ny
+    int n_up, n_dn;         // transfer counters: lane = counter & 1
+    bool wrapz;
+
+    int init(o3d_session* ses, int chunks) {
+        s = ses;
+        C = chunks;
+        const int nz = s->g.nz;
+        int maxnk = 0;
+        for (int c = 0; c <= C; ++c) z[c] = (int)((long long)nz * c / C);
+        for (int c = 0; c < C; ++c)
+            if (z[c + 1] - z[c] > maxnk) maxnk = z[c + 1] - z[c];
+        plane = (long long)s->g.nx * s->g.ny;
+        n_up = n_dn = 0;
+        wrapz = (s->g.bz_lo == BM_WRAP);
+        int rc = ensure_pipe(s, plane * maxnk, 3 * C);
+        if (rc) return rc;
+        p = s->pipe;
+        // the lanes start behind everything queued on the session stream so far (the lazy
+        // zero fill of freshly allocated fields, the memsets of the caller)
+        O3D_CUDA_CHECK(cudaEventRecord(p->ev_start, s->st));
+        for (int l = 0; l < 2; ++l) {
+            O3D_CUDA_CHECK(cudaStreamWaitEvent(p->up[l], p->ev_start, 0));
+            O3D_CUDA_CHECK(cudaStreamWaitEvent(p->dn[l], p->ev_start, 0));
+        }
+        return O3D_OK;
+    }
+    cudaEvent_t ev_up(int c, int lane) const { return p->ev[2 * c + lane]; }
+    cudaEvent_t ev_cmp(int c) const { return p->ev[2 * C + c]; }
+    // last upload chunk that chunk c reads
+    int need(int c) const {
+        if (wrapz && c == 0) return C - 1;
+        return (c + 1 < C) ? c + 1 : C - 1;
+    }
+    // planes of chunk c: host array -> staging slot -> padded field `d` (interior origin)
+    int upload(double* d, const double* host, int c) {
+        const int lane = (n_up++) & 1;
+        const int k0 = z[c], nk = z[c + 1] - z[c];
+        O3D_CUDA_CHECK(cudaMemcpyAsync(p->slot_up[lane], host + (long long)k0 * plane,
+                                       (size_t)(plane * nk) * sizeof(double),
+                                       cudaMemcpyHostToDevice, p->up[lane]));
+        if (launch_pack_planes(p->up[lane], s->g, p->slot_up[lane], d, k0, nk)) {
+            set_error("pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return O3D_ERR_CUDA;
+        }
+        return O3D_OK;
+    }
+    int uploaded(int c) {
+        for (int l = 0; l < 2; ++l) O3D_CUDA_CHECK(cudaEventRecord(ev_up(c, l), p->up[l]));
+        return O3D_OK;
+    }
+    // the session stream may read everything up to upload chunk j
+    int wait_uploads(int j) {
+        for (int l = 0; l < 2; ++l) O3D_CUDA_CHECK(cudaStreamWaitEvent(s->st, ev_up(j, l), 0));
+        return O3D_OK;
+    }
+    // chunk c has been computed on the session stream: its planes may be downloaded
+    int computed(int c) {
+        O3D_CUDA_CHECK(cudaEventRecord(ev_cmp(c), s->st));
+        for (int l = 0; l < 2; ++l) O3D_CUDA_CHECK(cudaStreamWaitEvent(p->dn[l], ev_cmp(c), 0));
+        return O3D_OK;
+    }
+    int download(const double* d, double* host, int c) {
+        const int lane = (n_dn++) & 1;
+        const int k0 = z[c], nk = z[c + 1] - z[c];
+        if (launch_unpack_planes(p->dn[lane], s->g, d, p->slot_dn[lane], k0, nk)) {
+            set_error("unpack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return O3D_ERR_CUDA;
+        }
+        O3D_CUDA_CHECK(cudaMemcpyAsync(host + (long long)k0 * plane, p->slot_dn[lane],
+                                       (size_t)(plane * nk) * sizeof(double),
+                                       cudaMemcpyDeviceToHost, p->dn[lane]));
+        return O3D_OK;
+    }
+    // ghost cells a kernel on chunk c reads, for `nf` fields with parity par[q]: the x / y faces of
+    // the chunk's own planes, and the z faces once their source planes are on the device (mirror:
+    // the low side with chunk 0, the high side with the last chunk; wrap: both sides with chunk 0,
+    // which need() schedules behind the last upload, so the last chunk finds them filled).
+    // A z stencil only reads the thread's own column: no x / y ghosts in other planes are needed.
+    int fill_ghosts(double* const* d, const unsigned* par, int nf, int c, bool& zwrap_done) {
+        Geom gg = s->g;
+        gg.zr_lo = z[c], gg.zr_hi = z[c + 1];
+        GhostArgs ga;
+        ga.njobs = 0;
+        for (int q = 0; q < nf; ++q) {
+            GhostJob& jb = ga.job[ga.njobs++];
+            jb.p = d[q], jb.par = par[q], jb.axes = 0x3u;
+            if (wrapz) {
+                if (!zwrap_done && (c == 0 || c == C - 1)) jb.axes |= 0x4u;
+            } else {
+                if (c == 0) jb.axes |= 0x4u | GHOST_Z_LO_ONLY;
+                if (c == C - 1) jb.axes |= 0x4u | GHOST_Z_HI_ONLY;
+                if (c == 0 && c == C - 1) jb.axes = 0x7u;
+            }
+        }
+        if (wrapz && (c == 0 || c == C - 1)) zwrap_done = true;
+        if (launch_fill_ghosts(s->st, gg, ga)) {
+            set_error("ghost fill launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return O3D_ERR_CUDA;
+        }
+        return O3D_OK;
+    }
+    // every stream idle: all host output arrays are complete (also called on the error paths --
+    // no copy may still be in flight when the procedure returns)
+    int drain() {
+        cudaError_t e = cudaSuccess, q;
+        for (int l = 0; l < 2; ++l) {
+            if ((q = cudaStreamSynchronize(p->up[l])) != cudaSuccess) e = q;
+            if ((q = cudaStreamSynchronize(p->dn[l])) != cudaSuccess) e = q;
+        }
+        if ((q = cudaStreamSynchronize(s->st)) != cudaSuccess) e = q;
+        if (e != cudaSuccess) {
+            set_error("pipelined procedure failed: %s", cudaGetErrorString(e));
+            return O3D_ERR_CUDA;
+        }
+        return O3D_OK;
+    }
+};
+
+}  // namespace
+
+static int pipe_setting() {
+    if (g_pipe_setting < 0) {
+        const char* e = getenv("O3D_PIPELINE");
+        g_pipe_setting = e ? (atoi(e) > 0 ? atoi(e) : 0) : DEFAULT_CHUNKS;
+    }
+    return g_pipe_setting;
+}
+
+int pipe_chunks(int nz) {
+    int c = pipe_setting();
+    if (c > MAX_CHUNKS) c = MAX_CHUNKS;
+    while (c >= 2 && nz / c < MIN_PLANES) --c;
+    return c >= 2 ? c : 0;
+}
+
+void pipe_destroy(o3d_session* s) {
+    Pipe* p = s->pipe;
+    if (!p) return;
+    for (int l = 0; l < 2; ++l) {
+        if (p->up[l]) cudaStreamSynchronize(p->up[l]);
+        if (p->dn[l]) cudaStreamSynchronize(p->dn[l]);
+    }
+    for (int l = 0; l < 2; ++l) {
+        if (p->slot_up[l]) cudaFree(p->slot_up[l]);
+        if (p->slot_dn[l]) cudaFree(p->slot_dn[l]);
+        if (p->up[l]) cudaStreamDestroy(p->up[l]);
+        if (p->dn[l]) cudaStreamDestroy(p->dn[l]);
+    }
+    for (auto e : p->ev) cudaEventDestroy(e);
+    if (p->ev_start) cudaEventDestroy(p->ev_start);
+    delete p;
+    s->pipe = nullptr;
+}
+
+// predict_velocity (src/integration.f90:14-197) on host arrays: u_h[3] in, f_h[3] = fux/fuy/fuz
+// (nx,ny,nz,3) inout, up_h[3] and nu_t_h out.  The caller (o3d_predict_velocity) has set the
+// configuration, reset the history mapping and zeroed nu_t when iles /= 1.
+int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
+                          const double* const* u_h, double* const* f_h, double* nu_t_h) {
+    const int C = pipe_chunks(s->g.nz);
+    if (C < 2 || s->cfg.nranks > 1) return O3D_ERR_INVALID;
+    RhsArgs a;
+    int tgt[3];
+    int rc = rhs_prepare(s, itime, a, tgt);
+    if (rc) return rc;
+    const long long N = s->nloc;
+    // device buffers of the inputs (history levels 2 and 3 as they are BEFORE the rotation) ...
+    double* ud[3];
+    double* f2d[3];
+    double* f3d[3];
+    for (int k = 0; k < 3; ++k) {
+        ud[k] = a.u[k].p;
+        f2d[k] = field(s, hist_id(s, k, 2));
+        f3d[k] = field(s, hist_id(s, k, 3));
+        if (!f2d[k] || !f3d[k]) return O3D_ERR_CUDA;
+    }
+    // ... and of the outputs: the three levels as the reference leaves them AFTER its shifting
+    // copies (src/integration.f90:176-188).  rhs_finish is pure bookkeeping (level -> buffer map,
+    // ghost state of u*), so it can run before the kernels are queued.
+    rhs_finish(s, tgt, a.iles != 0);
+    const double* fout[3][3];
+    for (int k = 0; k < 3; ++k)
+        for (int l = 0; l < 3; ++l) {
+            fout[k][l] = field(s, hist_id(s, k, l + 1));
+            if (!fout[k][l]) return O3D_ERR_CUDA;
+        }
+    Run r;
+    if ((rc = r.init(s, C))) return rc;
+    auto body = [&]() -> int {
+        int rc2;
+        bool issued[MAX_CHUNKS] = {false};
+        bool zwrap_done = false;
+        for (int j = 0; j < C; ++j) {
+            for (int k = 0; k < 3; ++k)
+                if ((rc2 = r.upload(ud[k], u_h[k], j))) return rc2;
+            for (int k = 0; k < 3; ++k) {
+                // level 1 is overwritten before it is read (src/integration.f90:129)
+                if ((rc2 = r.upload(f2d[k], f_h[k] + N, j))) return rc2;
+                if ((rc2 = r.upload(f3d[k], f_h[k] + 2 * N, j))) return rc2;
+            }
+            if ((rc2 = r.uploaded(j))) return rc2;
+            for (int c = 0; c < C; ++c) {
+                if (issued[c] || r.need(c) > j) continue;
+                issued[c] = true;
+                if ((rc2 = r.wait_uploads(j))) return rc2;
+                // parity table of src/integration.f90:118-165 = natural-parity ghosts of u
+                if ((rc2 = r.fill_ghosts(ud, NAT3, 3, c, zwrap_done))) return rc2;
+                Geom gg = s->g;
+                gg.zr_lo = r.z[c], gg.zr_hi = r.z[c + 1];
+                if (launch_rhs(s->st, gg, a)) {
+                    set_error("rhs kernel launch failed: %s",
+                              cudaGetErrorString(cudaGetLastError()));
+                    return O3D_ERR_CUDA;
+                }
+                if ((rc2 = r.computed(c))) return rc2;
+                for (int k = 0; k < 3; ++k)
+                    if ((rc2 = r.download(a.up[k], up_h[k], c))) return rc2;
+                if ((rc2 = r.download(a.nu_t, nu_t_h, c))) return rc2;
+                for (int k = 0; k < 3; ++k)
+                    for (int l = 0; l < 3; ++l)
+                        if ((rc2 = r.download(fout[k][l], f_h[k] + (long long)l * N, c)))
+                            return rc2;
+            }
+        }
+        return O3D_OK;
+    };
+    rc = body();
+    const int rcd = r.drain();
+    // the interiors of the inputs were rewritten: whatever ghost state was recorded is stale
+    for (int k = 0; k < 3; ++k) {
+        touch(s, O3D_F_UX + k);
+        touch(s, hist_id(s, k, 3));  // level 3 holds the uploaded level 2
+    }
+    return rc ? rc : rcd;
+}
+
+// correct_velocity (src/integration.f90:257-330) on host arrays: pp_h, up_h[3] in, u_h[3] out;
+// O3D_ERR_DIVERGED after the outputs are complete if the NaN / > 1000 guard fired.
+int pipe_correct_velocity(o3d_session* s, double* const* u_h, const double* const* up_h,
+                          const double* pp_h) {
+    const int C = pipe_chunks(s->g.nz);
+    if (C < 2 || s->cfg.nranks > 1) return O3D_ERR_INVALID;
+    const o3d_config& c = s->cfg;
+    FieldRef up[3] = {fref(s, O3D_F_UX_PRED), fref(s, O3D_F_UY_PRED), fref(s, O3D_F_UZ_PRED)};
+    double* u[3] = {field(s, O3D_F_UX), field(s, O3D_F_UY), field(s, O3D_F_UZ)};
+    FieldRef pp = fref(s, O3D_F_PP);
+    for (int k = 0; k < 3; ++k)
+        if (!up[k].p || !u[k]) return O3D_ERR_CUDA;
+    if (!pp.p) return O3D_ERR_CUDA;
+    O3D_CUDA_CHECK(cudaMemsetAsync(s->flag_d, 0, sizeof(int), s->st));
+    Run r;
+    int rc = r.init(s, C);
+    if (rc) return rc;
+    auto body = [&]() -> int {
+        int rc2;
+        bool issued[MAX_CHUNKS] = {false};
+        bool zwrap_done = false;
+        const unsigned even = 0u;
+        for (int j = 0; j < C; ++j) {
+            if ((rc2 = r.upload(pp.p, pp_h, j))) return rc2;
+            for (int k = 0; k < 3; ++k)
+                if ((rc2 = r.upload(up[k].p, up_h[k], j))) return rc2;
+            if ((rc2 = r.uploaded(j))) return rc2;
+            for (int cc = 0; cc < C; ++cc) {
+                if (issued[cc] || r.need(cc) > j) continue;
+                issued[cc] = true;
+                if ((rc2 = r.wait_uploads(j))) return rc2;
+                // derxp / deryp / derzp of pp (src/integration.f90:298-300): even ghosts
+                if ((rc2 = r.fill_ghosts(&pp.p, &even, 1, cc, zwrap_done))) return rc2;
+                Geom gg = s->g;
+                gg.zr_lo = r.z[cc], gg.zr_hi = r.z[cc + 1];
+                if (launch_corr(s->st, gg, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d)) {
+                    set_error("correction kernel launch failed: %s",
+                              cudaGetErrorString(cudaGetLastError()));
+                    return O3D_ERR_CUDA;
+                }
+                if ((rc2 = r.computed(cc))) return rc2;
+                for (int k = 0; k < 3; ++k)
+                    if ((rc2 = r.download(u[k], u_h[k], cc))) return rc2;
+            }
+        }
+        O3D_CUDA_CHECK(
+            cudaMemcpyAsync(s->flag_h, s->flag_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+        return O3D_OK;
+    };
+    rc = body();
+    const int rcd = r.drain();
+    touch(s, O3D_F_PP);
+    for (int k = 0; k < 3; ++k) {
+        touch(s, O3D_F_UX_PRED + k);
+        // the kernel wrote the natural-parity ghost images of u with the interior, as in the
+        // whole-slab launch
+        s->gaxes[O3D_F_UX + k] = 0xFu;
+        s->gpar[O3D_F_UX + k] = NAT3[k];
+    }
+    s->flag_pending = 0;
+    if (rc) return rc;
+    if (rcd) return rcd;
+    if (*s->flag_h) {
+        set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
+        return O3D_ERR_DIVERGED;
+    }
+    return O3D_OK;
+}
+
+}  // namespace o3d
+
+extern "C" int o3d_set_pipeline(int chunks) {
+    if (chunks < 0) return O3D_ERR_INVALID;
+    o3d::g_pipe_setting = chunks;
+    return O3D_OK;
+}
+
+extern "C" int o3d_get_pipeline(void) { return o3d::pipe_setting(); }

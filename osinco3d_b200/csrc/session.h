@@ -10,6 +10,7 @@ namespace o3d {
 struct Comm;  // z-slab halo exchange + reductions over NCCL (comm.cu)
 struct MgHierarchy;  // level arrays + transfer tables of the V-cycle (multigrid.cu)
 struct IoEngine;     // asynchronous field output: staging buffers, I/O stream, writer thread (io.cu)
+struct Pipe;         // copy streams + staging slots of the pipelined host-pointer procedures (pipeline.cu)
 }
 
 struct o3d_session {
@@ -67,6 +68,7 @@ struct o3d_session {
     o3d::Comm* comm;
     o3d::MgHierarchy* mg;  // built lazily by mg_solve, cached across steps
     o3d::IoEngine* io;     // built lazily by the first output call
+    o3d::Pipe* pipe;       // built lazily by the first pipelined host-pointer call
     int use_src;           // transeq source term uploaded to O3D_F_SCRATCH1
 
     // timers
@@ -134,6 +136,20 @@ void span_end(o3d_session* s, int stage, long long count);
 
 // gated launch of the projection correction behind the SOR passes already queued (api.cu)
 int spec_correct_launch(o3d_session* s);
+
+// the two halves of o3d_s_predict_velocity around its kernel launch (api.cu)
+int rhs_prepare(o3d_session* s, int itime, RhsArgs& a, int* tgt);
+void rhs_finish(o3d_session* s, const int* tgt, bool iles);
+
+// Pipelined host-pointer procedures (pipeline.cu): the host arrays are cut into z chunks and
+// upload / kernel / download of successive chunks overlap on three streams (full-duplex PCIe).
+// pipe_chunks(nz): number of chunks for a grid of nz planes (0 = pipelining off / grid too thin).
+int pipe_chunks(int nz);
+int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h, const double* const* u_h,
+                          double* const* f_h, double* nu_t_h);
+int pipe_correct_velocity(o3d_session* s, double* const* u_h, const double* const* up_h,
+                          const double* pp_h);
+void pipe_destroy(o3d_session* s);
 
 // Poisson solvers (poisson.cu)
 int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double* dmax);

@@ -37,6 +37,17 @@ def set_sor_order(order):
     check(lib().o3d_set_sor_order(order))
 
 
+def set_pipeline(chunks):
+    """z-chunk copy pipelining of predict_velocity / correct_velocity (0 = off; default
+    O3D_PIPELINE or 8); no counterpart in the reference.  Results are bitwise those of the
+    unpipelined procedures."""
+    check(lib().o3d_set_pipeline(int(chunks)))
+
+
+def get_pipeline():
+    return lib().o3d_get_pipeline()
+
+
 def der(axis, order, closure, f, d):
     df = _like(f)
     nx, ny, nz = f.shape
