@@ -239,6 +239,27 @@ module o3d_b200_c
        integer(c_int) :: rc
      end function o3d_function_stats
 
+     !> page-lock a host array so that the copies of the stateless procedures run at full PCIe
+     !> speed and overlap (copy pipeline, DESIGN.md 4.7): call once after `allocate`, e.g.
+     !>   rc = o3d_host_register(c_loc(ux), int(8, c_long_long) * size(ux, kind=c_long_long))
+     function o3d_host_register(ptr, bytes) bind(C, name="o3d_host_register") result(rc)
+       import :: c_int, c_ptr, c_long_long
+       type(c_ptr), value :: ptr
+       integer(c_long_long), value :: bytes
+       integer(c_int) :: rc
+     end function o3d_host_register
+     function o3d_host_unregister(ptr) bind(C, name="o3d_host_unregister") result(rc)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ptr
+       integer(c_int) :: rc
+     end function o3d_host_unregister
+     !> z chunks of the pipelined predict_velocity / correct_velocity (0 = off, default 8)
+     function o3d_set_pipeline(chunks) bind(C, name="o3d_set_pipeline") result(rc)
+       import :: c_int
+       integer(c_int), value :: chunks
+       integer(c_int) :: rc
+     end function o3d_set_pipeline
+
      !=== section B of include/o3d_b200.h: device-resident session ==========================
      function o3d_session_create(cfg, ses) bind(C, name="o3d_session_create") result(rc)
        import :: c_int, c_ptr, o3d_config
