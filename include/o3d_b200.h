@@ -101,6 +101,13 @@ int o3d_host_unregister(void* ptr);
  * are correct but the copies serialise. */
 int o3d_set_pipeline(int chunks);
 int o3d_get_pipeline(void);
+/* The schedule a pipelined call would use for nz planes under the current setting (host logic
+ * only, no device needed): returns the number of chunks C (0 = plain path); z_bounds[C+1] = plane
+ * ranges [z[c], z[c+1]); issue_after[C] = the upload chunk after which the kernels on chunk c are
+ * queued (chunks released by the same upload run in ascending order); zfill[C] = z ghost sides
+ * filled right before chunk c (1 low, 2 high, 3 both).  Arrays may be NULL; size them for 64
+ * chunks (65 bounds). */
+int o3d_pipeline_plan(int nz, int periodic_z, int* z_bounds, int* issue_after, int* zfill);
 
 /* schemes(), src/initialization.f90:226-304: binds the 12 derivative closures and the
  * Poisson solver variant from the boundary flags.  Returns O3D_ERR_BC for the combinations

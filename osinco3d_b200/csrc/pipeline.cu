@@ -50,6 +50,42 @@ constexpr int MIN_PLANES = 8;  // per chunk: > stencil radius + mirror source pl
 
 const unsigned NAT3[3] = {0x1u, 0x2u, 0x4u};
 
+// The schedule of one pipelined call (pure host logic; o3d_pipeline_plan exposes it to the CPU
+// tests).  Chunks are uploaded in ascending order; after upload j every chunk c that has not been
+// issued yet and has need[c] <= j is issued, in ascending order.
+struct Plan {
+    int C;                  // number of chunks (0: too thin, plain path)
+    int z[MAX_CHUNKS + 1];  // chunk c = planes [z[c], z[c+1])
+    int need[MAX_CHUNKS];   // last upload chunk that the kernel on chunk c reads
+    int zfill[MAX_CHUNKS];  // z ghost sides filled just before chunk c runs: 1 = low, 2 = high
+};
+
+void make_plan(int nz, int chunks, bool wrapz, Plan& p) {
+    int C = chunks;
+    if (C > MAX_CHUNKS) C = MAX_CHUNKS;
+    while (C >= 2 && nz / C < MIN_PLANES) --C;
+    p.C = (C >= 2) ? C : 0;
+    if (!p.C) return;
+    for (int c = 0; c <= C; ++c) p.z[c] = (int)((long long)nz * c / C);
+    for (int c = 0; c < C; ++c) {
+        // three planes beyond its end = the next chunk; a periodic z axis makes chunk 0 read the
+        // LAST planes (wrap ghosts), so it goes behind the last upload
+        p.need[c] = (c + 1 < C) ? c + 1 : C - 1;
+        p.zfill[c] = 0;
+    }
+    if (wrapz) {
+        // both sides with chunk 0: their sources are planes nz-3 .. nz-1 and 0 .. 2, and chunk 0
+        // is issued before the last chunk (ascending order among the chunks upload C-1 releases)
+        p.need[0] = C - 1;
+        p.zfill[0] = 3;
+    } else {
+        // mirror: the low ghosts copy planes 1 .. 3 (chunk 0), the high ghosts planes nz-4 ..
+        // nz-2 (last chunk): each side as soon as its own chunk has landed
+        p.zfill[0] = 1;
+        p.zfill[C - 1] = 2;
+    }
+}
+
 int ensure_pipe(o3d_session* s, long long slot_elems, int nev) {
     Pipe* p = s->pipe;
     if (!p) {
@@ -90,23 +126,23 @@ int ensure_pipe(o3d_session* s, long long slot_elems, int nev) {
 struct Run {
     o3d_session* s;
     Pipe* p;
+    Plan pl;
     int C;
-    int z[MAX_CHUNKS + 1];  // chunk c = planes [z[c], z[c+1])
+    const int* z;           // = pl.z
     long long plane;        // nx * ny
     int n_up, n_dn;         // transfer counters: lane = counter & 1
-    bool wrapz;
 
     int init(o3d_session* ses, int chunks) {
         s = ses;
-        C = chunks;
-        const int nz = s->g.nz;
+        make_plan(s->g.nz, chunks, s->g.bz_lo == BM_WRAP, pl);
+        C = pl.C;
+        z = pl.z;
+        if (C < 2) return O3D_ERR_INVALID;
         int maxnk = 0;
-        for (int c = 0; c <= C; ++c) z[c] = (int)((long long)nz * c / C);
         for (int c = 0; c < C; ++c)
             if (z[c + 1] - z[c] > maxnk) maxnk = z[c + 1] - z[c];
         plane = (long long)s->g.nx * s->g.ny;
         n_up = n_dn = 0;
-        wrapz = (s->g.bz_lo == BM_WRAP);
         int rc = ensure_pipe(s, plane * maxnk, 3 * C);
         if (rc) return rc;
         p = s->pipe;
@@ -122,10 +158,7 @@ struct Run {
     cudaEvent_t ev_up(int c, int lane) const { return p->ev[2 * c + lane]; }
     cudaEvent_t ev_cmp(int c) const { return p->ev[2 * C + c]; }
     // last upload chunk that chunk c reads
-    int need(int c) const {
-        if (wrapz && c == 0) return C - 1;
-        return (c + 1 < C) ? c + 1 : C - 1;
-    }
+    int need(int c) const { return pl.need[c]; }
     // planes of chunk c: host array -> staging slot -> padded field `d` (interior origin)
     int upload(double* d, const double* host, int c) {
         const int lane = (n_up++) & 1;
@@ -167,11 +200,9 @@ struct Run {
         return O3D_OK;
     }
     // ghost cells a kernel on chunk c reads, for `nf` fields with parity par[q]: the x / y faces of
-    // the chunk's own planes, and the z faces once their source planes are on the device (mirror:
-    // the low side with chunk 0, the high side with the last chunk; wrap: both sides with chunk 0,
-    // which need() schedules behind the last upload, so the last chunk finds them filled).
+    // the chunk's own planes, and the z faces the plan assigns to this chunk (Plan::zfill).
     // A z stencil only reads the thread's own column: no x / y ghosts in other planes are needed.
-    int fill_ghosts(double* const* d, const unsigned* par, int nf, int c, bool& zwrap_done) {
+    int fill_ghosts(double* const* d, const unsigned* par, int nf, int c) {
         Geom gg = s->g;
         gg.zr_lo = z[c], gg.zr_hi = z[c + 1];
         GhostArgs ga;
@@ -179,15 +210,10 @@ struct Run {
         for (int q = 0; q < nf; ++q) {
             GhostJob& jb = ga.job[ga.njobs++];
             jb.p = d[q], jb.par = par[q], jb.axes = 0x3u;
-            if (wrapz) {
-                if (!zwrap_done && (c == 0 || c == C - 1)) jb.axes |= 0x4u;
-            } else {
-                if (c == 0) jb.axes |= 0x4u | GHOST_Z_LO_ONLY;
-                if (c == C - 1) jb.axes |= 0x4u | GHOST_Z_HI_ONLY;
-                if (c == 0 && c == C - 1) jb.axes = 0x7u;
-            }
+            if (pl.zfill[c] == 1) jb.axes |= 0x4u | GHOST_Z_LO_ONLY;
+            if (pl.zfill[c] == 2) jb.axes |= 0x4u | GHOST_Z_HI_ONLY;
+            if (pl.zfill[c] == 3) jb.axes |= 0x4u;
         }
-        if (wrapz && (c == 0 || c == C - 1)) zwrap_done = true;
         if (launch_fill_ghosts(s->st, gg, ga)) {
             set_error("ghost fill launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return O3D_ERR_CUDA;
@@ -213,7 +239,7 @@ struct Run {
 
 }  // namespace
 
-static int pipe_setting() {
+int pipe_setting() {
     if (g_pipe_setting < 0) {
         const char* e = getenv("O3D_PIPELINE");
         g_pipe_setting = e ? (atoi(e) > 0 ? atoi(e) : 0) : DEFAULT_CHUNKS;
@@ -222,10 +248,9 @@ static int pipe_setting() {
 }
 
 int pipe_chunks(int nz) {
-    int c = pipe_setting();
-    if (c > MAX_CHUNKS) c = MAX_CHUNKS;
-    while (c >= 2 && nz / c < MIN_PLANES) --c;
-    return c >= 2 ? c : 0;
+    Plan p;
+    make_plan(nz, pipe_setting(), false, p);
+    return p.C;
 }
 
 void pipe_destroy(o3d_session* s) {
@@ -284,7 +309,6 @@ int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
     auto body = [&]() -> int {
         int rc2;
         bool issued[MAX_CHUNKS] = {false};
-        bool zwrap_done = false;
         for (int j = 0; j < C; ++j) {
             for (int k = 0; k < 3; ++k)
                 if ((rc2 = r.upload(ud[k], u_h[k], j))) return rc2;
@@ -299,7 +323,7 @@ int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
                 issued[c] = true;
                 if ((rc2 = r.wait_uploads(j))) return rc2;
                 // parity table of src/integration.f90:118-165 = natural-parity ghosts of u
-                if ((rc2 = r.fill_ghosts(ud, NAT3, 3, c, zwrap_done))) return rc2;
+                if ((rc2 = r.fill_ghosts(ud, NAT3, 3, c))) return rc2;
                 Geom gg = s->g;
                 gg.zr_lo = r.z[c], gg.zr_hi = r.z[c + 1];
                 if (launch_rhs(s->st, gg, a)) {
@@ -349,7 +373,6 @@ int pipe_correct_velocity(o3d_session* s, double* const* u_h, const double* cons
     auto body = [&]() -> int {
         int rc2;
         bool issued[MAX_CHUNKS] = {false};
-        bool zwrap_done = false;
         const unsigned even = 0u;
         for (int j = 0; j < C; ++j) {
             if ((rc2 = r.upload(pp.p, pp_h, j))) return rc2;
@@ -361,7 +384,7 @@ int pipe_correct_velocity(o3d_session* s, double* const* u_h, const double* cons
                 issued[cc] = true;
                 if ((rc2 = r.wait_uploads(j))) return rc2;
                 // derxp / deryp / derzp of pp (src/integration.f90:298-300): even ghosts
-                if ((rc2 = r.fill_ghosts(&pp.p, &even, 1, cc, zwrap_done))) return rc2;
+                if ((rc2 = r.fill_ghosts(&pp.p, &even, 1, cc))) return rc2;
                 Geom gg = s->g;
                 gg.zr_lo = r.z[cc], gg.zr_hi = r.z[cc + 1];
                 if (launch_corr(s->st, gg, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d)) {
@@ -407,3 +430,17 @@ extern "C" int o3d_set_pipeline(int chunks) {
 }
 
 extern "C" int o3d_get_pipeline(void) { return o3d::pipe_setting(); }
+
+extern "C" int o3d_pipeline_plan(int nz, int periodic_z, int* z_bounds, int* issue_after,
+                                 int* zfill) {
+    if (nz < 1) return 0;
+    o3d::Plan p;
+    o3d::make_plan(nz, o3d::pipe_setting(), periodic_z != 0, p);
+    for (int c = 0; c < p.C; ++c) {
+        if (z_bounds) z_bounds[c] = p.z[c];
+        if (issue_after) issue_after[c] = p.need[c];
+        if (zfill) zfill[c] = p.zfill[c];
+    }
+    if (p.C && z_bounds) z_bounds[p.C] = p.z[p.C];
+    return p.C;
+}
