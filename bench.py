@@ -47,7 +47,7 @@ B_SOR_FUSED = 24.0    # fused red+black pass with ping-pong: read pp + read rhs 
 B_CORR = 56.0
 B_TRANSEQ = 88.0
 # z chunks of the e2e leg (csrc/pipeline.cu: the library default); O3D_PIPELINE overrides
-E2E_PIPELINE_CHUNKS = int(os.environ.get("O3D_PIPELINE", "8"))
+E2E_PIPELINE_CHUNKS = int(os.environ.get("O3D_PIPELINE", "16"))
 
 
 def parse():

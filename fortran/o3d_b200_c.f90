@@ -253,7 +253,7 @@ module o3d_b200_c
        type(c_ptr), value :: ptr
        integer(c_int) :: rc
      end function o3d_host_unregister
-     !> z chunks of the pipelined predict_velocity / correct_velocity (0 = off, default 8)
+     !> z chunks of the pipelined predict_velocity / correct_velocity (0 = off, default 16)
      function o3d_set_pipeline(chunks) bind(C, name="o3d_set_pipeline") result(rc)
        import :: c_int
        integer(c_int), value :: chunks

@@ -95,7 +95,7 @@ int o3d_host_unregister(void* ptr);
  * the reference, whose arrays never leave the host).  chunks >= 2: the host arrays are cut into
  * that many z chunks and the upload of chunk j+1, the kernels on chunk j and the download of
  * chunk j-1 overlap, so both PCIe directions are busy at once; results are bitwise those of the
- * unpipelined call.  0 = off.  Default: environment variable O3D_PIPELINE, else 8.  Grids with
+ * unpipelined call.  0 = off.  Default: environment variable O3D_PIPELINE, else 16.  Grids with
  * fewer than 8 planes per chunk use fewer chunks (or the plain path).  The overlap needs
  * page-locked host arrays (o3d_host_alloc / o3d_host_register); with pageable arrays the calls
  * are correct but the copies serialise. */

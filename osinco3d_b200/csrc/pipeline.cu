@@ -41,9 +41,9 @@ namespace {
 
 int g_pipe_setting = -1;  // -1: take O3D_PIPELINE from the environment at first use
 // Default number of chunks.  Measured end to end on the 256^3 TGV step (B200, PCIe Gen5, pinned
-// arrays; profiles/r1p_e2e_pipeline.jsonl): 86.8 ms unpipelined, 71.3 / 65.8 / 65.1 ms with
-// 4 / 8 / 16 chunks.
-constexpr int DEFAULT_CHUNKS = 8;
+// arrays; profiles/r1p_e2e_pipeline.jsonl, r1q_e2e_pipeline.jsonl): 86.8 ms unpipelined, 71.3 /
+// 65.8 / 65.1 ms with 4 / 8 / 16 chunks; flat (63.4 - 63.9 ms on a second box) from 12 to 32.
+constexpr int DEFAULT_CHUNKS = 16;
 
 constexpr int MAX_CHUNKS = 64;
 constexpr int MIN_PLANES = 8;  // per chunk: > stencil radius + mirror source planes

@@ -39,7 +39,7 @@ def set_sor_order(order):
 
 def set_pipeline(chunks):
     """z-chunk copy pipelining of predict_velocity / correct_velocity (0 = off; default
-    O3D_PIPELINE or 8); no counterpart in the reference.  Results are bitwise those of the
+    O3D_PIPELINE or 16); no counterpart in the reference.  Results are bitwise those of the
     unpipelined procedures."""
     check(lib().o3d_set_pipeline(int(chunks)))
 
