@@ -7,8 +7,13 @@
  * (src/Makefile:15) emits neither, and expressions below keep the Fortran evaluation order
  * (left-to-right for equal precedence, parentheses honoured).
  *
- * Parity status: PINNED against the reference's golden statistics files
- * (tests/test_oracle_golden.py) -- not against a compiled reference (none can be built here).
+ * Parity status: PINNED, two ways -- not against a compiled reference (none can be built here):
+ *  (1) the reference's golden statistics files (tests/test_oracle_golden.py);
+ *  (2) the reference SOURCE: every hot-path routine is translated statement by statement from
+ *      /root/reference/src into NumPy and executed (tests/golden/f90np.py,
+ *      make_hotpath_golden.py -> tests/golden/hotpath.npz); this file reproduces those vectors
+ *      bit for bit -- stencils, operators, predictor, the three SOR solvers with their iteration
+ *      counts and dynamic omega, correction, transeq (tests/test_oracle_reference_source.py).
  */
 #include "o3d_oracle.h"
 

@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""Golden vectors for the whole hot path, produced FROM THE REFERENCE SOURCE: every routine of
+SURVEY.md section 8(a) -- the 20 `derivation` routines, schemes(), divergence / rotational /
+calculate_Q_criterion, calculate_nu_t, predict_velocity, the three poisson_solver variants,
+correct_pression, correct_velocity, transeq, function_stats -- is read from /root/reference/src,
+translated statement by statement into NumPy by f90np.py (see its header for why this is
+operation-for-operation what gfortran computes) and executed on seeded inputs for three boundary
+configurations.  The reference cannot be compiled in the build image (no Fortran compiler); this
+is the closest thing to running it.
+
+    python tests/golden/make_hotpath_golden.py            # writes tests/golden/hotpath.npz
+    python tests/golden/make_hotpath_golden.py --check    # regenerate and compare with the file
+
+Run in the build container (where /root/reference exists).  Tests read only the .npz.
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import f90np  # noqa: E402
+
+REF = "/root/reference/src"
+OUT = os.path.join(HERE, "hotpath.npz")
+FILES = ["derivation.f90", "differential_operators.f90", "les_turbulence.f90", "poisson.f90",
+         "integration.f90", "functions.f90", "initialization.f90"]
+DER = ["derx_00", "derxp_11", "derxi_11", "dery_00", "deryp_11", "deryi_11", "derz_00", "derzp_11",
+       "derzi_11", "derxx_00", "derxxp_11", "derxxi_11", "deryy_00", "deryyp_11", "deryyi_11",
+       "derzz_00", "derzzp_11", "derzzi_11", "derz_2dsim", "derzz_2dsim"]
+NAMES = DER + ["contains_nan", "function_stats", "schemes", "divergence", "rotational",
+               "calculate_q_criterion", "calculate_nu_t", "predict_velocity",
+               "poisson_solver_0000", "poisson_solver_0011", "poisson_solver_111111",
+               "correct_pression", "correct_velocity", "transeq"]
+
+SHAPE = (9, 8, 10)                   # all extents different, >= 7
+D = (0.0371, 0.0412, 0.0293)
+# (nbcx, nbcy, nbcz, sim2d): the three Poisson variants + a 2-D run
+CONFIGS = {"ppp": (0, 0, 0, 0), "fff": (1, 1, 1, 0), "pfp": (0, 1, 0, 0), "pfp2d": (0, 1, 0, 1)}
+RE, SC, CS, DT = 1600.0, 0.7, 0.17, 1.3e-3
+
+
+def farr(a):
+    return np.asfortranarray(np.array(a, dtype=np.float64))
+
+
+def smooth(seed, shape=SHAPE):
+    """smooth, non-symmetric O(1) field"""
+    rng = np.random.default_rng(seed)
+    x = np.linspace(0.0, 1.0, shape[0])[:, None, None]
+    y = np.linspace(0.0, 1.0, shape[1])[None, :, None]
+    z = np.linspace(0.0, 1.0, shape[2])[None, None, :]
+    a = rng.uniform(0.5, 3.0, 6)
+    return farr(np.sin(a[0] * x + 0.3) * np.cos(a[1] * y - 0.2) * np.sin(a[2] * z + 0.7) +
+                0.5 * np.cos(a[3] * x * y) + 0.25 * np.sin(a[4] * y * z + a[5] * x))
+
+
+def ab_coefficients(dt):
+    """adt / bdt / cdt exactly as src/initialization.f90 assigns them (lines matched by pattern,
+    right-hand sides evaluated by the translator)"""
+    c = {"adt": [None] * 3, "bdt": [None] * 3, "cdt": [None] * 3}
+    for st in f90np.logical_lines(open(os.path.join(REF, "initialization.f90")).read()):
+        m = re.match(r"^([abc]dt)\((\d)\)\s*=\s*(.+)$", st)
+        if m:
+            c[m.group(1)][int(m.group(2)) - 1] = float(eval(f90np.expr_py(m.group(3), set()),
+                                                            {"dt": dt}))
+    assert all(v is not None for k in c for v in c[k]), c
+    return farr(c["adt"]), farr(c["bdt"]), farr(c["cdt"])
+
+
+def namespace():
+    ns = dict(f90np.RUNTIME)
+    ns.update(periodic=0, free_slip=1, huge=lambda x: np.finfo(np.float64).max)
+    text = open(os.path.join(REF, "initialization.f90")).read()
+    # the two named constants, from the source
+    for nm in ("PERIODIC", "FREE_SLIP"):
+        m = re.search(r"integer,\s*parameter\s*::\s*%s\s*=\s*(\d+)" % nm, text)
+        ns[nm.lower()] = int(m.group(1))
+    f90np.load([os.path.join(REF, f) for f in FILES], NAMES, ns)
+    return ns
+
+
+def generate():
+    ns = namespace()
+    out = {}
+    nx, ny, nz = SHAPE
+    dx, dy, dz = D
+    delta = (dx * dy * dz) ** (1.0 / 3.0)
+    adt, bdt, cdt = ab_coefficients(DT)
+    out["adt"], out["bdt"], out["cdt"] = adt, bdt, cdt
+    inp = {"ux": smooth(1), "uy": smooth(2), "uz": smooth(3), "pp": smooth(4),
+           "rhs": smooth(5) - np.mean(smooth(5)),
+           "phi": farr(np.clip(0.5 + 0.6 * smooth(6), 0.0, 1.0)), "nu_t_in": farr(1e-3 * np.abs(smooth(7)))}
+    rng = np.random.default_rng(77)
+    for c in "xyz":
+        inp["fu" + c] = farr(0.3 * rng.standard_normal(SHAPE + (3,)))
+    inp["fphi"] = farr(0.3 * rng.standard_normal(SHAPE + (3,)))
+    for k, v in inp.items():
+        out["in_" + k] = v
+    new = lambda: np.full(SHAPE, np.nan, order="F")  # noqa: E731
+
+    # ---- the 20 stencil routines (also on a minimum-size grid: overlapping boundary planes) ----
+    small = farr(np.random.default_rng(9).standard_normal((7, 7, 7)))
+    out["in_small"] = small
+    for name in DER:
+        d = {"x": dx, "y": dy, "z": dz}[name[3]]
+        for tag, f in (("", inp["pp"]), ("_small", small)):
+            df = np.full(f.shape, np.nan, order="F")
+            ns[name](df, f, d)
+            assert not np.isnan(df).any(), name
+            out["%s%s" % (name, tag)] = df
+    out["function_stats"] = farr(ns["function_stats"](inp["pp"], nx, ny, nz))
+
+    for cfg, (bx, by, bz, sim2d) in CONFIGS.items():
+        ns.update(nbcx1=bx, nbcxn=bx, nbcy1=by, nbcyn=by, nbcz1=bz, nbczn=bz, sim2d=sim2d)
+        ns["schemes"]()
+        P = cfg + "_"
+        ux, uy, uz = (inp[k].copy(order="F") for k in ("ux", "uy", "uz"))
+        for odd in (0, 1):
+            o = new()
+            ns["divergence"](o, ux, uy, uz, dx, dy, dz, nx, ny, nz, odd)
+            out[P + "divergence_odd%d" % odd] = o
+        r = [new() for _ in range(3)]
+        ns["rotational"](r[0], r[1], r[2], ux, uy, uz, dx, dy, dz, nx, ny, nz)
+        for c, a in zip("xyz", r):
+            out[P + "rot" + c] = a
+        q = new()
+        ns["calculate_q_criterion"](q, ux, uy, uz, dx, dy, dz, nx, ny, nz)
+        out[P + "q"] = q
+        nu = new()
+        ns["calculate_nu_t"](nu, ux, uy, uz, dx, dy, dz, CS, delta)
+        out[P + "nu_t"] = nu
+
+        # predict_velocity: the Euler / AB2 / AB3 start-up of an AB3 run, DNS and LES
+        for iles in (0, 1):
+            f = [inp["fu" + c].copy(order="F") for c in "xyz"]
+            for itime in (1, 2, 3):
+                up = [new() for _ in range(3)]
+                nut = inp["nu_t_in"].copy(order="F")
+                ns["predict_velocity"](up[0], up[1], up[2], ux, uy, uz, f[0], f[1], f[2], RE, adt,
+                                       bdt, cdt, itime, 3, dx, dy, dz, nx, ny, nz, iles, CS,
+                                       delta, nut)
+                for c, a in zip("xyz", up):
+                    out[P + "pred_les%d_it%d_u%s" % (iles, itime, c)] = a
+                out[P + "pred_les%d_it%d_nu_t" % (iles, itime)] = nut
+            for c, a in zip("xyz", f):
+                out[P + "pred_les%d_fu%s" % (iles, c)] = a
+        # itscheme = 2 history shift
+        f = [inp["fu" + c].copy(order="F") for c in "xyz"]
+        up = [new() for _ in range(3)]
+        nut = inp["nu_t_in"].copy(order="F")
+        ns["predict_velocity"](up[0], up[1], up[2], ux, uy, uz, f[0], f[1], f[2], RE, adt, bdt, cdt,
+                               4, 2, dx, dy, dz, nx, ny, nz, 0, CS, delta, nut)
+        out[P + "pred_sch2_ux"] = up[0]
+        out[P + "pred_sch2_fux"] = f[0]
+
+        if sim2d == 0:
+            # the bound poisson_solver: (a) kmax sweeps without convergence (loop runs out: iter =
+            # kmax + 1), (b) dynamic omega until one of the two exits fires
+            for tag, (omega, eps, kmax, idyn) in (("fixed", (1.6, 1e-30, 12, 0)),
+                                                  ("dyn", (1.9, 2e-3, 400, 1))):
+                pp = inp["pp"].copy(order="F")
+                loc = ns["poisson_solver"](pp, inp["rhs"], dx, dy, dz, nx, ny, nz, omega, eps,
+                                           kmax, idyn)
+                out[P + "sor_%s_pp" % tag] = pp
+                out[P + "sor_%s_scalars" % tag] = farr([loc["iter"], loc["omega"], loc["dmax"]])
+            # correct_pression on u* = u (divergence / dt -> rhs -> SOR)
+            pp = inp["pp"].copy(order="F")
+            loc = ns["correct_pression"](pp, ux, uy, uz, dx, dy, dz, nx, ny, nz, DT, 1.7, 1e-4, 300,
+                                         1, 0)
+            out[P + "pression_pp"] = pp
+            out[P + "pression_omega"] = farr([loc["omega"]])
+
+        u = [new() for _ in range(3)]
+        ns["correct_velocity"](u[0], u[1], u[2], ux, uy, uz, inp["pp"], DT, dx, dy, dz, nx, ny, nz)
+        for c, a in zip("xyz", u):
+            out[P + "corr_u" + c] = a
+
+        # transeq: three steps of an AB3 run with clipping at both ends, DNS and LES diffusivity
+        for iles in (0, 1):
+            phi = inp["phi"].copy(order="F")
+            fphi = inp["fphi"].copy(order="F")
+            src = farr(np.zeros(SHAPE))
+            big = farr([40.0 * v for v in adt])      # large steps: the clip / redistribution acts
+            for itime in (1, 2, 3):
+                ns["transeq"](phi, ux, uy, uz, src, fphi, RE, SC, big, bdt, cdt, itime, 3, dx, dy,
+                              dz, nx, ny, nz, iles, out[P + "nu_t"])
+                out[P + "transeq_les%d_it%d_phi" % (iles, itime)] = phi.copy(order="F")
+            out[P + "transeq_les%d_fphi" % iles] = fphi
+    # the divergence guard: stop on NaN or > 1000
+    bad = inp["ux"].copy(order="F")
+    bad[3, 4, 5] = 2000.0
+    try:
+        ns["correct_velocity"](new(), new(), new(), bad, inp["uy"], inp["uz"], farr(np.zeros(SHAPE)),
+                               DT, dx, dy, dz, nx, ny, nz)
+        out["corr_guard_stops"] = farr([0.0])
+    except f90np.FortranStop:
+        out["corr_guard_stops"] = farr([1.0])
+    out["params"] = farr([RE, SC, CS, DT, delta, dx, dy, dz])
+    return out
+
+
+def main():
+    new = generate()
+    if "--check" in sys.argv:
+        old = np.load(OUT)
+        bad = [k for k in new if k not in old or not np.array_equal(old[k], new[k], equal_nan=True)]
+        print("entries: %d, mismatching: %s" % (len(new), bad))
+        sys.exit(1 if bad else 0)
+    np.savez_compressed(OUT, **new)
+    print("wrote %s: %d arrays, %d bytes" % (OUT, len(new), os.path.getsize(OUT)))
+
+
+if __name__ == "__main__":
+    main()

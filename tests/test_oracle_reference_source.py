@@ -1,0 +1,152 @@
+"""The oracle against the reference SOURCE.  tests/golden/hotpath.npz holds the outputs of every
+hot-path routine of SURVEY.md 8(a), obtained by translating the reference's Fortran statements
+mechanically into NumPy and executing them (tests/golden/make_hotpath_golden.py + f90np.py; the
+reference cannot be compiled in the build image).  The oracle -- the C restatement every GPU
+parity test compares against -- must reproduce them BIT FOR BIT: the 20 stencil routines, the
+procedure-pointer binding of schemes(), divergence / curl / Q, nu_t, predict_velocity with its
+history shifts, the three lexicographic SOR solvers (iterates, exit iteration, dynamic omega),
+correct_pression, correct_velocity and its guard, transeq with clipping and redistribution.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath.npz"))
+SHAPE = GOLD["in_ux"].shape
+RE, SC, CS, DT, DELTA, DX, DY, DZ = [float(v) for v in GOLD["params"]]
+CONFIGS = {"ppp": ((0, 0, 0), 0), "fff": ((1, 1, 1), 0), "pfp": ((0, 1, 0), 0),
+           "pfp2d": ((0, 1, 0), 1)}
+DER = ["derx_00", "derxp_11", "derxi_11", "dery_00", "deryp_11", "deryi_11", "derz_00", "derzp_11",
+       "derzi_11", "derxx_00", "derxxp_11", "derxxi_11", "deryy_00", "deryyp_11", "deryyi_11",
+       "derzz_00", "derzzp_11", "derzzi_11", "derz_2dsim", "derzz_2dsim"]
+
+
+def inp(name):
+    return np.asfortranarray(GOLD["in_" + name]).copy(order="F")
+
+
+def same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def closure_of(name):
+    axis = "xyz".index(name[3])
+    order = 2 if name[4] == name[3] else 1
+    if name.endswith("2dsim"):
+        return axis, order, 3
+    if name.endswith("_00"):
+        return axis, order, 0
+    return axis, order, 1 if "p_11" in name else 2
+
+
+@pytest.mark.parametrize("name", DER)
+def test_stencil_routine(O, name):
+    """src/derivation.f90: all 18 + 2 routines, explicit boundary planes included"""
+    axis, order, closure = closure_of(name)
+    d = (DX, DY, DZ)[axis]
+    for tag, f in (("", inp("pp")), ("_small", inp("small"))):
+        assert same(O.der(axis, order, closure, f, d), GOLD[name + tag]), (name, tag)
+
+
+def test_ab_coefficients_and_function_stats(O):
+    """src/initialization.f90:194-202, src/functions.f90:27-63"""
+    a, b, c = O.ab_coefficients(DT)
+    assert same(a, GOLD["adt"]) and same(b, GOLD["bdt"]) and same(c, GOLD["cdt"])
+    assert same(O.function_stats(inp("pp")), GOLD["function_stats"])
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_operators(O, cfg):
+    """src/differential_operators.f90:7-108, src/les_turbulence.f90:10-97 under the pointers
+    schemes() binds (src/initialization.f90:226-281)"""
+    bc, sim2d = CONFIGS[cfg]
+    g = O.grid(*SHAPE, DX, DY, DZ, bc, sim2d)
+    u = [inp(k) for k in ("ux", "uy", "uz")]
+    for odd in (0, 1):
+        assert same(O.divergence(g, *u, odd), GOLD["%s_divergence_odd%d" % (cfg, odd)]), odd
+    for c, a in zip("xyz", O.rotational(g, *u)):
+        assert same(a, GOLD["%s_rot%s" % (cfg, c)]), c
+    assert same(O.q_criterion(g, *u), GOLD[cfg + "_q"])
+    assert same(O.calculate_nu_t(g, *u, CS, DELTA), GOLD[cfg + "_nu_t"])
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_predict_velocity(O, cfg):
+    """src/integration.f90:14-197: Euler -> AB2 -> AB3 start-up, DNS and LES, history shifts of
+    itscheme 3 and 2"""
+    bc, sim2d = CONFIGS[cfg]
+    g = O.grid(*SHAPE, DX, DY, DZ, bc, sim2d)
+    u = [inp(k) for k in ("ux", "uy", "uz")]
+    for iles in (0, 1):
+        f = [inp("fu" + c) for c in "xyz"]
+        for itime in (1, 2, 3):
+            got = O.predict_velocity(g, *u, *f, RE, DT, itime, 3, iles, CS, DELTA)
+            for c, a in zip("xyz", got[:3]):
+                assert same(a, GOLD["%s_pred_les%d_it%d_u%s" % (cfg, iles, itime, c)]), (iles, itime, c)
+            assert same(got[3], GOLD["%s_pred_les%d_it%d_nu_t" % (cfg, iles, itime)]), (iles, itime)
+        for c, a in zip("xyz", f):
+            assert same(a, GOLD["%s_pred_les%d_fu%s" % (cfg, iles, c)]), (iles, c)
+    f = [inp("fu" + c) for c in "xyz"]
+    got = O.predict_velocity(g, *u, *f, RE, DT, 4, 2, 0, CS, DELTA)
+    assert same(got[0], GOLD[cfg + "_pred_sch2_ux"]) and same(f[0], GOLD[cfg + "_pred_sch2_fux"])
+
+
+@pytest.mark.parametrize("cfg", ["ppp", "fff", "pfp"])
+def test_sor_solvers_and_correct_pression(O, cfg):
+    """src/poisson.f90:6,132,257 (the variant schemes() binds): iterates, the value of `iter`
+    after the loop (kmax + 1 when it runs out), the dynamic relaxation factor;
+    src/integration.f90:199-255"""
+    bc, _ = CONFIGS[cfg]
+    g = O.grid(*SHAPE, DX, DY, DZ, bc)
+    for tag, (omega, eps, kmax, idyn) in (("fixed", (1.6, 1e-30, 12, 0)),
+                                          ("dyn", (1.9, 2e-3, 400, 1))):
+        pp = inp("pp")
+        it, om, dmax = O.poisson_solver(g, pp, inp("rhs"), omega, eps, kmax, idyn)
+        ref = GOLD["%s_sor_%s_scalars" % (cfg, tag)]
+        assert (it, om, dmax) == (int(ref[0]), float(ref[1]), float(ref[2])), (tag, it, om, dmax, ref)
+        assert same(pp, GOLD["%s_sor_%s_pp" % (cfg, tag)]), tag
+    assert int(GOLD[cfg + "_sor_fixed_scalars"][0]) == 13          # ran out: kmax + 1
+    assert 1 < int(GOLD[cfg + "_sor_dyn_scalars"][0]) <= 400       # one of the exits fired
+    pp = inp("pp")
+    it, om, dmax, rhs = O.correct_pression(g, pp, inp("ux"), inp("uy"), inp("uz"), DT, 1.7, 1e-4,
+                                           300, 1)
+    assert same(pp, GOLD[cfg + "_pression_pp"])
+    assert om == float(GOLD[cfg + "_pression_omega"][0])
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_correct_velocity_and_transeq(O, cfg):
+    """src/integration.f90:257-330 and :332-468"""
+    bc, sim2d = CONFIGS[cfg]
+    g = O.grid(*SHAPE, DX, DY, DZ, bc, sim2d)
+    u = [inp(k) for k in ("ux", "uy", "uz")]
+    got = O.correct_velocity(g, *u, inp("pp"), DT)
+    for c, a in zip("xyz", got[:3]):
+        assert same(a, GOLD["%s_corr_u%s" % (cfg, c)]), c
+    assert got[3] == 0
+    v3 = lambda v: (C.c_double * 3)(*[float(x) for x in v])  # noqa: E731
+    big = [40.0 * v for v in GOLD["adt"]]
+    for iles in (0, 1):
+        phi, fphi = inp("phi"), inp("fphi")
+        nu_t = np.asfortranarray(GOLD[cfg + "_nu_t"]).copy(order="F")
+        for itime in (1, 2, 3):
+            rc = O.lib().orc_transeq(C.byref(g), O._p(phi), O._p(u[0]), O._p(u[1]), O._p(u[2]), None,
+                                     O._p(fphi), C.c_double(RE), C.c_double(SC), v3(big),
+                                     v3(GOLD["bdt"]), v3(GOLD["cdt"]), itime, 3, iles, O._p(nu_t))
+            assert rc == 0
+            assert same(phi, GOLD["%s_transeq_les%d_it%d_phi" % (cfg, iles, itime)]), (iles, itime)
+        assert same(fphi, GOLD["%s_transeq_les%d_fphi" % (cfg, iles)]), iles
+        # the steps were large enough for the clip and the redistribution to act
+        assert phi.min() == 0.0 or phi.max() == 1.0
+
+
+def test_divergence_guard(O):
+    """src/integration.f90:309-325: the reference stops on NaN or a value > 1000"""
+    assert GOLD["corr_guard_stops"][0] == 1.0
+    g = O.grid(*SHAPE, DX, DY, DZ, (1, 1, 1))
+    bad = inp("ux")
+    bad[3, 4, 5] = 2000.0
+    assert O.correct_velocity(g, bad, inp("uy"), inp("uz"), np.asfortranarray(np.zeros(SHAPE)),
+                              DT)[3] != 0
