@@ -197,10 +197,13 @@ class Parser:
         if self.peek()[1] == "**":
             self.take()
             k, v = self.peek()
-            if k != "num" or not v.isdigit():
-                raise SyntaxError("only small integer literal exponents are supported: %r" % (self.t,))
+            # integer literal, or a real literal with an integer value (x**2.d0: gfortran folds
+            # pow(x, 2.0) to x*x, which is also what a correctly rounded pow returns)
+            ev = float(re.sub(r"[dD]", "e", v)) if k == "num" else None
+            if ev is None or ev != int(ev) or not 1 <= int(ev) <= 4:
+                raise SyntaxError("only small integer-valued literal exponents are supported: %r" % (self.t,))
             self.take()
-            a = "_ipow(%s, %s)" % (a, v)
+            a = "_ipow(%s, %d)" % (a, int(ev))
         return a
 
     def args(self):
@@ -259,9 +262,17 @@ class Parser:
                 return "%s[%s]" % (name, index(args))
             if name == "huge":      # huge(x): a constant of x's kind (all reals here are binary64)
                 return repr(float(np.finfo(np.float64).max))
-            if name == "real":      # real(x, kind=8)
+            if name == "tiny":
+                return repr(float(np.finfo(np.float64).tiny))
+            if name == "real":      # real(x, kind=8) -> binary64; real(x) -> default real = binary32
                 pos = [a for kd, a in args if kd == "expr"]
-                return "float(%s)" % pos[0]
+                kinds = [a for kd, a in args if kd == "kw"] + [("kind", p2) for p2 in pos[1:]]
+                if kinds:
+                    assert kinds[0][1].strip("()") == "8", kinds
+                    return "float(%s)" % pos[0]
+                return "float(np.float32(%s))" % pos[0]
+            if name == "int":
+                return "int(%s)" % args[0][1]
             fn = INTRINSICS.get(name, name)
             parts = []
             for kd, a in args:

@@ -26,14 +26,16 @@ import f90np  # noqa: E402
 REF = "/root/reference/src"
 OUT = os.path.join(HERE, "hotpath.npz")
 FILES = ["derivation.f90", "differential_operators.f90", "les_turbulence.f90", "poisson.f90",
-         "integration.f90", "functions.f90", "initialization.f90"]
+         "integration.f90", "functions.f90", "initialization.f90", "utils.f90"]
 DER = ["derx_00", "derxp_11", "derxi_11", "dery_00", "deryp_11", "deryi_11", "derz_00", "derzp_11",
        "derzi_11", "derxx_00", "derxxp_11", "derxxi_11", "deryy_00", "deryyp_11", "deryyi_11",
        "derzz_00", "derzzp_11", "derzzi_11", "derz_2dsim", "derzz_2dsim"]
 NAMES = DER + ["contains_nan", "function_stats", "schemes", "divergence", "rotational",
                "calculate_q_criterion", "calculate_nu_t", "predict_velocity",
                "poisson_solver_0000", "poisson_solver_0011", "poisson_solver_111111",
-               "correct_pression", "correct_velocity", "transeq"]
+               "correct_pression", "correct_velocity", "transeq",
+               "average_3d_array", "statistics_calc", "calculate_residuals", "old_values",
+               "compute_cfl"]
 
 SHAPE = (9, 8, 10)                   # all extents different, >= 7
 D = (0.0371, 0.0412, 0.0293)
@@ -78,6 +80,10 @@ def namespace():
     for nm in ("PERIODIC", "FREE_SLIP"):
         m = re.search(r"integer,\s*parameter\s*::\s*%s\s*=\s*(\d+)" % nm, text)
         ns[nm.lower()] = int(m.group(1))
+    # the three output routines the diagnostics end in: capture what they are handed
+    ns["_captured"] = {}
+    for nm in ("write_statistics", "print_residuals", "save_residu"):
+        ns[nm] = (lambda key: (lambda *a: ns["_captured"].__setitem__(key, [float(v) for v in a])))(nm)
     f90np.load([os.path.join(REF, f) for f in FILES], NAMES, ns)
     return ns
 
@@ -189,6 +195,23 @@ def generate():
                               dz, nx, ny, nz, iles, out[P + "nu_t"])
                 out[P + "transeq_les%d_it%d_phi" % (iles, itime)] = phi.copy(order="F")
             out[P + "transeq_les%d_fphi" % iles] = fphi
+        # statistics_calc: the 17 stats.dat columns as handed to write_statistics
+        ns["statistics_calc"](ux, uy, uz, nx, ny, nz, dx, dy, dz, RE, 0.25)
+        out[P + "statistics"] = farr(ns["_captured"]["write_statistics"])
+
+    # per-step driver diagnostics: residuals, old_values, CFL
+    old = [smooth(11), smooth(12), smooth(13)]
+    ns["calculate_residuals"](inp["ux"], inp["uy"], inp["uz"], old[0], old[1], old[2], DT, 3.1, 0.9,
+                              nx, ny, nz, 7)
+    for c, a in zip("uvw", old):
+        out["in_old_" + c] = a
+    out["residuals"] = farr(ns["_captured"]["print_residuals"])
+    out["residuals_saved"] = farr(ns["_captured"]["save_residu"])
+    o3 = [new() for _ in range(3)]
+    ns["old_values"](inp["ux"], inp["uy"], inp["uz"], o3[0], o3[1], o3[2], nx, ny, nz)
+    assert all(np.array_equal(a, inp[k]) for a, k in zip(o3, ("ux", "uy", "uz")))
+    loc = ns["compute_cfl"](0.0, 0.0, 0.0, inp["ux"], inp["uy"], inp["uz"], dx, dy, dz, DT)
+    out["cfl"] = farr([loc["cflx"], loc["cfly"], loc["cflz"]])
     # the divergence guard: stop on NaN or > 1000
     bad = inp["ux"].copy(order="F")
     bad[3, 4, 5] = 2000.0

@@ -150,3 +150,29 @@ def test_divergence_guard(O):
     bad[3, 4, 5] = 2000.0
     assert O.correct_velocity(g, bad, inp("uy"), inp("uz"), np.asfortranarray(np.zeros(SHAPE)),
                               DT)[3] != 0
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_statistics_calc(O, cfg):
+    """src/utils.f90:243-375: the 17 stats.dat columns as handed to write_statistics, including
+    average_3d_array's i-outer / k-inner summation order (src/functions.f90:123-155)"""
+    bc, sim2d = CONFIGS[cfg]
+    g = O.grid(*SHAPE, DX, DY, DZ, bc, sim2d)
+    got = O.statistics_calc(g, inp("ux"), inp("uy"), inp("uz"), RE, 0.25)
+    ref = GOLD[cfg + "_statistics"]
+    assert got.shape == ref.shape == (17,)
+    assert same(got, ref), np.max(np.abs(got - ref) / np.abs(ref))
+
+
+def test_residuals_and_cfl(O):
+    """src/utils.f90:93-160 (with its single-precision real(nx*ny*nz) and the last-match arg-max
+    scan), :165-176, :178-205"""
+    got = O.calculate_residuals(inp("ux"), inp("uy"), inp("uz"), inp("old_u"), inp("old_v"),
+                                inp("old_w"), DT, 3.1, 0.9)
+    r = GOLD["residuals"]     # print_residuals(res_u,res_v,res_w, aa,ia,ja,ka, bb,ib,jb,kb, cc,ic,jc,kc)
+    ref = np.array([r[0], r[1], r[2], r[3], r[7], r[11], r[4], r[5], r[6], r[8], r[9], r[10],
+                    r[12], r[13], r[14]])
+    assert same(got, ref), (got, ref)
+    assert same(GOLD["residuals_saved"], [7.0, r[0], r[1], r[2]])
+    cfl = [np.max(np.abs(inp(k))) * DT / d for k, d in (("ux", DX), ("uy", DY), ("uz", DZ))]
+    assert same(GOLD["cfl"], cfl)
