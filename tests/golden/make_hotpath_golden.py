@@ -199,6 +199,38 @@ def generate():
         ns["statistics_calc"](ux, uy, uz, nx, ny, nz, dx, dy, dz, RE, 0.25)
         out[P + "statistics"] = farr(ns["_captured"]["write_statistics"])
 
+    # ---- whole time steps: the call sequence of src/osinco3d_main.f90:105-115, four steps from
+    # rest histories (Euler -> AB2 -> AB3 -> AB3), SOR with the omega carried from step to step
+    for cfg, iles, nscr, idyn in (("fff", 1, 1, 1), ("pfp", 0, 1, 0), ("ppp", 1, 0, 1)):
+        bx, by, bz, sim2d = CONFIGS[cfg]
+        ns.update(nbcx1=bx, nbcxn=bx, nbcy1=by, nbcyn=by, nbcz1=bz, nbczn=bz, sim2d=sim2d)
+        ns["schemes"]()
+        ux, uy, uz, pp, phi = (inp[k].copy(order="F") for k in ("ux", "uy", "uz", "pp", "phi"))
+        ux *= 0.2
+        uy *= 0.2
+        uz *= 0.2
+        fu = [farr(np.zeros(SHAPE + (3,))) for _ in range(3)]
+        fphi = farr(np.zeros(SHAPE + (3,)))
+        nut = farr(np.zeros(SHAPE))
+        src = farr(np.zeros(SHAPE))
+        up = [new() for _ in range(3)]
+        omega, eps, kmax = 1.8, 1e-4, 300
+        log = []
+        for itime in (1, 2, 3, 4):
+            ns["predict_velocity"](up[0], up[1], up[2], ux, uy, uz, fu[0], fu[1], fu[2], RE, adt,
+                                   bdt, cdt, itime, 3, dx, dy, dz, nx, ny, nz, iles, CS, delta, nut)
+            loc = ns["correct_pression"](pp, up[0], up[1], up[2], dx, dy, dz, nx, ny, nz, DT, omega,
+                                         eps, kmax, idyn, 0)
+            omega = loc["omega"]
+            ns["correct_velocity"](ux, uy, uz, up[0], up[1], up[2], pp, DT, dx, dy, dz, nx, ny, nz)
+            if nscr == 1:
+                ns["transeq"](phi, ux, uy, uz, src, fphi, RE, SC, adt, bdt, cdt, itime, 3, dx, dy,
+                              dz, nx, ny, nz, iles, nut)
+            log.append(omega)
+        for k, a in (("ux", ux), ("uy", uy), ("uz", uz), ("pp", pp), ("phi", phi), ("nu_t", nut)):
+            out["steps_%s_%s" % (cfg, k)] = a
+        out["steps_%s_omega" % cfg] = farr(log)
+
     # per-step driver diagnostics: residuals, old_values, CFL
     old = [smooth(11), smooth(12), smooth(13)]
     ns["calculate_residuals"](inp["ux"], inp["uy"], inp["uz"], old[0], old[1], old[2], DT, 3.1, 0.9,

@@ -176,3 +176,25 @@ def test_residuals_and_cfl(O):
     assert same(GOLD["residuals_saved"], [7.0, r[0], r[1], r[2]])
     cfl = [np.max(np.abs(inp(k))) * DT / d for k, d in (("ux", DX), ("uy", DY), ("uz", DZ))]
     assert same(GOLD["cfl"], cfl)
+
+
+@pytest.mark.parametrize("cfg,iles,nscr,idyn", [("fff", 1, 1, 1), ("pfp", 0, 1, 0), ("ppp", 1, 0, 1)])
+def test_whole_time_steps(O, cfg, iles, nscr, idyn):
+    """four steps of the call sequence of src/osinco3d_main.f90:105-115 (Euler -> AB2 -> AB3 ->
+    AB3 from rest histories, SOR with omega carried from step to step, scalar transport) through
+    the oracle's main-loop restatement (orc_sim_step)"""
+    bc, _ = CONFIGS[cfg]
+    g = O.grid(*SHAPE, DX, DY, DZ, bc)
+    sim = O.Sim(g, re=RE, dt=DT, itscheme=3, iles=iles, cs=CS, delta=DELTA, nscr=nscr, sc=SC,
+                omega=1.8, eps=1e-4, kmax=300, idyn=idyn)
+    sim.set(ux=0.2 * inp("ux"), uy=0.2 * inp("uy"), uz=0.2 * inp("uz"), pp=inp("pp"))
+    if nscr:
+        sim.set(phi=inp("phi"))
+    omegas = []
+    for _ in range(4):
+        sim.step()
+        omegas.append(sim.omega)
+    assert same(omegas, GOLD["steps_%s_omega" % cfg]), (omegas, GOLD["steps_%s_omega" % cfg])
+    for k in ("ux", "uy", "uz", "pp") + (("phi",) if nscr else ()):
+        assert same(sim.field(k), GOLD["steps_%s_%s" % (cfg, k)]), k
+    sim.close()
