@@ -71,8 +71,16 @@ def _mod(a, b):
     return a % b
 
 
-def _size(a, d):
-    return a.shape[d - 1]
+def _size(a, d=None):
+    return a.size if d is None else a.shape[d - 1]
+
+
+def _elemental(mfn, nfn):
+    # scalars go through libm (math.*), which is what gfortran calls for a scalar argument;
+    # numpy's vectorised loops may differ from libm in the last bit
+    def fn(x):
+        return nfn(x) if isinstance(x, np.ndarray) and x.ndim > 0 else mfn(float(x))
+    return fn
 
 
 def _copyback(fn, ret, pos, old):
@@ -85,12 +93,18 @@ def _copyback(fn, ret, pos, old):
     return old if isinstance(v, np.ndarray) and v.ndim > 0 else v
 
 
-RUNTIME = {"np": np, "_ipow": _ipow, "_seqsum": _seqsum, "_fmax": _fmax, "_fmin": _fmin,
+import math  # noqa: E402
+
+RUNTIME = {"_sin": _elemental(math.sin, np.sin), "_cos": _elemental(math.cos, np.cos),
+           "_tanh": _elemental(math.tanh, np.tanh), "_log": _elemental(math.log, np.log),
+           "_exp": _elemental(math.exp, np.exp), "_acos": _elemental(math.acos, np.arccos),
+           "np": np, "_ipow": _ipow, "_seqsum": _seqsum, "_fmax": _fmax, "_fmin": _fmin,
            "_mod": _mod, "_size": _size, "_copyback": _copyback, "FortranStop": FortranStop}
 
 INTRINSICS = {"abs": "np.abs", "sqrt": "np.sqrt", "max": "_fmax", "min": "_fmin", "mod": "_mod",
               "sum": "_seqsum", "maxval": "np.max", "minval": "np.min", "size": "_size",
-              "isnan": "np.isnan", "dble": "float"}
+              "isnan": "np.isnan", "dble": "float", "sin": "_sin", "cos": "_cos", "tanh": "_tanh",
+              "log": "_log", "exp": "_exp", "acos": "_acos"}
 
 # ------------------------------------------------------------------------------------------
 # lexer / expression parser
@@ -414,9 +428,11 @@ def routines(text):
     return out
 
 
-def translate(r, known_scalars_out=()):
-    """Routine -> Python source of `def name(dummies)` that returns its locals()"""
-    arrays, alloc, params = set(), [], []
+def translate(r, module_arrays=()):
+    """Routine -> Python source of `def name(dummies)` that returns its locals().
+    module_arrays: names of module-level arrays the routine reads through `use` (globals of the
+    namespace the translation is executed in)"""
+    arrays, alloc, params = set(a.lower() for a in module_arrays), [], []
     for st in r.body:                         # pass 1: declarations
         if not DECL.match(st) or "::" not in st:
             continue
@@ -623,7 +639,7 @@ def translate(r, known_scalars_out=()):
     return "\n".join(out)
 
 
-def load(paths, names, namespace):
+def load(paths, names, namespace, module_arrays=()):
     """translate the routines `names` found in the Fortran files `paths` and define them in
     `namespace` (which must already hold RUNTIME); returns {name: python source}"""
     found = {}
@@ -632,7 +648,7 @@ def load(paths, names, namespace):
     src = {}
     for nm in names:
         r = found[nm.lower()]
-        code = translate(r)
+        code = translate(r, module_arrays)
         exec(compile(code, "<f90np:%s>" % r.name, "exec"), namespace)
         fn = namespace[r.name]
         fn.__dummies__ = list(r.dummies)

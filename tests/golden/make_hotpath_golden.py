@@ -26,7 +26,8 @@ import f90np  # noqa: E402
 REF = "/root/reference/src"
 OUT = os.path.join(HERE, "hotpath.npz")
 FILES = ["derivation.f90", "differential_operators.f90", "les_turbulence.f90", "poisson.f90",
-         "integration.f90", "functions.f90", "initialization.f90", "utils.f90"]
+         "integration.f90", "functions.f90", "initialization.f90", "utils.f90",
+         "initial_conditions.f90"]
 DER = ["derx_00", "derxp_11", "derxi_11", "dery_00", "deryp_11", "deryi_11", "derz_00", "derzp_11",
        "derzi_11", "derxx_00", "derxxp_11", "derxxi_11", "deryy_00", "deryyp_11", "deryyi_11",
        "derzz_00", "derzzp_11", "derzzi_11", "derz_2dsim", "derzz_2dsim"]
@@ -35,7 +36,11 @@ NAMES = DER + ["contains_nan", "function_stats", "schemes", "divergence", "rotat
                "poisson_solver_0000", "poisson_solver_0011", "poisson_solver_111111",
                "correct_pression", "correct_velocity", "transeq",
                "average_3d_array", "statistics_calc", "calculate_residuals", "old_values",
-               "compute_cfl"]
+               "compute_cfl",
+               "compute_velocity_magnitude",
+               "initialize_taylor_green_vortex", "initialize_mixing_layer",
+               "initialize_coplanar_jet", "dery1d", "calcul_u_base", "normalize1d",
+               "add_oscillations_init"]
 
 SHAPE = (9, 8, 10)                   # all extents different, >= 7
 D = (0.0371, 0.0412, 0.0293)
@@ -84,7 +89,9 @@ def namespace():
     ns["_captured"] = {}
     for nm in ("write_statistics", "print_residuals", "save_residu"):
         ns[nm] = (lambda key: (lambda *a: ns["_captured"].__setitem__(key, [float(v) for v in a])))(nm)
-    f90np.load([os.path.join(REF, f) for f in FILES], NAMES, ns)
+    # x, y, z are module-level arrays of `initialization` for the routines that do not get them
+    # as dummy arguments (add_oscillations_init)
+    f90np.load([os.path.join(REF, f) for f in FILES], NAMES, ns, module_arrays=("x", "y", "z"))
     return ns
 
 
@@ -230,6 +237,34 @@ def generate():
         for k, a in (("ux", ux), ("uy", uy), ("uz", uz), ("pp", pp), ("phi", phi), ("nu_t", nut)):
             out["steps_%s_%s" % (cfg, k)] = a
         out["steps_%s_omega" % cfg] = farr(log)
+
+    # ---- initial conditions (inputs of the benchmarks / examples, SURVEY 8c "inputs"):
+    # src/initial_conditions.f90:103-174 (TGV + scalar blob), :329-394 (mixing layer), :244-327
+    # (coplanar jet), :554-629 + src/utils.f90:9-45 + src/derivation.f90:950-992 (ici = 1
+    # oscillations); coordinates as src/initialization.f90:211-219
+    u0, l0 = 1.3, 0.8
+    origin = (-0.4, -0.15, 0.2)
+    xs = [farr([o + float(i) * d for i in range(n)]) for o, d, n in zip(origin, D, SHAPE)]
+    out["init_params"] = farr([u0, l0, origin[0], origin[1], origin[2]])
+    ns.update(u0=u0, ici=0, delta=delta, x=xs[0], y=xs[1], z=xs[2],
+              xlx=D[0] * (nx - 1))
+    for nm, fn, ratio in (("tgv", "initialize_taylor_green_vortex", 1.0),
+                          ("mixing", "initialize_mixing_layer", 0.0),
+                          ("mixing_r", "initialize_mixing_layer", 0.25),
+                          ("jet", "initialize_coplanar_jet", 3.0)):
+        f5 = [new() for _ in range(5)]
+        ns[fn](f5[0], f5[1], f5[2], f5[3], f5[4], xs[0], xs[1], xs[2], nx, ny, nz, l0, ratio, 1)
+        for k, a in zip(("ux", "uy", "uz", "pp", "phi"), f5):
+            out["init_%s_%s" % (nm, k)] = a
+        if nm in ("mixing", "jet"):
+            # typesim: 3 = mixing layer in the reference's numbering of the oscillation branch,
+            # 0 = the generic branch (coplanar jet)
+            for typesim in (3, 0):
+                o = [a.copy(order="F") for a in f5[:3]]
+                ns["add_oscillations_init"](o[0], o[1], o[2], nx, ny, nz, dy, u0, 0.05, 0.03, 0.02,
+                                            typesim)
+                for k, a in zip(("ux", "uy", "uz"), o):
+                    out["init_%s_osc%d_%s" % (nm, typesim, k)] = a
 
     # per-step driver diagnostics: residuals, old_values, CFL
     old = [smooth(11), smooth(12), smooth(13)]

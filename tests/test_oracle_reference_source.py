@@ -198,3 +198,36 @@ def test_whole_time_steps(O, cfg, iles, nscr, idyn):
     for k in ("ux", "uy", "uz", "pp") + (("phi",) if nscr else ()):
         assert same(sim.field(k), GOLD["steps_%s_%s" % (cfg, k)]), k
     sim.close()
+
+
+def test_initial_conditions(O):
+    """src/initial_conditions.f90:103-174, :244-327, :329-394 with the coordinates of
+    src/initialization.f90:211-219 -- the inputs of the TGV / mixing-layer / coplanar-jet
+    benchmarks and example tests"""
+    u0, l0, x0, y0, z0 = [float(v) for v in GOLD["init_params"]]
+    g = O.grid(*SHAPE, DX, DY, DZ, (1, 1, 1))
+    cases = {"tgv": O.init_tgv(g, nscr=1, delta=DELTA, u0=u0, l0=l0, ratio=1.0, origin=(x0, y0, z0)),
+             "mixing": O.init_mixing_layer(g, nscr=1, u0=u0, l0=l0, ratio=0.0, origin=(x0, y0, z0)),
+             "mixing_r": O.init_mixing_layer(g, nscr=1, u0=u0, l0=l0, ratio=0.25,
+                                             origin=(x0, y0, z0)),
+             "jet": O.init_coplanar_jet(g, nscr=1, u0=u0, l0=l0, ratio=3.0, origin=(x0, y0, z0))}
+    for nm, fields in cases.items():
+        for k, a in zip(("ux", "uy", "uz", "pp", "phi"), fields):
+            assert same(a, GOLD["init_%s_%s" % (nm, k)]), (nm, k, np.max(np.abs(a - GOLD["init_%s_%s" % (nm, k)])))
+
+
+@pytest.mark.parametrize("nm", ["mixing", "jet"])
+@pytest.mark.parametrize("typesim", [3, 0])
+def test_deterministic_oscillations(O, nm, typesim):
+    """src/initial_conditions.f90:554-629 + src/utils.f90:9-45 + src/derivation.f90:950-992
+    (ici = 1).  The oracle's version is vectorised NumPy (np.sin / np.cos instead of libm), so
+    this one is compared to 4 ulp of the velocity scale instead of bitwise."""
+    u0, l0, x0, y0, z0 = [float(v) for v in GOLD["init_params"]]
+    g = O.grid(*SHAPE, DX, DY, DZ, (1, 1, 1))
+    base = [np.asfortranarray(GOLD["init_%s_%s" % (nm, k)]).copy(order="F") for k in ("ux", "uy", "uz")]
+    got = O.add_oscillations_init(g, *base, u0, (0.05, 0.03, 0.02), typesim, x0,
+                                  DX * (SHAPE[0] - 1))
+    for k, a in zip(("ux", "uy", "uz"), got):
+        ref = GOLD["init_%s_osc%d_%s" % (nm, typesim, k)]
+        assert np.max(np.abs(a - ref)) <= 4 * np.finfo(float).eps * u0, (k, np.max(np.abs(a - ref)))
+    assert np.max(np.abs(got[0] - base[0])) > 1e-3       # the perturbation is really there
