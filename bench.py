@@ -46,6 +46,10 @@ B_SOR_HALF = 16.0     # in-place colour half-sweep (odd periodic grids): half of
 B_SOR_FUSED = 24.0    # fused red+black pass with ping-pong: read pp + read rhs + write pp
 B_CORR = 56.0
 B_TRANSEQ = 88.0
+# --impl reference: wall-clock budget of the whole run and the port's nominal throughput, used
+# only to decide whether K + W steps of the full grid fit (else a smaller sample grid is used)
+REF_BUDGET_S = 150.0
+REF_RATE_PTS_S = 6.0e6
 # z chunks of the e2e leg (csrc/pipeline.cu: the library default); O3D_PIPELINE overrides
 E2E_PIPELINE_CHUNKS = int(os.environ.get("O3D_PIPELINE", "16"))
 
@@ -208,26 +212,35 @@ def cpu_sample(args, steps, n):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The Fortran
     source cannot be compiled here (no Fortran compiler / FFTW3 in the image), so this times the
-    oracle port (gcc -O2, strict IEEE), single thread: the reference is serial code."""
+    oracle port (gcc -O2, strict IEEE), single thread: the reference is serial code.
+
+    Exactly W warm-up and K timed steps are run.  One step = one full time step of the workload;
+    when K + W steps of the full grid would not end within a few minutes (REF_BUDGET_S at the
+    port's ~7 Mpts*steps/s), each step is a bounded sample instead: the same workload on a
+    smaller grid (the metric is per grid point, so it carries over), named in `sample`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_n or args.n
+    K, W = max(1, args.steps), max(0, args.warmup)
+    n_full = args.n
+    n = args.cpu_n or n_full
+    if not args.cpu_n:
+        per_step = n ** 3 / REF_RATE_PTS_S
+        if (K + W) * per_step > REF_BUDGET_S:
+            n = max(32, int((REF_BUDGET_S / (K + W) * REF_RATE_PTS_S) ** (1.0 / 3.0)))
+            n = min(n, n_full)
     w = workload(args, 1)
-    K, W = args.steps, args.warmup
-    # each bench "step" = one time step of the sample grid; bounded so the run ends in minutes
-    budget_steps = max(1, min(K + W, 6 if n >= 256 else 12))
-    W_eff = min(W, max(0, budget_steps - 1), 2)
-    K_eff = budget_steps - W_eff
-    times, iters = cpu_sample(args, W_eff + K_eff, n)
-    t = times[W_eff:]
+    times, iters = cpu_sample(args, W + K, n)
+    t = times[W:]
     ms = 1e3 * sum(t) / len(t)
     val = (n ** 3) / 1e6 / (ms / 1e3)
-    sample = ("%d timed steps (after %d warm-up) of %s at %d^3, SOR iters/step %s"
-              % (len(t), W_eff, w["name"], n, iters[W_eff:]))
+    sample = ("%d timed steps (after %d warm-up) of %s at %d^3%s, SOR iters/step %s"
+              % (len(t), W, w["name"], n,
+                 "" if n == n_full else " (bounded sample of the %d^3 workload)" % n_full,
+                 iters[W:]))
     line = {"impl": "reference", "metric": "Mpts*steps/s (full AB3+SOR time step)",
             "value": val, "unit": "Mpts*steps/s", "n_gpus": args.gpus, "steps": len(t),
-            "warmup": W_eff, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "grid": [n, n, n], "host": "cpu"},
             "cpu_baseline": {"value": val, "unit": "Mpts*steps/s", "cores": 1, "kind": "port",
