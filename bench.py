@@ -557,7 +557,7 @@ def main():
             line["e2e_resident"] = e2e_res
         if not args.no_cpu:
             ncpu = args.cpu_n or n
-            nsteps = 3 if ncpu >= 200 else 6
+            nsteps = 5 if ncpu >= 200 else 8      # ~10-15 s of CPU work at 256^3
             times, its = cpu_sample(args, nsteps, ncpu)
             tt = times[1:] if len(times) > 1 else times
             ms = 1e3 * sum(tt) / len(tt)
