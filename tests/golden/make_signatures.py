@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Procedure names and dummy-argument lists of the reference modules that fortran/*_b200.f90
+replace, read from /root/reference/src (build container only) -> reference_signatures.json.
+tests/test_fortran_shims_cpu.py checks the shims against it (no Fortran compiler in the image)."""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import f90np  # noqa: E402
+
+REF = "/root/reference/src"
+MODULES = {"derivation": "derivation.f90", "diffoper": "differential_operators.f90",
+           "les_turbulence": "les_turbulence.f90", "poisson": "poisson.f90",
+           "poisson_multigrid": "poisson_multigrid.f90", "integration": "integration.f90"}
+
+
+def main():
+    out = {}
+    for mod, fn in MODULES.items():
+        rs = f90np.routines(open(os.path.join(REF, fn)).read())
+        out[mod] = {"file": "src/" + fn,
+                    "procedures": {r.name: r.dummies for r in rs.values()}}
+    with open(os.path.join(HERE, "reference_signatures.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print({m: len(v["procedures"]) for m, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
