@@ -51,7 +51,10 @@ B_TRANSEQ = 88.0
 REF_BUDGET_S = 150.0
 REF_RATE_PTS_S = 6.0e6
 # z chunks of the e2e leg (csrc/pipeline.cu: the library default); O3D_PIPELINE overrides
-E2E_PIPELINE_CHUNKS = int(os.environ.get("O3D_PIPELINE", "16"))
+try:
+    E2E_PIPELINE_CHUNKS = max(0, int(os.environ.get("O3D_PIPELINE", "16")))
+except ValueError:
+    E2E_PIPELINE_CHUNKS = 16
 
 
 def parse():
