@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath.npz"))
 SHAPE = GOLD["in_ux"].shape
 RE, SC, CS, DT, DELTA, DX, DY, DZ = [float(v) for v in GOLD["params"]]
-CONFIGS = {"ppp": (0, 0, 0), "fff": (1, 1, 1), "pfp": (0, 1, 0)}
+CONFIGS = {"ppp": (0, 0, 0), "fff": (1, 1, 1), "pfp": (0, 1, 0), "ffp": (1, 1, 0), "ppf": (0, 0, 1)}
 DER = ["derx_00", "derxp_11", "derxi_11", "dery_00", "deryp_11", "deryi_11", "derz_00", "derzp_11",
        "derzi_11", "derxx_00", "derxxp_11", "derxxi_11", "deryy_00", "deryyp_11", "deryyi_11",
        "derzz_00", "derzzp_11", "derzzi_11", "derz_2dsim", "derzz_2dsim"]

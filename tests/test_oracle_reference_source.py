@@ -17,7 +17,8 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath.npz"))
 SHAPE = GOLD["in_ux"].shape
 RE, SC, CS, DT, DELTA, DX, DY, DZ = [float(v) for v in GOLD["params"]]
 CONFIGS = {"ppp": ((0, 0, 0), 0), "fff": ((1, 1, 1), 0), "pfp": ((0, 1, 0), 0),
-           "pfp2d": ((0, 1, 0), 1)}
+           "pfp2d": ((0, 1, 0), 1), "ffp": ((1, 1, 0), 0), "ppf": ((0, 0, 1), 0),
+           "fpf": ((1, 0, 1), 0)}
 DER = ["derx_00", "derxp_11", "derxi_11", "dery_00", "deryp_11", "deryi_11", "derz_00", "derzp_11",
        "derzi_11", "derxx_00", "derxxp_11", "derxxi_11", "deryy_00", "deryyp_11", "deryyi_11",
        "derzz_00", "derzzp_11", "derzzi_11", "derz_2dsim", "derzz_2dsim"]
@@ -93,7 +94,7 @@ def test_predict_velocity(O, cfg):
     assert same(got[0], GOLD[cfg + "_pred_sch2_ux"]) and same(f[0], GOLD[cfg + "_pred_sch2_fux"])
 
 
-@pytest.mark.parametrize("cfg", ["ppp", "fff", "pfp"])
+@pytest.mark.parametrize("cfg", ["ppp", "fff", "pfp", "ffp", "ppf"])
 def test_sor_solvers_and_correct_pression(O, cfg):
     """src/poisson.f90:6,132,257 (the variant schemes() binds): iterates, the value of `iter`
     after the loop (kmax + 1 when it runs out), the dynamic relaxation factor;
