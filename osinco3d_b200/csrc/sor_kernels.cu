@@ -22,7 +22,9 @@ namespace {
 
 constexpr int SBX = 64, SBY = 4;
 
-__device__ __forceinline__ void nbr_idx(int p, int n, int mlo, int mhi, int& m1, int& p1) {
+// (__host__ too: tests/cpu/sor_classes_test.cu checks on the CPU that every colour / seam class
+// is an independent set under this neighbour rule)
+__host__ __device__ __forceinline__ void nbr_idx(int p, int n, int mlo, int mhi, int& m1, int& p1) {
     // src/poisson.f90:57-66 (periodic) / :197-206 (mirrored); BM_HALO: stored ghost plane
     m1 = p - 1;
     p1 = p + 1;
@@ -36,7 +38,7 @@ __device__ __forceinline__ void nbr_idx(int p, int n, int mlo, int mhi, int& m1,
     }
 }
 
-__device__ __forceinline__ int seam_pop(const SorArgs& a, int i, int j, int gk) {
+__host__ __device__ __forceinline__ int seam_pop(const SorArgs& a, int i, int j, int gk) {
     return (a.seam_x && i == a.nx - 1) + (a.seam_y && j == a.ny - 1) +
            (a.seam_z && gk == a.gnz - 1);
 }

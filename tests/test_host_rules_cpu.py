@@ -1,8 +1,14 @@
-"""The index rules shared by every kernel (csrc/o3d_common.cuh: map_index, image_offsets, the
-padded layout) and the host-side launch planning (csrc/kernels.h: pick_zchunk), checked on the
-CPU: tests/cpu/host_rules_test.cu is compiled by nvcc (host code only, no CUDA call) and run.
-Main invariant: the ghost images a producer kernel stores with each interior point are, cell for
-cell, what the ghost-fill rule of the closures of src/derivation.f90 would have written."""
+"""Logic the kernels share with the host, checked on the CPU: the .cu files under tests/cpu/ are
+compiled by nvcc (host code; they make no CUDA call) and run.
+
+host_rules_test.cu   csrc/o3d_common.cuh (map_index, image_offsets, padded layout) and
+                     csrc/kernels.h (pick_zchunk): the ghost images a producer kernel stores with
+                     each interior point are, cell for cell, what the ghost-fill rule of the
+                     closures of src/derivation.f90 would have written.
+sor_classes_test.cu  csrc/sor_kernels.cu (nbr_idx, seam_pop): every colour / seam class of the
+                     red-black SOR sweeps is an independent set under the neighbour rule of
+                     src/poisson.f90, for all three boundary variants and all extent parities.
+"""
 import os
 import shutil
 import subprocess
@@ -12,14 +18,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_host_rules(tmp_path):
+@pytest.mark.parametrize("name,ok", [("host_rules_test", "host rules OK"),
+                                     ("sor_classes_test", "sor classes OK")])
+def test_host_compiled_rules(tmp_path, name, ok):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    exe = str(tmp_path / "host_rules_test")
-    src = os.path.join(ROOT, "tests", "cpu", "host_rules_test.cu")
-    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
-                        "-o", exe, src], capture_output=True, text=True, timeout=600)
+    exe = str(tmp_path / name)
+    src = os.path.join(ROOT, "tests", "cpu", name + ".cu")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-fmad=false", "-gencode",
+                        "arch=compute_100a,code=sm_100a", "-o", exe, src], capture_output=True,
+                       text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0 and "host rules OK" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and ok in r.stdout, r.stdout + r.stderr
