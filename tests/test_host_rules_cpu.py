@@ -32,3 +32,40 @@ def test_host_compiled_rules(tmp_path, name, ok):
     assert r.returncode == 0, r.stdout + r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and ok in r.stdout, r.stdout + r.stderr
+
+
+def test_multigrid_transfer_tables_equal_the_design_model(tmp_path, built_lib):
+    """csrc/multigrid.cu (coarse_extent, axis_tables: non-nested vertex-centred coarsening for
+    mirrored / periodic axes of any parity) against oracle/mg_model.py, entry for entry --
+    including the exact 0 / 0.5 weights of the nested cases -- for the shipped extents"""
+    import json
+    import sys
+
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import mg_model as mm
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "mg_tables_dump")
+    libdir = os.path.join(ROOT, "osinco3d_b200", "lib")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-fmad=false", "-gencode",
+                        "arch=compute_100a,code=sm_100a", "-o", exe,
+                        os.path.join(ROOT, "tests", "cpu", "mg_tables_dump.cu"), "-L" + libdir,
+                        "-lo3d_b200", "-Xlinker", "-rpath", "-Xlinker", libdir],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 32
+    for t in lines:
+        n, mode = t["n"], t["mode"]
+        assert t["nc"] == mm.coarse_extent(n, mode), (n, mode)
+        if not t["nc"]:
+            continue
+        D, c0, w, ridx, rw = mm.axis_tables(n, 0.0371, mode, t["nc"])
+        assert t["D"] == D, (n, mode)
+        assert t["c0"] == list(c0) and t["w"] == list(w), (n, mode)
+        assert t["ridx"] == list(ridx.ravel()), (n, mode)
+        assert np.array_equal(np.array(t["rw"]), rw.ravel()), (n, mode)
