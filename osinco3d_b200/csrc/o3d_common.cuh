@@ -142,11 +142,13 @@ inline Coef make_coef(double d) {
 }
 
 // interior expressions, src/derivation.f90:43-47 and :529-533 (evaluation order kept)
-__device__ __forceinline__ double d1_expr(double a, double b, double c, double m3, double m2,
+// (__host__ too: tests/cpu/stencil_rules_test.cu evaluates them on ghost-extended lines on the CPU
+// against the vectors generated from the reference source)
+__host__ __device__ __forceinline__ double d1_expr(double a, double b, double c, double m3, double m2,
                                           double m1, double p1, double p2, double p3) {
     return a * (p3 - m3) - b * (p2 - m2) + c * (p1 - m1);
 }
-__device__ __forceinline__ double d2_expr(double a, double b, double c, double m2, double m1,
+__host__ __device__ __forceinline__ double d2_expr(double a, double b, double c, double m2, double m1,
                                           double f0, double p1, double p2) {
     return -(a * (m2 + p2)) + b * (m1 + p1) - c * f0;
 }

@@ -69,3 +69,38 @@ def test_multigrid_transfer_tables_equal_the_design_model(tmp_path, built_lib):
         assert t["c0"] == list(c0) and t["w"] == list(w), (n, mode)
         assert t["ridx"] == list(ridx.ravel()), (n, mode)
         assert np.array_equal(np.array(t["rw"]), rw.ravel()), (n, mode)
+
+
+def test_kernel_stencil_expressions_reproduce_the_reference_routines(tmp_path):
+    """d1_expr / d2_expr + make_coef + map_index (the arithmetic every stencil kernel performs,
+    csrc/o3d_common.cuh) evaluated on the host == the 18 routines of src/derivation.f90 as
+    executed from the reference source (tests/golden/hotpath.npz), bit for bit, boundary planes
+    included"""
+    import numpy as np
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "stencil_rules_test")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-fmad=false", "-Xcompiler", "-ffp-contract=off",
+                        "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                        os.path.join(ROOT, "tests", "cpu", "stencil_rules_test.cu")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "hotpath.npz"))
+    dx, dy, dz = [float(v) for v in gold["params"][5:8]]
+    for tag, key in (("", "in_pp"), ("_small", "in_small")):
+        f = np.asfortranarray(gold[key])
+        fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+        f.ravel(order="F").tofile(fin)
+        r = subprocess.run([exe, fin] + [str(n) for n in f.shape] + [repr(dx), repr(dy), repr(dz), fout],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        out = np.fromfile(fout).reshape((18,) + f.shape[::-1])
+        q = 0
+        for axis in "xyz":
+            for order in (1, 2):
+                for closure in ("_00", "p_11", "i_11"):
+                    name = "der" + axis * order + closure
+                    got = out[q].transpose(2, 1, 0)            # file is (k, j, i) C order
+                    assert np.array_equal(got, gold[name + tag]), (name, tag)
+                    q += 1
