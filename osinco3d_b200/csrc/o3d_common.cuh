@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 
@@ -151,6 +152,38 @@ __host__ __device__ __forceinline__ double d1_expr(double a, double b, double c,
 __host__ __device__ __forceinline__ double d2_expr(double a, double b, double c, double m2, double m1,
                                           double f0, double p1, double p2) {
     return -(a * (m2 + p2)) + b * (m1 + p1) - c * f0;
+}
+
+// ---- point-wise expressions of the velocity kernels (__host__ too: tests/cpu/step_rules_test.cu
+// evaluates them on the CPU against the vectors generated from the reference source) ----------
+// the nine first derivatives d[c][axis] of (ux, uy, uz)
+struct Grad {
+    double d[3][3];
+};
+
+// Smagorinsky viscosity, src/les_turbulence.f90:70-88
+__host__ __device__ __forceinline__ double smagorinsky(const Grad& G, double csd2) {
+    const double s11 = G.d[0][0], s22 = G.d[1][1], s33 = G.d[2][2];
+    const double s12 = 0.5 * (G.d[0][1] + G.d[1][0]);
+    const double s13 = 0.5 * (G.d[0][2] + G.d[2][0]);
+    const double s23 = 0.5 * (G.d[1][2] + G.d[2][1]);
+    const double smag = sqrt(2.0 * (s11 * s11 + s22 * s22 + s33 * s33 +
+                                    2.0 * (s12 * s12 + s13 * s13 + s23 * s23)));
+    return csd2 * smag;
+}
+
+// f_c = nu_eff (d2x + d2y + d2z) u_c - (ux dx + uy dy + uz dz) u_c, src/integration.f90:129-134
+__host__ __device__ __forceinline__ double rhs_expr(double nu_eff, double lx, double ly, double lz,
+                                                    double u0, double u1, double u2, double g0,
+                                                    double g1, double g2) {
+    return nu_eff * (lx + ly + lz) - (u0 * g0 + u1 * g1 + u2 * g2);
+}
+
+// u_c* = u_c + adu f1 + bdu f2 + cdu f3, src/integration.f90:132-134
+__host__ __device__ __forceinline__ double predictor_expr(double uc, double adu, double f1,
+                                                          double bdu, double f2, double cdu,
+                                                          double f3) {
+    return uc + adu * f1 + bdu * f2 + cdu * f3;
 }
 
 // ---- warp / block reductions ------------------------------------------------------------

@@ -26,10 +26,7 @@ struct Coefs3 {
     Coef x, y, z;
 };
 
-// the nine first derivatives d1[c][axis] of (ux,uy,uz)
-struct Grad {
-    double d[3][3];
-};
+// (struct Grad, smagorinsky, rhs_expr, predictor_expr: o3d_common.cuh)
 template <class RG>
 __device__ __forceinline__ Grad gradient(const RG& r, const Coefs3& q, int sim2d) {
     Grad G;
@@ -40,17 +37,6 @@ __device__ __forceinline__ Grad gradient(const RG& r, const Coefs3& q, int sim2d
         G.d[c][2] = sim2d ? 0.0 : r.d1z(c, q.z);  // derz_2dsim, src/derivation.f90:481
     }
     return G;
-}
-
-// Smagorinsky viscosity, src/les_turbulence.f90:70-88
-__device__ __forceinline__ double smagorinsky(const Grad& G, double csd2) {
-    const double s11 = G.d[0][0], s22 = G.d[1][1], s33 = G.d[2][2];
-    const double s12 = 0.5 * (G.d[0][1] + G.d[1][0]);
-    const double s13 = 0.5 * (G.d[0][2] + G.d[2][0]);
-    const double s23 = 0.5 * (G.d[1][2] + G.d[2][1]);
-    const double smag = sqrt(2.0 * (s11 * s11 + s22 * s22 + s33 * s33 +
-                                    2.0 * (s12 * s12 + s13 * s13 + s23 * s23)));
-    return csd2 * smag;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -121,10 +107,9 @@ struct RhsEpi {
             const double lx = r.d2x(c, q.x), ly = r.d2y(c, q.y);
             const double lz = (!FAST && sim2d) ? 0.0 : r.d2z(c, q.z);
             // src/integration.f90:129-134 (and :149-154, :169-174)
-            const double f = nu_eff * (lx + ly + lz) -
-                             (u0 * G.d[c][0] + u1 * G.d[c][1] + u2 * G.d[c][2]);
+            const double f = rhs_expr(nu_eff, lx, ly, lz, u0, u1, u2, G.d[c][0], G.d[c][1], G.d[c][2]);
             const double uc = (c == 0) ? u0 : (c == 1) ? u1 : u2;
-            const double upv = uc + adu * f + bdu * pre.f2v[c] + cdu * pre.f3v[c];
+            const double upv = predictor_expr(uc, adu, f, bdu, pre.f2v[c], cdu, pre.f3v[c]);
             f1[c][m] = f;
             up[c][m] = upv;
             ups[c] = upv;
@@ -214,9 +199,9 @@ struct RhsRoleEpi {
         const double lx = r.d2x(c, q.x), ly = r.d2y(c, q.y);
         const double lz = sim2d ? 0.0 : r.d2z(c, q.z);
         // src/integration.f90:129-134 (and :149-154, :169-174)
-        const double f = nu_eff * (lx + ly + lz) - (u0 * g0 + u1 * g1 + u2 * g2);
+        const double f = rhs_expr(nu_eff, lx, ly, lz, u0, u1, u2, g0, g1, g2);
         const double uc = (c == 0) ? u0 : (c == 1) ? u1 : u2;
-        const double upv = uc + adu * f + bdu * pre.f2v + cdu * pre.f3v;
+        const double upv = predictor_expr(uc, adu, f, bdu, pre.f2v, cdu, pre.f3v);
         if (!ok) return;
         f1c[m] = f;
         upc[m] = upv;

@@ -104,3 +104,55 @@ def test_kernel_stencil_expressions_reproduce_the_reference_routines(tmp_path):
                     got = out[q].transpose(2, 1, 0)            # file is (k, j, i) C order
                     assert np.array_equal(got, gold[name + tag]), (name, tag)
                     q += 1
+
+
+def test_kernel_rhs_arithmetic_reproduces_predict_velocity(tmp_path):
+    """the per-point sequence of the fused RHS + nu_t + predictor kernel -- d1_expr / d2_expr on
+    natural-parity ghost cells, smagorinsky(), rhs_expr(), predictor_expr(), all from
+    csrc/o3d_common.cuh -- on the host == predict_velocity (src/integration.f90:14-197) and
+    calculate_nu_t (src/les_turbulence.f90:10-97) as executed from the reference source, bit for
+    bit, for every boundary configuration, DNS and LES, Euler and AB2 coefficients"""
+    import numpy as np
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "step_rules_test")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-fmad=false", "-Xcompiler", "-ffp-contract=off",
+                        "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                        os.path.join(ROOT, "tests", "cpu", "step_rules_test.cu")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "hotpath.npz"))
+    re_, sc, cs, dt, delta, dx, dy, dz = [float(v) for v in gold["params"]]
+    shape = gold["in_ux"].shape
+    N = int(np.prod(shape))
+    u = [np.asfortranarray(gold["in_u" + c]) for c in "xyz"]
+    fu = [np.asfortranarray(gold["in_fu" + c]) for c in "xyz"]
+    blob = np.concatenate([a.ravel(order="F") for a in u] +
+                          [a[..., 1].ravel(order="F") for a in fu] +
+                          [a[..., 2].ravel(order="F") for a in fu])
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    blob.tofile(fin)
+    configs = {"ppp": (0, 0, 0, 0), "fff": (1, 1, 1, 0), "pfp": (0, 1, 0, 0), "pfp2d": (0, 1, 0, 1),
+               "ffp": (1, 1, 0, 0), "ppf": (0, 0, 1, 0), "fpf": (1, 0, 1, 0)}
+
+    def run(cfg, iles, level):
+        bx, by, bz, sim2d = configs[cfg]
+        coef = [repr(float(gold[k][level])) for k in ("adt", "bdt", "cdt")]
+        r = subprocess.run([exe, fin, fout] + [str(n) for n in shape] +
+                           [repr(dx), repr(dy), repr(dz), str(bx), str(by), str(bz), str(sim2d),
+                            str(iles), repr(re_), repr(cs), repr(delta)] + coef,
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        out = np.fromfile(fout).reshape((7, N))
+        return [o.reshape(shape, order="F") for o in out]
+
+    for cfg in configs:
+        for iles in (0, 1):                       # itime = 1: Euler coefficients
+            out = run(cfg, iles, 0)
+            for c, a in zip("xyz", out[:3]):
+                assert np.array_equal(a, gold["%s_pred_les%d_it1_u%s" % (cfg, iles, c)]), (cfg, iles, c)
+            assert np.array_equal(out[3], gold["%s_pred_les%d_it1_nu_t" % (cfg, iles)]), (cfg, iles)
+        out = run(cfg, 0, 1)                      # itscheme = 2: AB2 coefficients, f1 stored
+        assert np.array_equal(out[0], gold[cfg + "_pred_sch2_ux"]), cfg
+        assert np.array_equal(out[4], gold[cfg + "_pred_sch2_fux"][..., 0]), cfg
