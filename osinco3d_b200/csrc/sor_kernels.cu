@@ -43,6 +43,31 @@ __host__ __device__ __forceinline__ int seam_pop(const SorArgs& a, int i, int j,
            (a.seam_z && gk == a.gnz - 1);
 }
 
+// The reference's point update and relaxation, src/poisson.f90:95-98 and :102 (division by A: the
+// bit-parity form used by the verification ordering), and the bit pattern -> double view of the
+// residual accumulator.  __host__ too: tests/cpu/sor_sweep_test.cu runs the reference's
+// lexicographic sweep with them on the CPU.
+__host__ __device__ __forceinline__ double sor_pnew_ref(double ox, double oy, double oz, double pw,
+                                                        double pe, double ps, double pn, double pb,
+                                                        double pt, double rhs, double A) {
+    return (-(ox * (pw + pe)) - oy * (ps + pn) - oz * (pb + pt) + rhs) / A;
+}
+__host__ __device__ __forceinline__ double sor_relax(double omega, double pc, double p_new) {
+    return (1.0 - omega) * pc + omega * p_new;
+}
+__host__ __device__ __forceinline__ double bits_as_double(unsigned long long b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    union {
+        unsigned long long u;
+        double d;
+    } v;
+    v.u = b;
+    return v.d;
+#endif
+}
+
 template <bool IMAGES = false>
 __device__ __forceinline__ double sor_point(const SorArgs& a, int i, int j, int k,
                                             double omega) {
@@ -367,21 +392,20 @@ __global__ void __launch_bounds__(256) sor_wavefront_kernel(const SorArgs a, int
         const double pb = a.pp[(long long)km1 * sz + (long long)j * sy + i];
         const double pt = a.pp[(long long)kp1 * sz + (long long)j * sy + i];
         const double pc = a.pp[m];
-        const double p_new = (-(a.oneondx2 * (pw + pe)) - a.oneondy2 * (ps + pn) -
-                              a.oneondz2 * (pb + pt) + a.rhs[m]) /
-                             a.A;  // src/poisson.f90:95-98
+        const double p_new = sor_pnew_ref(a.oneondx2, a.oneondy2, a.oneondz2, pw, pe, ps, pn, pb,
+                                          pt, a.rhs[m], a.A);  // src/poisson.f90:95-98
         d = fabs(p_new - pc);
-        a.pp[m] = (1.0 - omega) * pc + omega * p_new;
+        a.pp[m] = sor_relax(omega, pc, p_new);
     }
     const double bm = block_max(d, red);
     if (threadIdx.x == 0 && threadIdx.y == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
 }
 
 // src/poisson.f90:110-122, evaluated once per completed sweep
-__device__ __forceinline__ void sor_control_step(SorCtrl* c, double eps, int kmax, int idyn,
-                                                 double factor) {
+__host__ __device__ __forceinline__ void sor_control_step(SorCtrl* c, double eps, int kmax,
+                                                          int idyn, double factor) {
     if (c->done) return;
-    const double dmax = __longlong_as_double((long long)c->dmax_bits);
+    const double dmax = bits_as_double(c->dmax_bits);
     c->dmax_bits = 0ull;
     const int iter = c->iter + 1;
     c->iter = iter;

@@ -156,3 +156,41 @@ def test_kernel_rhs_arithmetic_reproduces_predict_velocity(tmp_path):
         out = run(cfg, 0, 1)                      # itscheme = 2: AB2 coefficients, f1 stored
         assert np.array_equal(out[0], gold[cfg + "_pred_sch2_ux"]), cfg
         assert np.array_equal(out[4], gold[cfg + "_pred_sch2_fux"][..., 0]), cfg
+
+
+def test_kernel_sor_functions_reproduce_the_reference_solvers(tmp_path):
+    """nbr_idx + sor_pnew_ref + sor_relax + sor_control_step (csrc/sor_kernels.cu: what
+    sor_wavefront_kernel and sor_control_kernel execute) in the reference's loop order on the host
+    == poisson_solver_0000 / _0011 / _111111 as executed from the reference source: iterates,
+    the loop variable after the loop, the dynamic omega and dmax, bit for bit"""
+    import numpy as np
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "sor_sweep_test")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-fmad=false", "-Xcompiler", "-ffp-contract=off",
+                        "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                        os.path.join(ROOT, "tests", "cpu", "sor_sweep_test.cu")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "hotpath.npz"))
+    dx, dy, dz = [float(v) for v in gold["params"][5:8]]
+    shape = gold["in_pp"].shape
+    N = int(np.prod(shape))
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.concatenate([np.asfortranarray(gold["in_pp"]).ravel(order="F"),
+                    np.asfortranarray(gold["in_rhs"]).ravel(order="F")]).tofile(fin)
+    # configuration -> the variant schemes() binds from the x and y flags
+    variants = {"ppp": 0, "ppf": 0, "pfp": 1, "fff": 2, "ffp": 2}
+    for cfg, variant in variants.items():
+        for tag, (omega, eps, kmax, idyn) in (("fixed", (1.6, 1e-30, 12, 0)),
+                                              ("dyn", (1.9, 2e-3, 400, 1))):
+            r = subprocess.run([exe, fin, fout] + [str(n) for n in shape] +
+                               [repr(dx), repr(dy), repr(dz), str(variant), repr(omega), repr(eps),
+                                str(kmax), str(idyn)], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            out = np.fromfile(fout)
+            assert np.array_equal(out[:N].reshape(shape, order="F"), gold["%s_sor_%s_pp" % (cfg, tag)]), \
+                (cfg, tag)
+            assert np.array_equal(out[N:], gold["%s_sor_%s_scalars" % (cfg, tag)]), \
+                (cfg, tag, out[N:], gold["%s_sor_%s_scalars" % (cfg, tag)])
