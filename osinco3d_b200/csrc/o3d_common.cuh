@@ -186,6 +186,39 @@ __host__ __device__ __forceinline__ double predictor_expr(double uc, double adu,
     return uc + adu * f1 + bdu * f2 + cdu * f3;
 }
 
+// divergence (src/differential_operators.f90:35) [/ dt -> Poisson right-hand side,
+// src/integration.f90:239] and the projection correction u = u* - dt dp (src/integration.f90:304-306)
+__host__ __device__ __forceinline__ double div_expr(double dfx, double dfy, double dfz, int divide,
+                                                    double dt) {
+    double v = dfx + dfy + dfz;
+    if (divide) v = v / dt;
+    return v;
+}
+__host__ __device__ __forceinline__ double corr_expr(double ustar, double dt, double dp) {
+    return ustar - dt * dp;
+}
+
+// scalar transport, src/integration.f90:403-409 (effective diffusivity), :422-423 (right-hand
+// side), :436/:450 (clip to [0,1]), :443-447 (redistribution of the clipped excess)
+__host__ __device__ __forceinline__ double transeq_alpha(double resc, double nut, double sc,
+                                                         int iles) {
+    return iles ? (1.0 / resc + nut / sc) : (1.0 / resc);
+}
+__host__ __device__ __forceinline__ double transeq_rhs_expr(double alpha_eff, double dx2, double dy2,
+                                                            double dz2, double u0, double u1,
+                                                            double u2, double dx1, double dy1,
+                                                            double dz1, double src) {
+    return alpha_eff * (dx2 + dy2 + dz2) - (u0 * dx1 + u1 * dy1 + u2 * dz1) + src;
+}
+__host__ __device__ __forceinline__ double clip01(double x) { return fmax(0.0, fmin(1.0, x)); }
+__host__ __device__ __forceinline__ double transeq_weight(double pc) { return fmin(pc, 1.0 - pc); }
+__host__ __device__ __forceinline__ double transeq_redistribute(double pc, double excess,
+                                                                double sum_w) {
+    double wgt = transeq_weight(pc);
+    wgt = wgt / sum_w;
+    return clip01(pc + excess * wgt);
+}
+
 // ---- warp / block reductions ------------------------------------------------------------
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll

@@ -51,8 +51,8 @@ struct DivEpi {
         const double dfx = r.c_d1x(0, cx);
         const double dfy = r.c_d1y(1, cy);
         const double dfz = S2 ? 0.0 : r.d1z(0, cz);
-        double v = dfx + dfy + dfz;  // src/differential_operators.f90:35
-        if (divide) v = v / dt;      // src/integration.f90:239
+        // src/differential_operators.f90:35, src/integration.f90:239
+        const double v = div_expr(dfx, dfy, dfz, divide, dt);
         out[m] = v;
         if (edge_xy || k <= zimg_lo || k >= zimg_hi) {  // boundary-adjacent points only
             const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
@@ -105,9 +105,9 @@ struct CorrEpi {
         const double dpdy = r.d1y(0, cy);
         const double dpdz = S2 ? 0.0 : r.d1z(0, cz);
         // src/integration.f90:304-306
-        const double u0 = r.st(0) - dt * dpdx;
-        const double u1 = r.st(1) - dt * dpdy;
-        const double u2 = r.st(2) - dt * dpdz;
+        const double u0 = corr_expr(r.st(0), dt, dpdx);
+        const double u1 = corr_expr(r.st(1), dt, dpdy);
+        const double u2 = corr_expr(r.st(2), dt, dpdz);
         u[0][m] = u0;
         u[1][m] = u1;
         u[2][m] = u2;

@@ -47,19 +47,19 @@ struct TranseqEpi {
         const double dz1 = sim2d ? 0.0 : r.d1z(0, cz);
         const double dz2 = sim2d ? 0.0 : r.d2z(0, cz);
         // src/integration.f90:403-409
-        const double alpha_eff = iles ? (1.0 / resc + p.nut / sc) : (1.0 / resc);
+        const double alpha_eff = transeq_alpha(resc, p.nut, sc, iles);
         // :422-423
-        const double f = alpha_eff * (dx2 + dy2 + dz2) -
-                         (p.u[0] * dx1 + p.u[1] * dy1 + p.u[2] * dz1) + p.srcv;
+        const double f = transeq_rhs_expr(alpha_eff, dx2, dy2, dz2, p.u[0], p.u[1], p.u[2], dx1, dy1,
+                                          dz1, p.srcv);
         // :426
-        const double pn = r.c(0) + adu * f + bdu * p.f2v + cdu * p.f3v;
+        const double pn = predictor_expr(r.c(0), adu, f, bdu, p.f2v, cdu, p.f3v);
         f1[m] = f;
         phi_new[m] = pn;
         // :433-444 partial sums
         s_old += pn;
-        const double pc = fmax(0.0, fmin(1.0, pn));
+        const double pc = clip01(pn);
         s_clip += pc;
-        s_w += fmin(pc, 1.0 - pc);
+        s_w += transeq_weight(pc);
     }
     __device__ __forceinline__ void finish(int tid, double* smem) {
         const double a = warp_sum(s_old), b = warp_sum(s_clip), c = warp_sum(s_w);
@@ -94,12 +94,8 @@ __global__ void __launch_bounds__(256) transeq_clip_kernel(const Geom g,
         const long long base = (long long)k * g.sz + (long long)j * g.sy;
         for (int i = threadIdx.x; i < g.nx; i += blockDim.x) {
             const long long m = base + i;
-            const double pc = fmax(0.0, fmin(1.0, __ldg(phi_new + m)));  // :436
-            double wgt = fmin(pc, 1.0 - pc);                             // :443
-            wgt = wgt / sw;                                              // :444
-            double p = pc + excess * wgt;                                // :447
-            p = fmax(0.0, fmin(1.0, p));                                 // :450
-            phi[m] = p;
+            const double pc = clip01(__ldg(phi_new + m));       // :436
+            phi[m] = transeq_redistribute(pc, excess, sw);      // :443-450
         }
     }
 }

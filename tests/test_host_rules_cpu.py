@@ -194,3 +194,52 @@ def test_kernel_sor_functions_reproduce_the_reference_solvers(tmp_path):
                 (cfg, tag)
             assert np.array_equal(out[N:], gold["%s_sor_%s_scalars" % (cfg, tag)]), \
                 (cfg, tag, out[N:], gold["%s_sor_%s_scalars" % (cfg, tag)])
+
+
+def test_kernel_divergence_correction_and_transeq_arithmetic(tmp_path):
+    """div_expr / corr_expr / transeq_* / clip01 / predictor_expr (csrc/o3d_common.cuh: what
+    DivEpi, CorrEpi, TranseqEpi and transeq_clip_kernel call) on ghost cells on the host ==
+    divergence, correct_velocity and transeq (clip + redistribution included) as executed from
+    the reference source, bit for bit, on every boundary configuration"""
+    import numpy as np
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "scalar_rules_test")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-fmad=false", "-Xcompiler", "-ffp-contract=off",
+                        "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                        os.path.join(ROOT, "tests", "cpu", "scalar_rules_test.cu")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "hotpath.npz"))
+    re_, sc, cs, dt, delta, dx, dy, dz = [float(v) for v in gold["params"]]
+    shape = gold["in_ux"].shape
+    N = int(np.prod(shape))
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    flat = lambda a: np.asfortranarray(a).ravel(order="F")  # noqa: E731
+    configs = {"ppp": (0, 0, 0, 0), "fff": (1, 1, 1, 0), "pfp": (0, 1, 0, 0), "pfp2d": (0, 1, 0, 1),
+               "ffp": (1, 1, 0, 0), "ppf": (0, 0, 1, 0), "fpf": (1, 0, 1, 0)}
+
+    def run(mode, fields, cfg, extra, nout):
+        np.concatenate([flat(a) for a in fields]).tofile(fin)
+        r = subprocess.run([exe, mode, fin, fout] + [str(n) for n in shape] +
+                           [repr(dx), repr(dy), repr(dz)] + [str(v) for v in configs[cfg]] + extra,
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, (mode, cfg, r.stdout + r.stderr)
+        return [o.reshape(shape, order="F") for o in np.fromfile(fout).reshape((nout, N))]
+
+    u = [gold["in_u" + c] for c in "xyz"]
+    for cfg in configs:
+        for odd in (0, 1):
+            got = run("div", u, cfg, [str(odd)], 1)[0]
+            assert np.array_equal(got, gold["%s_divergence_odd%d" % (cfg, odd)]), (cfg, odd)
+        got = run("corr", u + [gold["in_pp"]], cfg, [repr(dt)], 3)
+        for c, a in zip("xyz", got):
+            assert np.array_equal(a, gold["%s_corr_u%s" % (cfg, c)]), (cfg, c)
+        for iles in (0, 1):      # first step of the golden sequence: Euler with the enlarged adt
+            coef = [repr(40.0 * float(gold["adt"][0])), repr(float(gold["bdt"][0])),
+                    repr(float(gold["cdt"][0]))]
+            fphi = gold["in_fphi"]
+            got = run("transeq", [gold["in_phi"]] + u + [gold[cfg + "_nu_t"], fphi[..., 1], fphi[..., 2]],
+                      cfg, [str(iles), repr(re_), repr(sc)] + coef, 2)
+            assert np.array_equal(got[0], gold["%s_transeq_les%d_it1_phi" % (cfg, iles)]), (cfg, iles)
