@@ -172,6 +172,12 @@ __host__ __device__ __forceinline__ double smagorinsky(const Grad& G, double csd
     return csd2 * smag;
 }
 
+// Q criterion, src/differential_operators.f90:103-104
+__host__ __device__ __forceinline__ double q_criterion_expr(const Grad& G) {
+    return -(0.5 * (G.d[0][0] * G.d[0][0] + G.d[1][1] * G.d[1][1] + G.d[2][2] * G.d[2][2])) -
+           G.d[0][1] * G.d[1][0] - G.d[0][2] * G.d[2][0] - G.d[1][2] * G.d[2][1];
+}
+
 // f_c = nu_eff (d2x + d2y + d2z) u_c - (ux dx + uy dy + uz dz) u_c, src/integration.f90:129-134
 __host__ __device__ __forceinline__ double rhs_expr(double nu_eff, double lx, double ly, double lz,
                                                     double u0, double u1, double u2, double g0,

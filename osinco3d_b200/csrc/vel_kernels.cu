@@ -285,9 +285,7 @@ struct QEpi {
     __device__ __forceinline__ Pre prefetch(long long, bool) const { return Pre(); }
     __device__ __forceinline__ void apply(const Ring<3>& r, long long m, int, int, int, const Pre&) {
         const Grad G = gradient(r, q, sim2d);
-        // src/differential_operators.f90:103-104
-        qc[m] = -(0.5 * (G.d[0][0] * G.d[0][0] + G.d[1][1] * G.d[1][1] + G.d[2][2] * G.d[2][2])) -
-                G.d[0][1] * G.d[1][0] - G.d[0][2] * G.d[2][0] - G.d[1][2] * G.d[2][1];
+        qc[m] = q_criterion_expr(G);  // src/differential_operators.f90:103-104
     }
     __device__ __forceinline__ void finish(int, double*) {}
 };

@@ -9,7 +9,10 @@
 // rings, ghost images) -- that is what the GPU parity tests are for.
 //
 //   step_rules_test in.bin out.bin nx ny nz dx dy dz bx by bz sim2d iles re cs delta adu bdu cdu
-//   in  = ux uy uz | f2x f2y f2z | f3x f3y f3z        out = upx upy upz | nu_t | f1x f1y f1z
+//   in  = ux uy uz | f2x f2y f2z | f3x f3y f3z
+//   out = upx upy upz | nu_t | f1x f1y f1z | Q | rotx roty rotz
+// (Q = q_criterion_expr on the same natural-parity gradient, src/differential_operators.f90:79-108;
+//  the curl as RotEpi forms it from the off-diagonal -- even -- derivatives, :64-73)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -30,7 +33,7 @@ int main(int argc, char** argv) {
     const double re = atof(argv[14]), cs = atof(argv[15]), delta = atof(argv[16]);
     const double adu = atof(argv[17]), bdu = atof(argv[18]), cdu = atof(argv[19]);
     const size_t N = (size_t)nx * ny * nz;
-    std::vector<double> in(9 * N), out(7 * N);
+    std::vector<double> in(9 * N), out(11 * N);
     FILE* fi = fopen(argv[1], "rb");
     if (!fi || fread(in.data(), 8, 9 * N, fi) != 9 * N) return 3;
     fclose(fi);
@@ -68,6 +71,10 @@ int main(int argc, char** argv) {
                                          : d2_expr(q[a].a2, q[a].b2, q[a].c2, at(c, a, -2), at(c, a, -1),
                                                    at(c, a, 0), at(c, a, 1), at(c, a, 2));
                     }
+                out[7 * N + m] = q_criterion_expr(G);
+                out[8 * N + m] = G.d[2][1] - G.d[1][2];   // duzdy - duydz
+                out[9 * N + m] = G.d[0][2] - G.d[2][0];   // duxdz - duzdx
+                out[10 * N + m] = G.d[1][0] - G.d[0][1];  // duydx - duxdy
                 double nut = 0.0;
                 if (iles) nut = smagorinsky(G, csd2);
                 out[3 * N + m] = nut;
@@ -81,7 +88,7 @@ int main(int argc, char** argv) {
                 }
             }
     FILE* fo = fopen(argv[2], "wb");
-    if (!fo || fwrite(out.data(), 8, 7 * N, fo) != 7 * N) return 4;
+    if (!fo || fwrite(out.data(), 8, 11 * N, fo) != 11 * N) return 4;
     fclose(fo);
     printf("step rules written\n");
     return 0;

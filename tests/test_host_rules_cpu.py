@@ -144,7 +144,7 @@ def test_kernel_rhs_arithmetic_reproduces_predict_velocity(tmp_path):
                             str(iles), repr(re_), repr(cs), repr(delta)] + coef,
                            capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stdout + r.stderr
-        out = np.fromfile(fout).reshape((7, N))
+        out = np.fromfile(fout).reshape((11, N))
         return [o.reshape(shape, order="F") for o in out]
 
     for cfg in configs:
@@ -153,6 +153,10 @@ def test_kernel_rhs_arithmetic_reproduces_predict_velocity(tmp_path):
             for c, a in zip("xyz", out[:3]):
                 assert np.array_equal(a, gold["%s_pred_les%d_it1_u%s" % (cfg, iles, c)]), (cfg, iles, c)
             assert np.array_equal(out[3], gold["%s_pred_les%d_it1_nu_t" % (cfg, iles)]), (cfg, iles)
+        # rotational / calculate_Q_criterion (src/differential_operators.f90:40-108)
+        assert np.array_equal(out[7], gold[cfg + "_q"]), cfg
+        for c, a in zip("xyz", out[8:11]):
+            assert np.array_equal(a, gold["%s_rot%s" % (cfg, c)]), (cfg, c)
         out = run(cfg, 0, 1)                      # itscheme = 2: AB2 coefficients, f1 stored
         assert np.array_equal(out[0], gold[cfg + "_pred_sch2_ux"]), cfg
         assert np.array_equal(out[4], gold[cfg + "_pred_sch2_fux"][..., 0]), cfg
