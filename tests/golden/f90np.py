@@ -645,6 +645,10 @@ def load(paths, names, namespace, module_arrays=()):
     found = {}
     for p in paths:
         found.update(routines(open(p).read()))
+    # the translated text comes from a source tree we do not control: it only ever needs these
+    # builtins, so nothing else (open, exec, __import__ ...) is reachable from it
+    namespace.setdefault("__builtins__", {"range": range, "float": float, "int": int,
+                                          "locals": locals})
     src = {}
     for nm in names:
         r = found[nm.lower()]

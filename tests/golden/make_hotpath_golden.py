@@ -77,7 +77,7 @@ def ab_coefficients(dt):
         m = re.match(r"^([abc]dt)\((\d)\)\s*=\s*(.+)$", st)
         if m:
             c[m.group(1)][int(m.group(2)) - 1] = float(eval(f90np.expr_py(m.group(3), set()),
-                                                            {"dt": dt}))
+                                                            {"__builtins__": {}, "dt": dt}))
     assert all(v is not None for k in c for v in c[k]), c
     return farr(c["adt"]), farr(c["bdt"]), farr(c["cdt"])
 
