@@ -70,3 +70,30 @@ def test_operators_and_predictor_from_the_reference_source(M, cfg):
     for c, a in zip("xyz", got[:3]):
         assert np.array_equal(a, GOLD["%s_corr_u%s" % (cfg, c)]), c
     assert got[3] is False
+
+
+def test_cpp_host_mirror_on_the_device(gpu, tmp_path):
+    """include/o3d_b200.hpp from a compiled C++ program (tests/cpu/hpp_mirror_test.cpp): the 18
+    derivative routines, divergence and correct_velocity through the namespaces that mirror the
+    reference's modules, against the reference-source vectors, bit for bit"""
+    from test_hpp_mirror_cpu import build_hpp_test
+    import subprocess
+    exe = build_hpp_test(tmp_path)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    fields = [inp("pp"), inp("ux"), inp("uy"), inp("uz"), inp("pp")]
+    np.concatenate([a.ravel(order="F") for a in fields]).tofile(fin)
+    r = subprocess.run([exe, "run", fin, fout] + [str(n) for n in SHAPE] +
+                       [repr(DX), repr(DY), repr(DZ), repr(DT)], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "hpp mirror run OK" in r.stdout, r.stdout + r.stderr
+    N = int(np.prod(SHAPE))
+    out = [o.reshape(SHAPE, order="F") for o in np.fromfile(fout).reshape((22, N))]
+    q = 0
+    for axis in "xyz":
+        for order in (1, 2):
+            for closure in ("_00", "p_11", "i_11"):
+                assert np.array_equal(out[q], GOLD["der" + axis * order + closure]), (axis, order, closure)
+                q += 1
+    assert np.array_equal(out[18], GOLD["fff_divergence_odd1"])
+    for c, a in zip("xyz", out[19:22]):
+        assert np.array_equal(a, GOLD["fff_corr_u" + c]), c
