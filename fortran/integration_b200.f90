@@ -8,17 +8,27 @@
 !>          call.  Bit-for-bit the reference's data flow; PCIe-bound (34 N doubles per step).
 !>  .true.  (resident, the intended production mode): the fields live in a device session created
 !>          on the first call from the module `initialization` globals.  ux, uy, uz, pp, phi and
-!>          the AB histories are uploaded ONCE; per step only ux, uy, uz (and phi) are mirrored
-!>          back so that the driver's own prints / I-O keep working.  The driver must not modify
-!>          ux, uy, uz, pp, phi between steps (osinco3d_main.f90:97-188 does not).
+!>          the AB histories are uploaded ONCE.  What comes back per step is `o3d_mirror`:
+!>            1 (default, works with the UNCHANGED driver): every array the reference's main loop
+!>              reads after the step is refreshed on the host -- ux_pred, uy_pred, uz_pred
+!>              (divergence(divu_pred, ...), osinco3d_main.f90:116), pp (visualize_2d,
+!>              write_all_data, :133-150), nu_t, ux, uy, uz, phi: 8-9 N doubles D2H per step;
+!>            0: nothing is mirrored; the driver must then take its prints from
+!>              o3d_s_step_diagnostics and its files from fortran/output_b200.f90
+!>              (INTEGRATION.md section 3 lists the ~10 lines of osinco3d_main.f90:116-183 to
+!>              replace), and ux_pred / pp / nu_t / ux / uy / uz / phi on the host are STALE.
+!>          The driver must not modify ux, uy, uz, pp, phi between steps
+!>          (osinco3d_main.f90:97-188 does not).
 module integration
   use iso_c_binding
-  use initialization, only : nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d, sc0 => sc
+  use initialization, only : nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d, sc0 => sc, &
+       nscr0 => nscr
   use IOfunctions
   use o3d_b200_c
   implicit none
 
   logical :: o3d_resident = .true.
+  integer :: o3d_mirror = 1
   type(c_ptr), private :: ses = c_null_ptr
   logical, private :: primed = .false.
 
@@ -49,7 +59,9 @@ contains
     c%re = re; c%sc = sc0; c%cs = cs; c%delta = delta
     c%dt = adt(1)                       ! adt(1) = dt, src/initialization.f90:194
     c%adt = adt; c%bdt = bdt; c%cdt = cdt
-    c%itscheme = itscheme; c%iles = iles; c%nscr = 0
+    c%itscheme = itscheme; c%iles = iles
+    c%nscr = nscr0                      ! Scalar namelist (src/initialization.f90:62,122): the
+                                        ! session's o3d_step / write_all_data need the real value
     c%omega = 1.d0; c%eps = 1.d-6; c%kmax = 1; c%idyn = 0; c%multigrid = 0   ! set per call below
     c%sor_order = 0; c%sor_check_every = 0
     c%rank = 0; c%nranks = 1
@@ -88,6 +100,13 @@ contains
             dx, dy, dz, nx, ny, nz, iles, cs, delta)
     end if
     call o3d_check(o3d_s_predict_velocity(ses, itime), "predict_velocity")
+    if (o3d_mirror /= 0) then
+       ! intent(out) arrays the unchanged driver reads at osinco3d_main.f90:116-119
+       call o3d_check(o3d_download(ses, O3D_F_UX_PRED, ux_pred), "download ux_pred")
+       call o3d_check(o3d_download(ses, O3D_F_UY_PRED, uy_pred), "download uy_pred")
+       call o3d_check(o3d_download(ses, O3D_F_UZ_PRED, uz_pred), "download uz_pred")
+       if (iles == 1) call o3d_check(o3d_download(ses, O3D_F_NU_T, nu_t), "download nu_t")
+    end if
   end subroutine predict_velocity
 
   subroutine correct_pression(pp, ux_pred, uy_pred, uz_pred, dx, dy, dz, &
@@ -114,6 +133,8 @@ contains
     end if
     call o3d_check(o3d_s_correct_pression(ses, iters, dmax), "correct_pression")
     call o3d_check(o3d_get_omega(ses, omega), "get omega")   ! omega is intent(inout), :222
+    ! pp is intent(inout): visualize_2d / write_all_data read it (osinco3d_main.f90:133-150)
+    if (o3d_mirror /= 0) call o3d_check(o3d_download(ses, O3D_F_PP, pp), "download pp")
   end subroutine correct_pression
 
   subroutine correct_velocity(ux, uy, uz, ux_pred, uy_pred, uz_pred, pp, dt, dx, dy, dz, nx, ny, nz)
@@ -128,10 +149,12 @@ contains
             nx, ny, nz)
     else
        rc = o3d_s_correct_velocity(ses)
-       ! mirror the new velocity for the driver's prints / output (3 N doubles D2H per step)
-       call o3d_check(o3d_download(ses, O3D_F_UX, ux), "download ux")
-       call o3d_check(o3d_download(ses, O3D_F_UY, uy), "download uy")
-       call o3d_check(o3d_download(ses, O3D_F_UZ, uz), "download uz")
+       if (o3d_mirror /= 0) then
+          ! the new velocity for the driver's prints / output (3 N doubles D2H per step)
+          call o3d_check(o3d_download(ses, O3D_F_UX, ux), "download ux")
+          call o3d_check(o3d_download(ses, O3D_F_UY, uy), "download uy")
+          call o3d_check(o3d_download(ses, O3D_F_UZ, uz), "download uz")
+       end if
     end if
     if (rc == O3D_ERR_DIVERGED) then
        ! src/integration.f90:309-325: NaN or max(u) > 1000 -> report and stop
@@ -160,7 +183,7 @@ contains
        phi_up = .true.
     end if
     call o3d_check(o3d_s_transeq(ses, itime), "transeq")
-    call o3d_check(o3d_download(ses, O3D_F_PHI, phi), "download phi")
+    if (o3d_mirror /= 0) call o3d_check(o3d_download(ses, O3D_F_PHI, phi), "download phi")
   end subroutine transeq
 
 end module integration

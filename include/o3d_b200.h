@@ -267,7 +267,14 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out);
 int o3d_session_destroy(o3d_session* s);
 /* local slab extent of this rank: planes [z0, z0+nz_local) of the global grid */
 int o3d_session_slab(const o3d_session* s, int* z0, int* nz_local);
-/* host <-> device copies of this rank's slab of one field (nx*ny*nz_local doubles) */
+/* host <-> device copies of this rank's slab of one field (nx*ny*nz_local doubles).
+ * History ids (O3D_F_FUX1..3 etc.) are LOGICAL levels 1..3 of fu?(:,:,:,1:3): the reference's
+ * shifts fu(:,:,:,2) = fu(:,:,:,1), fu(:,:,:,3) = fu(:,:,:,2) (src/integration.f90:176-188) are
+ * pointer rotations here, so after a step levels 1 and 2 hold the same data in ONE buffer.  An
+ * upload to level 1 is redirected to the free buffer first (it never overwrites level 2 or 3);
+ * a restart may therefore upload the levels in any order.
+ * o3d_download also reports a pending NaN / >1000 guard (O3D_ERR_DIVERGED, data still
+ * delivered), like o3d_sync. */
 int o3d_upload(o3d_session* s, int field, const double* host);
 int o3d_download(o3d_session* s, int field, double* host);
 /* Device fields are PADDED (ghost cells hold the boundary closure, DESIGN.md "Data layout"):

@@ -602,6 +602,17 @@ static int ensure_stage(o3d_session* s) {
 // full-speed DMA, followed / preceded by a pack kernel (HBM traffic, negligible next to PCIe).
 int o3d_upload(o3d_session* s, int fid, const double* host) {
     if (!s || !host) return O3D_ERR_INVALID;
+    // History ids are LOGICAL levels.  After the first rotation levels 1 and 2 share a physical
+    // buffer (level 1 is always rewritten by the next predictor before it is read, so the
+    // reference's copy fu(:,:,:,2) = fu(:,:,:,1) is a pointer assignment here): an upload to
+    // level 1 must not clobber level 2 -> give level 1 the free buffer first.
+    for (int c = 0; c < 4; ++c) {
+        const int hb = c < 3 ? O3D_F_FUX1 + 3 * c : O3D_F_FPHI1;
+        if (fid == hb && (s->lv[c][0] == s->lv[c][1] || s->lv[c][0] == s->lv[c][2])) {
+            for (int p = 0; p < 3; ++p)
+                if (p != s->lv[c][1] && p != s->lv[c][2]) s->lv[c][0] = p;
+        }
+    }
     const int id = phys_id(s, fid);
     double* d = field(s, id);
     if (!d) return O3D_ERR_CUDA;
@@ -625,6 +636,16 @@ int o3d_download(o3d_session* s, int fid, double* host) {
     O3D_CUDA_CHECK(cudaMemcpyAsync(host, s->stage_d, (size_t)s->nloc * sizeof(double),
                                    cudaMemcpyDeviceToHost, s->st));
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    // o3d_step leaves the NaN / >1000 guard of its correction in flight: a caller that steps and
+    // then downloads without o3d_sync must not get a diverged state silently (the data is still
+    // delivered, as the stateless o3d_correct_velocity does)
+    poll_flag(s);
+    if (s->diverged) {
+        s->diverged = 0;
+        cudaMemsetAsync(s->flag_d, 0, sizeof(int), s->st);
+        set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
+        return O3D_ERR_DIVERGED;
+    }
     return O3D_OK;
 }
 

@@ -158,9 +158,12 @@ int queue_field(o3d_session* s, IoEngine* e, const double* d, int fd, long long 
                 cudaEventRecord(e->buf[b].copied, e->st_io) != cudaSuccess))
         rc = O3D_ERR_CUDA;
     if (rc) {
-        std::lock_guard<std::mutex> lk(e->m);
-        e->buf[b].busy = false;
-        --e->in_flight;
+        {
+            std::lock_guard<std::mutex> lk(e->m);
+            e->buf[b].busy = false;
+            --e->in_flight;
+        }
+        e->cv_free.notify_all();  // a waiter in o3d_s_io_wait / queue_field must see the release
         if (close_fd) close(fd);
         set_error("I/O snapshot of a field failed: %s", cudaGetErrorString(cudaGetLastError()));
         return rc;
@@ -269,8 +272,11 @@ int o3d_s_save_fields(o3d_session* s, const char* filename, double time, const d
     if (!s || !filename || !x || !y || !z) return O3D_ERR_INVALID;
     const o3d_config& c = s->cfg;
     IoEngine* e;
-    int rc = io_engine(s, &e);
+    // the reference stops inside correct_velocity before any save_fields
+    // (src/integration.f90:309-325): report a pending NaN / >1000 flag instead of writing
+    int rc = o3d_sync(s);
     if (rc) return rc;
+    if ((rc = io_engine(s, &e))) return rc;
     // src/IOfunctions.f90:396-399
     const long long hdr = 8 + 12 + 8ll * (c.nx + c.ny + c.nz);
     const long long fbytes = (long long)c.nx * c.ny * c.nz * 8;
@@ -299,8 +305,21 @@ int o3d_s_save_fields(o3d_session* s, const char* filename, double time, const d
         }
     }
     const long long slab = (long long)c.nx * c.ny * 8 * s->z0;
-    for (int f = 0; f < 5; ++f)
-        if ((rc = queue_field(s, e, d[f], fd, hdr + f * fbytes + slab, f == 4))) return rc;
+    for (int f = 0; f < 5; ++f) {
+        if ((rc = queue_field(s, e, d[f], fd, hdr + f * fbytes + slab, f == 4))) {
+            // the five jobs share one descriptor that only the last one closes: drain what was
+            // queued, close it here and do not leave a full-size, partly written restart file
+            if (f < 4) {
+                {
+                    std::unique_lock<std::mutex> lk(e->m);
+                    e->cv_free.wait(lk, [&] { return e->in_flight == 0; });
+                }
+                close(fd);
+            }
+            if (c.nranks <= 1 || c.rank == 0) unlink(filename);
+            return rc;
+        }
+    }
     return O3D_OK;
 }
 
@@ -360,8 +379,9 @@ int o3d_s_read_fields(o3d_session* s, const char* filename, double* time, double
 int o3d_s_write_binary(o3d_session* s, const char* filename, int fid) {
     if (!s || !filename || fid < 0 || fid >= O3D_F_COUNT) return O3D_ERR_INVALID;
     IoEngine* e;
-    int rc = io_engine(s, &e);
+    int rc = o3d_sync(s);
     if (rc) return rc;
+    if ((rc = io_engine(s, &e))) return rc;
     double* d = field(s, phys_id(s, fid));
     if (!d) return O3D_ERR_CUDA;
     return write_raw(s, e, filename, d);
@@ -371,8 +391,9 @@ int o3d_s_write_all_data(o3d_session* s, const char* dir, int num) {
     if (!s || !dir) return O3D_ERR_INVALID;
     const o3d_config& c = s->cfg;
     IoEngine* e;
-    int rc = io_engine(s, &e);
+    int rc = o3d_sync(s);  // a diverged state is reported, not written (see o3d_s_save_fields)
     if (rc) return rc;
+    if ((rc = io_engine(s, &e))) return rc;
     mkdir(dir, 0755);  // the reference's check_directories(); EEXIST is fine
     auto path = [&](const char* name) {
         return std::string(dir) + "/" + name + "_" + std::to_string(num) + ".bin";

@@ -235,10 +235,15 @@ int build(o3d_session* s, int max_levels) {
     L0.g.nx = s->g.nx, L0.g.ny = s->g.ny, L0.g.nz = s->g.nz;
     L0.g.sy = s->g.sy, L0.g.sz = s->g.sz;
     L0.g.mx = modes[0], L0.g.my = modes[1];
-    L0.g.mz_lo = multi ? s->g.bz_lo : modes[2];
-    L0.g.mz_hi = multi ? s->g.bz_hi : modes[2];
-    if (multi && s->g.bz_lo != BM_HALO) L0.g.mz_lo = modes[2];  // wall side of an end rank
-    if (multi && s->g.bz_hi != BM_HALO) L0.g.mz_hi = modes[2];
+    {   // z rule of the Poisson VARIANT (src/initialization.f90:283-301: _0000 / _0011 wrap z,
+        // _111111 mirrors it), not of the session's nbcz closures -- the two differ when nbcz is
+        // free-slip under variant 0/1 or periodic under variant 2 -- with BM_HALO on the sides
+        // that face another rank: exactly what sor_solve and the level-0 smoother use, and what
+        // comm_exchange(zwrap = variant != 2) fills
+        const SorArgs sa = make_sor_args(s, nullptr, nullptr);
+        L0.g.mz_lo = sa.mz_lo;
+        L0.g.mz_hi = sa.mz_hi;
+    }
     L0.gn[0] = s->g.nx, L0.gn[1] = s->g.ny, L0.gn[2] = s->cfg.nz;
     for (int a = 0; a < 3; ++a) L0.d[a] = H->d[a];
     set_operator(L0.g, L0.d);

@@ -85,6 +85,15 @@ def main():
         ("periodic_even_multigrid", 32, 16 * world, (0, 0, 0), 0, 1, 1e-8, 0, 3, 1),
         ("periodic_odd_multigrid_ragged", 33, 16 * world + 3, (0, 0, 0), 1, 0, 1e-8, 0, 3, 1),
         ("mixed_0011_multigrid", 40, 20 * world + 1, (0, 1, 0), 0, 0, 1e-8, 0, 3, 1),
+        # nbcz differs from the Poisson variant's z rule (src/initialization.f90:283-301 picks the
+        # variant from the x / y flags only): _0000 / _0011 wrap z across the ranks although the
+        # stencils mirror it, _111111 mirrors z on the end ranks although the stencils wrap it
+        ("zrule_0000_freeslipz_SOR", 32, 16 * world, (0, 0, 1), 0, 0, 1e-7, 0, 3),
+        ("zrule_0011_freeslipz_SOR", 33, 16 * world + 1, (0, 1, 1), 0, 1, 1e-6, 1, 3),
+        ("zrule_111111_periodicz_SOR", 33, 16 * world + 2, (1, 1, 0), 1, 0, 1e-6, 0, 3),
+        ("zrule_0000_freeslipz_multigrid", 32, 16 * world, (0, 0, 1), 0, 0, 1e-8, 0, 3, 1),
+        ("zrule_0011_freeslipz_multigrid", 33, 16 * world + 1, (0, 1, 1), 0, 0, 1e-8, 0, 3, 1),
+        ("zrule_111111_periodicz_multigrid", 33, 16 * world + 2, (1, 1, 0), 0, 0, 1e-8, 0, 3, 1),
     ]
     only = os.environ.get("O3D_MGPU_ONLY")
     for case in cases:

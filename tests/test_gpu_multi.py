@@ -22,4 +22,4 @@ def test_slab_decomposition_is_bitwise_equal_to_one_gpu(gpu, world):
                        timeout=900)
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:]
-    assert r.stdout.count("BITWISE-EQUAL") >= 12
+    assert r.stdout.count("BITWISE-EQUAL") >= 18

@@ -133,41 +133,78 @@ def test_stage_calls_equal_fused_step(gpu, O):
     sim.close()
 
 
-def test_golden_dns_row2_on_gpu(gpu, O):
-    """examples/tgv_re1600_dns: 185^3, 25 steps, shipped omega/eps, RED_BLACK fast path, against
-    the reference's own stats row 2 (t = 25 dt).  Same bounds as the oracle's pin test."""
+ORACLE_HIST = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                          "oracle_history.json")))
+
+
+def test_golden_dns_history_all_rows_on_gpu(gpu, O):
+    """examples/tgv_re1600_dns: 185^3, shipped omega/eps, RED_BLACK fast path, 100 steps with
+    statistics_calc every 25 (src/osinco3d_main.f90:167-181), against ALL FIVE rows of the
+    reference's own history (examples/tgv_re1600_dns/tgv_stats_re1600_dns.dat:18-22) -- north star
+    "kinetic-energy and enstrophy histories <= 1e-6" -- and against the oracle's history
+    (tests/golden/oracle_history.json, lexicographic SOR at the same eps)."""
     n = 185
     d = PI / (n - 1)
     sim, ses = make_pair(gpu, O, (n, n, n), (d, d, d), (1, 1, 1), tgv(O), re=1600.0,
                          dt=0.05 * d, omega=1.887, eps=1e-4)
     sim.close()
-    its = [ses.step() for _ in range(25)]
-    st = ses.statistics()
-    ref = np.array(GOLD["tgv_re1600_dns"]["rows"][1])
-    assert abs(st[0] - ref[0]) < 1e-13
-    assert abs(st[1] - ref[1]) / ref[1] < 1e-6        # E_k      (history tolerance)
-    assert abs(st[4] - ref[4]) / ref[4] < 1e-6        # enstrophy
-    assert abs(st[1] - ref[1]) / ref[1] < 5e-8, ((st[1] - ref[1]) / ref[1], its)
-    assert abs(st[2] - ref[2]) / ref[2] < 1e-6
+    rows = GOLD["tgv_re1600_dns"]["rows"]
+    orc = ORACLE_HIST["tgv_re1600_dns"]["rows"]
+    assert len(rows) == 5 and len(orc) == 5
+    its, step, worst = [], 0, 0.0
+    for r, ref in enumerate(rows):
+        while step < 25 * r:
+            its.append(ses.step())
+            step += 1
+        st = ses.statistics()
+        ref = np.array(ref)
+        assert abs(st[0] - ref[0]) < 1e-13, (r, st[0], ref[0])         # time = step * dt
+        for c in (1, 4):        # E_k, enstrophy: the history tolerance, with margin
+            rel = abs(st[c] - ref[c]) / ref[c]
+            worst = max(worst, rel)
+            assert rel < 1e-6, (r, c, st[c], ref[c])
+            assert rel < (6e-13 if r == 0 else 5e-8), (r, c, rel, its[-5:])
+            assert abs(st[c] - orc[r]["columns"][c]) / ref[c] < (1e-13 if r == 0 else 5e-8)
+        for c in (2, 3):        # the two dissipation estimates
+            assert abs(st[c] - ref[c]) / ref[c] < (6e-13 if r == 0 else 5e-7), (r, c)
+    print("DNS history, 5 rows: worst relative gap to the reference file %.2e; red-black SOR "
+          "iterations/step min %d mean %.1f max %d" % (worst, min(its), np.mean(its), max(its)))
     ses.close()
 
 
-def test_golden_les_row1_on_gpu(gpu, O):
-    """examples/tgv_re2500_les: 129^3 Smagorinsky, 25 steps, wavefront ordering so that the
-    reference's dynamic-omega heuristic sees the reference's dmax sequence."""
+def test_golden_les_history_all_rows_on_gpu(gpu, O):
+    """examples/tgv_re2500_les: 129^3 Smagorinsky, 125 steps, wavefront ordering so that the
+    reference's dynamic-omega heuristic sees the reference's dmax sequence.  The device history
+    must equal the ORACLE's (same source version) at every row to round-off; against the shipped
+    file (examples/tgv_re2500_les/tgv_stats_re2500_les.dat:18-22) row 1 is inside the 1e-6
+    history tolerance and the gap then grows linearly, 4.5e-7 per 25 steps, for the oracle and
+    the device alike: the file predates the current les_turbulence.f90 (SURVEY.md section 4;
+    tests/golden/make_oracle_history.py records the same drift on the CPU)."""
     n = 129
     d = PI / (n - 1)
     sim, ses = make_pair(gpu, O, (n, n, n), (d, d, d), (1, 1, 1), tgv(O), re=2500.0, dt=5e-4,
                          omega=1.999, eps=1e-6, idyn=1, iles=1, cs=0.17,
                          sor_order=gpu.SOR_LEXI_WAVEFRONT)
     sim.close()
-    for _ in range(25):
-        ses.step()
-    st = ses.statistics()
-    ref = np.array(GOLD["tgv_re2500_les"]["rows"][0])
-    assert abs(st[0] - ref[0]) < 1e-13
-    for c in (1, 2, 4):
-        assert abs(st[c] - ref[c]) / ref[c] < 1e-6, (c, st[c], ref[c])
+    rows = GOLD["tgv_re2500_les"]["rows"]
+    orc = ORACLE_HIST["tgv_re2500_les"]
+    assert len(rows) == 5
+    step, its = 0, []
+    for r, ref in enumerate(rows):
+        while step < 25 * (r + 1):
+            its.append(ses.step())
+            step += 1
+        st = ses.statistics()
+        ref = np.array(ref)
+        assert abs(st[0] - ref[0]) < 1e-13
+        for c in (1, 2, 4):
+            o = orc["rows"][r]["columns"][c]
+            assert abs(st[c] - o) <= 1e-11 * abs(o), (r, c, st[c], o)      # == oracle history
+            drift = abs(st[c] - ref[c]) / ref[c]
+            assert drift < 4.8e-7 * (r + 1), (r, c, drift)
+            if r == 0:
+                assert drift < 1e-6
+    assert its == orc["sor_iters_per_step"][:len(its)]     # the reference's iteration counts
     ses.close()
 
 
