@@ -350,6 +350,11 @@ int o3d_s_write_binary(o3d_session* s, const char* filename, int field);
 int o3d_s_write_all_data(o3d_session* s, const char* dir, int num);
 int o3d_s_io_wait(o3d_session* s);
 
+/* how the LAST red-black solve of this session ran (bench.py / tests report it; no counterpart in
+ * the reference): *persistent = 1 when all its iterations ran inside one cooperative launch
+ * (exit tests and dynamic omega on the device, no host poll), *peer = 1 when, on z slabs, its ghost
+ * planes and residual maxima travelled through peer-mapped memory instead of NCCL calls */
+int o3d_s_sor_path(const o3d_session* s, int* persistent, int* peer);
 /* current SOR relaxation factor (inout across steps, src/integration.f90:222,247) */
 int o3d_get_omega(const o3d_session* s, double* omega);
 int o3d_set_omega(o3d_session* s, double omega);

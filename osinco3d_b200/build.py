@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(OUT_DIR, "libo3d_b200.so")
 
 SOURCES = ["api.cu", "modules.cu", "pipeline.cu", "poisson.cu", "comm.cu", "tma.cu", "ghost_kernels.cu",
-           "der_kernel.cu", "vel_kernels.cu", "proj_kernels.cu", "sor_kernels.cu", "sor_tma_kernel.cu",
+           "der_kernel.cu", "vel_kernels.cu", "proj_kernels.cu", "sor_kernels.cu", "sor_tma_kernel.cu", "sor_persist_kernel.cu",
            "transeq_kernels.cu", "reduce_kernels.cu", "mg_kernels.cu", "multigrid.cu", "io.cu"]
 
 NVCC_FLAGS = [

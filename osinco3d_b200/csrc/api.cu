@@ -232,6 +232,15 @@ const CUtensorMap* sor_tmap(o3d_session* s, int id) {
     return &s->tmap_sor[id];
 }
 
+void swap_pp(o3d_session* s) {
+    std::swap(s->base[O3D_F_PP], s->base[O3D_F_PP2]);
+    std::swap(s->tmap[O3D_F_PP], s->tmap[O3D_F_PP2]);
+    std::swap(s->tmap_sor[O3D_F_PP], s->tmap_sor[O3D_F_PP2]);
+    std::swap(s->tmap_st[O3D_F_PP], s->tmap_st[O3D_F_PP2]);
+    std::swap(s->tmap_sor_ok[O3D_F_PP], s->tmap_sor_ok[O3D_F_PP2]);
+    s->pp_phys ^= 1;
+}
+
 int ensure_ghosts1(o3d_session* s, int id, unsigned par, unsigned axes, bool defer) {
     return ensure_ghosts(s, &id, 1, &par, axes, defer);
 }
@@ -514,6 +523,9 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->sw_a = nullptr, s->sw_b = nullptr;
     s->ctrl_d = nullptr, s->ctrl_h = nullptr, s->flag_d = nullptr, s->flag_h = nullptr;
     s->seam_sync_d = nullptr;
+    s->persist_sync_d = nullptr, s->ev_ctrl = nullptr;
+    s->pp_phys = 0, s->peers = nullptr, s->peers_tried = 0, s->peer_iter_base = 0ull;
+    s->last_sor_path = 0;
     s->scal_d = nullptr, s->scal_h = nullptr;
     fill_geom(s);
     cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
@@ -530,6 +542,8 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_h, sizeof(SorCtrl), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&s->seam_sync_d, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(s->seam_sync_d, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&s->persist_sync_d, 32 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ctrl, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->flag_d, sizeof(int));
     // the NaN / >1000 flag is sticky (only cleared when reported): it must start clean
     if (e == cudaSuccess) e = cudaMemset(s->flag_d, 0, sizeof(int));
@@ -564,6 +578,8 @@ int o3d_session_destroy(o3d_session* s) {
     if (s->stage_d) cudaFree(s->stage_d);
     if (s->ctrl_d) cudaFree(s->ctrl_d);
     if (s->seam_sync_d) cudaFree(s->seam_sync_d);
+    if (s->persist_sync_d) cudaFree(s->persist_sync_d);
+    if (s->ev_ctrl) cudaEventDestroy(s->ev_ctrl);
     if (s->ctrl_h) cudaFreeHost(s->ctrl_h);
     if (s->flag_d) cudaFree(s->flag_d);
     if (s->flag_h) cudaFreeHost(s->flag_h);
@@ -681,6 +697,13 @@ int o3d_sync(o3d_session* s) {
         set_error("velocity diverged: NaN or max(u) > 1000 (src/integration.f90:309-325)");
         return O3D_ERR_DIVERGED;
     }
+    return O3D_OK;
+}
+
+int o3d_s_sor_path(const o3d_session* s, int* persistent, int* peer) {
+    if (!s) return O3D_ERR_INVALID;
+    if (persistent) *persistent = s->last_sor_path & 1;
+    if (peer) *peer = (s->last_sor_path >> 1) & 1;
     return O3D_OK;
 }
 

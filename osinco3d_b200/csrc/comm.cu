@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <cstring>
+#include <vector>
 
 #include "session.h"
 
@@ -20,7 +21,7 @@ typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclSuccess_ = 0 };
 // ncclDataType_t / ncclRedOp_t values (nccl.h, stable since 2.x)
-enum { ncclUint64_ = 5, ncclFloat64_ = 8 };
+enum { ncclUint8_ = 1, ncclUint64_ = 5, ncclFloat64_ = 8 };
 enum { ncclSum_ = 0, ncclMax_ = 2, ncclMin_ = 3 };
 
 struct Api {
@@ -34,6 +35,7 @@ struct Api {
                               cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -70,6 +72,7 @@ bool load_api() {
     O3D_SYM(Recv, "ncclRecv")
     O3D_SYM(AllReduce, "ncclAllReduce")
     O3D_SYM(Broadcast, "ncclBroadcast")
+    O3D_SYM(AllGather, "ncclAllGather")
     O3D_SYM(GroupStart, "ncclGroupStart")
     O3D_SYM(GroupEnd, "ncclGroupEnd")
     O3D_SYM(GetErrorString, "ncclGetErrorString")
@@ -122,7 +125,147 @@ int comm_create(o3d_session* s) {
     return O3D_OK;
 }
 
+// ---- peer memory (CUDA IPC over NVLink) for the persistent SOR kernel ------------------------
+// Every rank exports three allocations: its PeerBlock and its two physical pp buffers.  The
+// handles travel in one ncclAllGather; a rank maps all blocks (the residual maxima go all-to-all)
+// and the pp buffers of its z neighbours (ghost planes are stored straight into them).
+struct PeerState {
+    int ok = 0;
+    PeerBlock* mine = nullptr;
+    PeerBlock* all[16] = {};
+    double* nb_alloc[16][2] = {};  // [rank][physical buffer]: mapped allocation bases (neighbours)
+    int nb_nz[16] = {};
+    void* opened[48] = {};
+    int nopened = 0;
+};
+
+namespace {
+struct PeerExport {
+    cudaIpcMemHandle_t block, p[2];
+    int nzl, ok, pad[2];
+};
+}  // namespace
+
+int comm_peer_setup(o3d_session* s) {
+    Comm* c = s->comm;
+    if (!c || c->nranks > 16) return 1;
+    if (s->peers) return s->peers->ok ? 0 : 1;
+    if (s->peers_tried) return 1;
+    s->peers_tried = 1;
+    PeerState* ps = new PeerState();
+    s->peers = ps;
+    const int P = c->nranks, me = c->rank;
+    PeerExport mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.nzl = s->nzl;
+    mine.ok = 1;
+    // physical buffer 0 is the allocation that was O3D_F_PP at session start
+    double* phys[2] = {s->base[s->pp_phys ? O3D_F_PP2 : O3D_F_PP],
+                       s->base[s->pp_phys ? O3D_F_PP : O3D_F_PP2]};
+    if (!phys[0] || !phys[1]) mine.ok = 0;
+    if (mine.ok && (cudaMalloc(&ps->mine, sizeof(PeerBlock)) != cudaSuccess ||
+                    cudaMemset(ps->mine, 0, sizeof(PeerBlock)) != cudaSuccess))
+        mine.ok = 0;
+    if (mine.ok && (cudaIpcGetMemHandle(&mine.block, ps->mine) != cudaSuccess ||
+                    cudaIpcGetMemHandle(&mine.p[0], phys[0]) != cudaSuccess ||
+                    cudaIpcGetMemHandle(&mine.p[1], phys[1]) != cudaSuccess)) {
+        (void)cudaGetLastError();
+        mine.ok = 0;
+    }
+    // all-gather the exports (every rank takes part, also one that failed so far)
+    PeerExport* dev = nullptr;
+    std::vector<PeerExport> allx(P);
+    if (cudaMalloc(&dev, sizeof(PeerExport) * (size_t)(P + 1)) != cudaSuccess) return 1;
+    cudaMemcpyAsync(dev + P, &mine, sizeof(mine), cudaMemcpyHostToDevice, s->st);
+    ncclResult_t r = g_api.AllGather(dev + P, dev, sizeof(PeerExport), ncclUint8_, c->nccl, s->st);
+    cudaMemcpyAsync(allx.data(), dev, sizeof(PeerExport) * (size_t)P, cudaMemcpyDeviceToHost, s->st);
+    const cudaError_t ce = cudaStreamSynchronize(s->st);
+    cudaFree(dev);
+    if (r != ncclSuccess_ || ce != cudaSuccess) return 1;
+    bool ok = true;
+    for (int q = 0; q < P; ++q) ok = ok && allx[q].ok;
+    // neighbours in the slab ring (the wrap link is mapped whether or not this solve uses it)
+    const int up = (me + 1) % P, dn = (me + P - 1) % P;
+    for (int q = 0; q < P && ok; ++q) {
+        ps->nb_nz[q] = allx[q].nzl;
+        if (q == me) {
+            ps->all[q] = ps->mine;
+            continue;
+        }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, allx[q].block, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = false;
+            break;
+        }
+        ps->opened[ps->nopened++] = ptr;
+        ps->all[q] = static_cast<PeerBlock*>(ptr);
+        if (q == up || q == dn) {
+            for (int b = 0; b < 2 && ok; ++b) {
+                if (cudaIpcOpenMemHandle(&ptr, allx[q].p[b], cudaIpcMemLazyEnablePeerAccess) !=
+                    cudaSuccess) {
+                    ok = false;
+                    break;
+                }
+                ps->opened[ps->nopened++] = ptr;
+                ps->nb_alloc[q][b] = static_cast<double*>(ptr);
+            }
+        }
+    }
+    if (!ok) (void)cudaGetLastError();
+    // the decision must be the same on every rank: agree on it (min over ranks)
+    double* flag = s->scal_d + 100;
+    const double mineok = ok ? 1.0 : 0.0;
+    double allok = 0.0;
+    cudaMemcpyAsync(flag, &mineok, sizeof(double), cudaMemcpyHostToDevice, s->st);
+    r = g_api.AllReduce(flag, flag, 1, ncclFloat64_, ncclMin_, c->nccl, s->st);
+    cudaMemcpyAsync(&allok, flag, sizeof(double), cudaMemcpyDeviceToHost, s->st);
+    if (cudaStreamSynchronize(s->st) != cudaSuccess || r != ncclSuccess_) return 1;
+    ps->ok = allok > 0.5;
+    return ps->ok ? 0 : 1;
+}
+
+int comm_peer_args(o3d_session* s, PeerSync* out) {
+    PeerState* ps = s->peers;
+    Comm* c = s->comm;
+    if (!ps || !ps->ok || !c) return 1;
+    memset(out, 0, sizeof(*out));
+    const int P = c->nranks, me = c->rank;
+    const int wrap = (s->sor_variant != 2);  // _0000 / _0011 wrap z, _111111 mirrors it
+    const int up = (me + 1 < P) ? me + 1 : (wrap ? 0 : -1);
+    const int dn = (me > 0) ? me - 1 : (wrap ? P - 1 : -1);
+    out->nranks = P, out->rank = me;
+    out->has_lo = dn >= 0, out->has_hi = up >= 0;
+    out->iter_base = s->peer_iter_base;
+    out->mine = ps->mine;
+    for (int q = 0; q < P; ++q) out->all[q] = ps->all[q];
+    const long long ioff = interior_offset(s->g);
+    // role order of the neighbour's buffers = ours: all ranks swap in lockstep (same iteration
+    // counts), so its current O3D_F_PP is its physical buffer pp_phys
+    if (dn >= 0) {
+        out->lo = ps->all[dn];
+        out->lo_nz = ps->nb_nz[dn];
+        out->lo_p[0] = ps->nb_alloc[dn][s->pp_phys] + ioff;
+        out->lo_p[1] = ps->nb_alloc[dn][s->pp_phys ^ 1] + ioff;
+    }
+    if (up >= 0) {
+        out->hi = ps->all[up];
+        out->hi_p[0] = ps->nb_alloc[up][s->pp_phys] + ioff;
+        out->hi_p[1] = ps->nb_alloc[up][s->pp_phys ^ 1] + ioff;
+    }
+    return 0;
+}
+
+static void peer_destroy(o3d_session* s) {
+    PeerState* ps = s->peers;
+    if (!ps) return;
+    for (int q = 0; q < ps->nopened; ++q) cudaIpcCloseMemHandle(ps->opened[q]);
+    if (ps->mine) cudaFree(ps->mine);
+    delete ps;
+    s->peers = nullptr;
+}
+
 void comm_destroy(o3d_session* s) {
+    peer_destroy(s);
     if (!s->comm) return;
     g_api.CommDestroy(s->comm->nccl);
     delete s->comm;

@@ -191,6 +191,38 @@ int sor_tma_box_y();
 int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_map,
                    const CUtensorMap* rhs_map, double* p_new, int bx, int by, int bz_lo,
                    int bz_hi, SorCtrl* ctrl, int zmode = 0, int zedge = 0);
+// ---- persistent SOR: all iterations of a solve in one cooperative launch (sor_persist_kernel.cu)
+// Synchronisation block of one rank of a z-slab run.  It lives in that rank's device memory and is
+// mapped by every other rank of the node (CUDA IPC): neighbours count the ghost planes they have
+// stored into this rank's pp buffers, all ranks deposit their residual maxima.
+struct PeerBlock {
+    unsigned long long halo_cnt[2];       // planes received into my low / high ghost planes (monotone)
+    unsigned long long pad0[14];
+    unsigned long long dmax_slot[2][16];  // [global iteration & 1][source rank]
+    unsigned long long dmax_flag[16];     // [source rank] = global iterations published so far
+};
+struct PeerSync {
+    int nranks, rank;                     // nranks <= 1: single rank, nothing below is read
+    int has_lo, has_hi;                   // a neighbour rank below / above (periodic wrap included)
+    int lo_nz;                            // the lower neighbour's number of owned planes
+    unsigned long long iter_base;         // iterations all ranks completed in earlier persistent solves
+    PeerBlock* mine;
+    PeerBlock* lo;
+    PeerBlock* hi;
+    PeerBlock* all[16];                   // every rank's block (all[rank] == mine)
+    double* lo_p[2];                      // the neighbours' ping-pong buffers (interior origins), in
+    double* hi_p[2];                      //   the same role order as the local p0 / p1
+};
+// 0: launched; 1: CUDA error; 2: not applicable (no cooperative launch / slabs with seams) -> the
+// caller uses the launch-per-pass path.  Runs until ctrl->done or max_iters iterations; iteration t
+// reads p[first_src ^ (t & 1)].  sync: >= 32 device words (zeroed here).  fixed != 0: smoother
+// mode, no exit tests.
+int sor_persist_available();
+int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pmap0,
+                       const CUtensorMap* pmap1, const CUtensorMap* rhs_map, double* p0, double* p1,
+                       int first_src, int bx, int by, int bz_lo, int bz_hi, SorCtrl* ctrl,
+                       unsigned long long* sync, int max_iters, double eps, int kmax, int idyn,
+                       double factor, int fixed, const PeerSync* peer);
 // end-of-iteration control: exits and dynamic omega, src/poisson.f90:110-122
 int launch_sor_control(cudaStream_t st, SorCtrl* ctrl, double eps, int kmax, int idyn,
                        double factor);

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <utility>
 
 #include "session.h"
@@ -115,6 +116,71 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         }
     }
     const double factor = sor_factor(s);
+    s->last_sor_path = 0;
+    const bool speculate_p = s->spec_arm && tma && same_bc && id_pp == O3D_F_PP && !multi;
+    s->spec_state = 0;
+    // ---- persistent path: the whole solve in one cooperative launch (sor_persist_kernel.cu) ----
+    // O3D_SOR_PERSIST=0 or a forced host poll interval (sor_check_every) keep the launch-per-pass
+    // loop below, which stays the bitwise reference of this path.
+    {
+        const char* e_p = getenv("O3D_SOR_PERSIST");
+        bool persist = tma && !(e_p && e_p[0] == '0') && !seam_split && c.sor_check_every <= 0 &&
+                       c.kmax >= 1 && id_pp == O3D_F_PP && sor_persist_available();
+        PeerSync peer;
+        memset(&peer, 0, sizeof(peer));
+        if (persist && multi) {
+            const char* e_peer = getenv("O3D_SOR_PEER");
+            if (seams || (e_peer && e_peer[0] == '0') || comm_peer_setup(s) ||
+                comm_peer_args(s, &peer))
+                persist = false;  // NCCL halos + all-reduce per sweep, below
+        }
+        if (persist) {
+            if (multi) {
+                // ghost planes of the initial iterate (2) and of the right-hand side (1; constant
+                // over the solve): one grouped NCCL exchange, stream-ordered before the kernel.
+                // Every later iterate travels inside the kernel through peer memory.
+                const long long ioff0 = interior_offset(s->g);
+                double* bases[2] = {pp - ioff0, const_cast<double*>(rhs) - ioff0};
+                const int widths[2] = {2, 1};
+                if (comm_exchange_async(s, bases, widths, 2, s->sor_variant != 2))
+                    return O3D_ERR_COMM;
+                const int rcw = comm_wait(s);
+                if (rcw) return rcw;
+            }
+            span_begin(s, ST_SOR);
+            const int lrc = launch_sor_persist(
+                s->st, a, sor_tmap(s, O3D_F_PP), sor_tmap(s, O3D_F_PP2), sor_tmap(s, id_rhs), pp, alt,
+                0, a.mx, a.my, a.mz_lo, a.mz_hi, s->ctrl_d, s->persist_sync_d, c.kmax, c.eps, c.kmax,
+                c.idyn, factor, 0, multi ? &peer : nullptr);
+            if (lrc == 1) return O3D_ERR_CUDA;
+            if (lrc == 0) {
+                span_end(s, ST_SOR, 0);
+                s->last_sor_path = 1 | (multi ? 2 : 0);
+                O3D_CUDA_CHECK(cudaMemcpyAsync(h, s->ctrl_d, sizeof(SorCtrl), cudaMemcpyDeviceToHost,
+                                               s->st));
+                O3D_CUDA_CHECK(cudaEventRecord(s->ev_ctrl, s->st));
+                if (speculate_p) {
+                    // the projection correction, gated on the solver's outcome, runs while the
+                    // host wakes up and queues the next step
+                    const int rc = spec_correct_launch(s);
+                    if (rc) return rc;
+                    s->spec_state = 2;
+                }
+                O3D_CUDA_CHECK(cudaEventSynchronize(s->ev_ctrl));
+                // the guard of the PREVIOUS correction has landed by now (the copy queued just
+                // above may or may not have: the flag is sticky, either reading is valid)
+                if (s->flag_pending && *s->flag_h) s->diverged = 1;
+                if (h->done == 9) {
+                    set_error("persistent SOR: a grid barrier or a peer rank timed out");
+                    return O3D_ERR_COMM;
+                }
+                if (multi) s->peer_iter_base += (unsigned long long)h->iter;
+                goto finished;
+            }
+            // lrc == 2: not applicable here, fall through
+        }
+    }
+    {
     int launched = 0;
     int batch = s->last_iters > 0 ? s->last_iters : 8;
     if (batch > 64) batch = 64;
@@ -215,14 +281,20 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         if (c.sor_check_every > 0) batch = c.sor_check_every;
         if (wavefront) batch = 1;
     }
+    }
+finished:
     if (fused && (h->iter & 1)) {
         // an odd number of ping-pong passes left the iterate in the alternate buffer: swap the
         // two physical fields (O(1), no copy)
-        std::swap(s->base[O3D_F_PP], s->base[O3D_F_PP2]);
-        std::swap(s->tmap[O3D_F_PP], s->tmap[O3D_F_PP2]);
-        std::swap(s->tmap_sor[O3D_F_PP], s->tmap_sor[O3D_F_PP2]);
-        std::swap(s->tmap_st[O3D_F_PP], s->tmap_st[O3D_F_PP2]);
-        std::swap(s->tmap_sor_ok[O3D_F_PP], s->tmap_sor_ok[O3D_F_PP2]);
+        if (id_pp == O3D_F_PP) {
+            swap_pp(s);
+        } else {
+            std::swap(s->base[id_pp], s->base[O3D_F_PP2]);
+            std::swap(s->tmap[id_pp], s->tmap[O3D_F_PP2]);
+            std::swap(s->tmap_sor[id_pp], s->tmap_sor[O3D_F_PP2]);
+            std::swap(s->tmap_st[id_pp], s->tmap_st[O3D_F_PP2]);
+            std::swap(s->tmap_sor_ok[id_pp], s->tmap_sor_ok[O3D_F_PP2]);
+        }
     }
     touch(s, O3D_F_PP);
     touch(s, O3D_F_PP2);
@@ -290,13 +362,7 @@ int sor_fixed_sweeps(o3d_session* s, const double* rhs, int sweeps, SorCtrl* ctr
                 if (launch_sor_rb(s->st, sa, colour, 1, ctrl, 1)) return O3D_ERR_CUDA;
         }
     }
-    if (sweeps & 1) {
-        std::swap(s->base[O3D_F_PP], s->base[O3D_F_PP2]);
-        std::swap(s->tmap[O3D_F_PP], s->tmap[O3D_F_PP2]);
-        std::swap(s->tmap_sor[O3D_F_PP], s->tmap_sor[O3D_F_PP2]);
-        std::swap(s->tmap_st[O3D_F_PP], s->tmap_st[O3D_F_PP2]);
-        std::swap(s->tmap_sor_ok[O3D_F_PP], s->tmap_sor_ok[O3D_F_PP2]);
-    }
+    if (sweeps & 1) swap_pp(s);
     touch(s, O3D_F_PP);
     touch(s, O3D_F_PP2);
     if (same_bc) {  // the last pass (and the seam sweeps) wrote the ghost images of what they stored

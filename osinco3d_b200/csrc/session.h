@@ -11,6 +11,7 @@ struct Comm;  // z-slab halo exchange + reductions over NCCL (comm.cu)
 struct MgHierarchy;  // level arrays + transfer tables of the V-cycle (multigrid.cu)
 struct IoEngine;     // asynchronous field output: staging buffers, I/O stream, writer thread (io.cu)
 struct Pipe;         // copy streams + staging slots of the pipelined host-pointer procedures (pipeline.cu)
+struct PeerState;    // CUDA-IPC mappings of the other ranks' pp buffers and sync blocks (comm.cu)
 }
 
 struct o3d_session {
@@ -46,6 +47,15 @@ struct o3d_session {
     o3d::SorCtrl* ctrl_d;
     o3d::SorCtrl* ctrl_h;  // pinned
     unsigned long long* seam_sync_d;  // grid-barrier / finish counters of sor_seam_fused_kernel
+    // persistent SOR (sor_persist_kernel.cu): grid-barrier words; event recorded once the control
+    // block of a finished solve is on its way to the host (the gated correction runs behind it)
+    unsigned long long* persist_sync_d;
+    cudaEvent_t ev_ctrl;
+    int pp_phys;           // which of the two physical pp allocations is O3D_F_PP now (0: the original)
+    o3d::PeerState* peers; // z slabs: peer-mapped neighbours, set up lazily by the first solve
+    int peers_tried;
+    unsigned long long peer_iter_base;  // iterations of all earlier peer-memory solves
+    int last_sor_path;     // bit 0: persistent kernel, bit 1: peer-memory halos (last solve)
     int sor_variant;       // 0: _0000, 1: _0011, 2: _111111
     int last_iters;
     double omega;
@@ -179,6 +189,15 @@ int comm_wait(o3d_session* s);
 int split_edge(const o3d_session* s);
 int launch_overlapped(o3d_session* s, const std::function<int(cudaStream_t, int, int)>& launch);
 int comm_allreduce(o3d_session* s, double* dev, int n, int op /* RED_* */);
+// Collective, lazy: map the neighbours' two pp allocations and every rank's PeerBlock through CUDA
+// IPC.  Returns 0 and fills `out` for this rank when the peer path is usable (all ranks agree),
+// non-zero otherwise (the solver then keeps the NCCL path).  p_phys0 / p_phys1: allocation bases
+// of this rank's two physical pp buffers.
+int comm_peer_setup(o3d_session* s);
+// PeerSync for a solve whose first iteration reads the buffer that is O3D_F_PP now
+int comm_peer_args(o3d_session* s, PeerSync* out);
+// swap the roles of O3D_F_PP and O3D_F_PP2 (O(1); after an odd number of ping-pong passes)
+void swap_pp(o3d_session* s);
 // rank r produced buf[first[r] .. first[r] + count[r]); replicate all chunks on every rank
 int comm_allgather_chunks(o3d_session* s, double* buf, const long long* first,
                           const long long* count);

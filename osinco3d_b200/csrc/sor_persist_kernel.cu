@@ -1,0 +1,616 @@
+// sor_persist_kernel.cu -- ALL iterations of one red-black SOR solve in ONE persistent launch
+// (the pressure Poisson solve, src/poisson.f90:6-381; exit tests and dynamic omega :110-122).
+//
+// sor_tma_kernel.cu does one red+black iteration per launch, followed by a 1-thread control
+// kernel (or the cooperative seam kernel) and a host poll every few iterations.  On the shipped
+// grids (4.7 - 17 M points, 11 - 84 iterations per time step) that is launch- and poll-bound.
+// Here a co-resident grid (cooperative launch, 3 CTAs per SM) keeps iterating:
+//
+//   iteration t:  every CTA sweeps its (tile, z-chunk) items -- the same TMA-staged, ping-pong
+//                 red+black pass as sor_tma_kernel, bit for bit the same arithmetic;
+//                 [odd periodic extents: grid barrier, odd red seam class, grid barrier, odd black
+//                  seam class -- the in-place class sweeps of sor_kernels.cu on the new iterate]
+//                 grid barrier; the LAST CTA to arrive evaluates dmax < eps, the stall exit,
+//                 kmax and the dynamic-omega rule (sor_control_step) before it releases the
+//                 others, which then read `done` / `omega` and go on or leave.
+//
+// No host round trip and no launch inside the solve: the host enqueues the kernel and (o3d_step)
+// the projection correction gated on its outcome.  Same class order and arithmetic as the
+// launch-per-pass path => bitwise equal iterates, iteration counts and omega history
+// (tests/test_gpu_poisson.py::test_persistent_solve_equals_launch_per_pass_bitwise).
+//
+// Hot loop, written for instruction count (the pass is co-limited by instruction issue):
+//   * a thread owns a y-pair = one red + one black cell per plane, whose roles alternate from
+//     plane to plane: the march is unrolled by two so the roles are compile-time;
+//   * the red value a thread computes for plane k+2 stays in a register until plane k is stored;
+//   * max|p_new - p| is kept per role with a 3-instruction compare/select and masked once per
+//     item (a cell outside the grid never contributes; ring / ghost / next-chunk cells a CTA
+//     recomputes are real grid points with identical bits, and max is idempotent);
+//   * ghost-image stores (boundary tiles / planes only) live in a noinline function so that none of
+//     their address arithmetic is hoisted into the interior path.
+//
+// Z slabs (nranks > 1): the two boundary planes per side of the new iterate are stored straight
+// into the neighbour rank's ghost planes through peer-mapped pointers (CUDA IPC over NVLink) by
+// the CTAs that compute them, followed by a system-scope release on a counter in the neighbour's
+// memory; a CTA whose chunk touches a slab end acquires that counter before it stages ghost
+// planes.  The residual maximum travels through per-rank slots + flags in peer memory and is
+// combined by the controlling CTA of every rank (identical inputs -> identical decisions).  No
+// NCCL call and no host inside the iteration.
+#include <cstring>
+
+#include "kernels.h"
+#include "sor_common.cuh"
+#include "tma.cuh"
+
+namespace o3d {
+namespace {
+
+constexpr int GTX = 32, GTY = 16, GNT = 256;
+constexpr int GBX = GTX + 4, GBY = GTY + 4, GPL = GBX * GBY;  // 36 x 20 = 720 cells, 5760 B
+constexpr int GP = 2;                                         // planes prefetched ahead
+constexpr int GNP = 5 + GP, GNR = 3 + GP, GNB = GP + 1;       // p stages, rhs stages, barriers
+constexpr int GSMEM = (GNP + GNR) * GPL * 8 + GNB * 8 + 32 * 8;
+constexpr long long SPIN_LIMIT = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
+
+struct PersistArgs {
+    SorArgs s;            // geometry, operator, neighbour rule; s.pp / s.rhs unused by the pass
+    double* p[2];         // interior origins of the two ping-pong buffers
+    int bx, by, bz_lo, bz_hi;  // closures for the ghost images of the new iterate
+    int tiles_x, tiles_y, nch, zchunk;
+    int first_src;        // buffer read by the first iteration of this launch
+    int max_iters;        // iterations this launch may run
+    double eps, factor;
+    int kmax, idyn;
+    int fixed;            // smoother mode: no exit tests, the control step only counts
+    long long nxf, nyf, nzf;  // sizes of the x / y / z seam planes (SEAM)
+    // ---- z slabs: peer-mapped neighbours (null: none on that side) ----
+    PeerSync peer;
+};
+
+struct alignas(64) PersistMaps {
+    CUtensorMap p[2], rhs;
+};
+
+template <int OFF>
+__device__ __forceinline__ double lds(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// generic-proxy global writes <-> async-proxy (TMA) reads of the same addresses
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// ghost images of the pair (vA at outp[0], vB at outp[sy]) of plane k -- boundary tiles / planes
+// only -- and, on a z slab, the copies of the two planes next to a rank boundary in the
+// neighbour's ghost planes (interior value + its x / y images; the neighbour's TMA boxes read them)
+__device__ __noinline__ void store_pair_extras(double* outp, double vA, double vB, bool inA,
+                                               bool inB, Img2 ix, Img2 iyA, Img2 iyB, int k, int nz,
+                                               int bz_lo, int bz_hi, long long sy, long long sz,
+                                               double* peer_lo, double* peer_hi) {
+    const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
+    if (ix.lo | ix.hi | iyA.lo | iyA.hi | iyB.lo | iyB.hi | iz.lo | iz.hi) {
+        if (inA) store_images(outp, 0, vA, ix, iyA.lo * sy, iyA.hi * sy, iz.lo * sz, iz.hi * sz);
+        if (inB) store_images(outp, sy, vB, ix, iyB.lo * sy, iyB.hi * sy, iz.lo * sz, iz.hi * sz);
+    }
+    // peer_lo / peer_hi: this pair's position in plane k of the neighbour's frame (null: no push)
+    double* const pq[2] = {k < 2 ? peer_lo : nullptr, k >= nz - 2 ? peer_hi : nullptr};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        double* o = pq[q];
+        if (!o) continue;
+        if (inA) {
+            o[0] = vA;
+            store_images(o, 0, vA, ix, iyA.lo * sy, iyA.hi * sy, 0, 0);
+        }
+        if (inB) {
+            o[sy] = vB;
+            store_images(o, sy, vB, ix, iyB.lo * sy, iyB.hi * sy, 0, 0);
+        }
+    }
+}
+
+// exit tests + dynamic omega on a private copy (every field of the control block is read and
+// written through volatile accesses: other SMs updated it in earlier iterations)
+__device__ __forceinline__ void control_step_volatile(SorCtrl* ctrl, unsigned long long dmax_bits,
+                                                      double eps, int kmax, int idyn, double factor,
+                                                      int fixed) {
+    volatile SorCtrl* v = ctrl;
+    SorCtrl c;
+    c.dmax_bits = dmax_bits;
+    c.omega = v->omega, c.dmax_old = v->dmax_old, c.dmax_last = v->dmax_last;
+    c.iter = v->iter, c.done = v->done;
+    if (fixed) {
+        c.iter += 1, c.dmax_bits = 0ull;
+    } else {
+        sor_control_step(&c, eps, kmax, idyn, factor);
+    }
+    v->dmax_bits = c.dmax_bits;
+    v->omega = c.omega, v->dmax_old = c.dmax_old, v->dmax_last = c.dmax_last;
+    v->iter = c.iter;
+    v->done = c.done;
+}
+
+template <bool SEAM, bool MULTI>
+__global__ void __launch_bounds__(GNT, 3)
+    sor_persist_kernel(const __grid_constant__ PersistMaps maps, const PersistArgs a, SorCtrl* ctrl,
+                       unsigned long long* sync) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sp = reinterpret_cast<double*>(smem_raw);
+    double* sr = sp + GNP * GPL;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sr + GNR * GPL);
+    double* red = reinterpret_cast<double*>(bars + GNB);
+    const int tid = threadIdx.x;
+    const uint32_t sp_s = smem_u32(sp), sr_s = smem_u32(sr), bars_s = smem_u32(bars);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GNB; ++s) mbar_init(bars_s + 8 * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const SorArgs& g = a.s;
+    const unsigned G = gridDim.x;
+    const int ntiles = a.tiles_x * a.tiles_y, nitems = ntiles * a.nch;
+    unsigned long long epoch = 0;  // grid barriers passed since launch (thread 0)
+    uint32_t gbase = 0;            // TMA groups issued (= waited for) by this CTA so far
+    constexpr uint32_t PLB = GPL * 8;
+    const uint32_t p_end = sp_s + GNP * PLB, r_end = sr_s + GNR * PLB;
+    const int tx = tid & 31, typ = tid >> 5;
+    const int own = (2 + 2 * typ) * GBX + 2 + tx;
+    const uint32_t ownA8 = own * 8, ownB8 = (own + GBX) * 8;
+    // ring-1 pairs (48 threads, warps 0 and 1): each holds exactly one red cell in every plane
+    int rcell = -1, rstep = 0, rlx = 0, rly = 0;
+    if (tid < 48) {
+        if (tid < 16) rlx = 2 + 2 * tid, rly = 1, rstep = 1;                       // below the tile
+        else if (tid < 32) rlx = 2 + 2 * (tid - 16), rly = GBY - 2, rstep = 1;     // above
+        else if (tid < 40) rlx = 1, rly = 2 + 2 * (tid - 32), rstep = GBX;         // left
+        else rlx = GBX - 2, rly = 2 + 2 * (tid - 40), rstep = GBX;                 // right
+        rcell = rly * GBX + rlx;
+    }
+    const bool has_ring = rcell >= 0;
+    const uint32_t ring0 = has_ring ? rcell * 8 : 0, ring1 = has_ring ? (rcell + rstep) * 8 : 0;
+    constexpr bool multi = MULTI;
+
+    // grid barrier; `last` runs in thread 0 of the last CTA to arrive, before the others go on
+    auto grid_barrier = [&](auto&& last) {
+        __syncthreads();
+        if (tid == 0) {
+            epoch += 1;
+            __threadfence();
+            const unsigned long long t = atomicAdd(&sync[0], 1ull);
+            if (t + 1 == epoch * G) {
+                last();
+                __threadfence();
+                atomicExch(&sync[16], epoch);
+            } else {
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(&sync[16]) < epoch) {
+                    if (clock64() - t0 > SPIN_LIMIT) {
+                        atomicExch(&ctrl->done, 9);
+                        break;
+                    }
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    };
+
+    for (int it = 0; it < a.max_iters; ++it) {
+        if (*((volatile int*)&ctrl->done)) break;  // uniform over the grid (read after a barrier)
+        const double omega = *((volatile double*)&ctrl->omega);
+        const double one_m_omega = 1.0 - omega;
+        const int src = a.first_src ^ (it & 1);
+        const CUtensorMap* pmap = &maps.p[src];
+        double* const p_new = a.p[src ^ 1];
+        // iterations completed by every rank before this one, over the whole session
+        const unsigned long long T = a.peer.iter_base + (unsigned long long)it;
+        double dmax = 0.0;
+
+        for (int item = blockIdx.x; item < nitems; item += G) {
+            const int tile = item % ntiles, ch = item / ntiles;
+            const int i0 = (tile % a.tiles_x) * GTX, j0 = (tile / a.tiles_x) * GTY;
+            const int kb = ch * a.zchunk, ke = min(g.nz, kb + a.zchunk);
+            const int niter = ke - kb;
+            const int ngroups = niter > 1 ? niter - 1 : 1;  // group n feeds red(kb + n + 2)
+            __syncthreads();  // the previous item's stages (and `red`) are no longer read
+
+            // p plane q lives in stage (q - (kb-2)) mod GNP, rhs plane q in (q - (kb-1)) mod GNR
+            const int cx = GX + i0 - 2, cy = GH + j0 - 2;
+            auto issue_p = [&](int plane, uint32_t bar) {
+                const unsigned st = (unsigned)(plane - (kb - 2)) % GNP;
+                tma_load_3d(sp_s + st * PLB, pmap, bar, cx, cy, GH + plane);
+            };
+            auto issue_r = [&](int plane, uint32_t bar) {
+                const unsigned st = (unsigned)(plane - (kb - 1)) % GNR;
+                tma_load_3d(sr_s + st * PLB, &maps.rhs, bar, cx, cy, GH + plane);
+            };
+            auto issue_group = [&](int n) {
+                const uint32_t bar = bars_s + 8 * ((gbase + n) % GNB);
+                if (n == 0) {
+                    mbar_expect_tx(bar, (6 + 4) * PLB);
+#pragma unroll
+                    for (int q = -2; q <= 3; ++q) issue_p(kb + q, bar);
+#pragma unroll
+                    for (int q = -1; q <= 2; ++q) issue_r(kb + q, bar);
+                } else {
+                    mbar_expect_tx(bar, 2 * PLB);
+                    issue_p(kb + n + 3, bar);
+                    issue_r(kb + n + 2, bar);
+                }
+            };
+            auto wait_group = [&](int n) {
+                const uint32_t q = gbase + n;
+                mbar_wait(bars_s + 8 * (q % GNB), (q / GNB) & 1u);
+            };
+            if (tid == 0) {
+                if (multi && T > 0) {
+                    // ghost planes of the previous iterate come from the neighbours' CTAs: two
+                    // planes per tile and side, counted in OUR memory (iteration 0 of a solve was
+                    // exchanged by the host before the launch)
+                    const unsigned long long need = 2ull * ntiles * T;
+                    const long long t0 = clock64();
+                    if (kb < 2 && a.peer.has_lo)
+                        while (ld_acquire_sys(&a.peer.mine->halo_cnt[0]) < need)
+                            if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                    if (ke + 1 >= g.nz && a.peer.has_hi)
+                        while (ld_acquire_sys(&a.peer.mine->halo_cnt[1]) < need)
+                            if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                }
+                fence_proxy_async_global();
+                for (int n = 0; n < GP && n < ngroups; ++n) issue_group(n);
+            }
+
+            const int gi = i0 + tx, gj = j0 + 2 * typ;
+            const bool inA = gi < g.nx && gj < g.ny, inB = gi < g.nx && gj + 1 < g.ny;
+            // role 0 = the member of the pair that is red in plane kb (and kb+2, ...)
+            const int m0 = (gi + gj + g.gz0 + kb) & 1;  // 1: member B
+            const uint32_t cell0 = m0 ? ownB8 : ownA8, cell1 = m0 ? ownA8 : ownB8;
+            const int rm0 = has_ring ? ((i0 - 2 + rlx + j0 - 2 + rly + g.gz0 + kb) & 1) : 0;
+            const uint32_t rcl0 = rm0 ? ring1 : ring0, rcl1 = rm0 ? ring0 : ring1;
+            // SEAM: seam parity of the pair's members in x,y and of the ring pair's cells (2 bits
+            // each: 0 / 1 = parity, 2 = ghost cell of an odd periodic axis, never updated)
+            int par0 = 0, par1 = 0, rcode0 = 0, rcode1 = 0;
+            if (SEAM) {
+                const int sx = (g.seam_x && gi == g.nx - 1) ? 1 : 0;
+                const int pA = sx ^ ((g.seam_y && gj == g.ny - 1) ? 1 : 0);
+                const int pB = sx ^ ((g.seam_y && gj + 1 == g.ny - 1) ? 1 : 0);
+                par0 = m0 ? pB : pA, par1 = m0 ? pA : pB;
+                if (has_ring) {
+                    int code[2];
+                    for (int m = 0; m < 2; ++m) {
+                        const int c = rcell + m * rstep;
+                        const int ri = i0 - 2 + c % GBX, rj = j0 - 2 + c / GBX;
+                        int cd = 0;
+                        if (g.seam_x) cd = (ri < 0 || ri >= g.nx) ? 2 : (ri == g.nx - 1);
+                        if (g.seam_y && cd != 2)
+                            cd = (rj < 0 || rj >= g.ny) ? 2 : (cd ^ (rj == g.ny - 1 ? 1 : 0));
+                        code[m] = cd;
+                    }
+                    rcode0 = rm0 ? code[1] : code[0], rcode1 = rm0 ? code[0] : code[1];
+                }
+            }
+            auto zseam = [&](int q) -> int {
+                if (!SEAM || !g.seam_z) return 0;
+                const int gk = g.gz0 + q;
+                return (gk < 0 || gk >= g.gnz) ? 2 : (gk == g.gnz - 1 ? 1 : 0);
+            };
+            const Img2 ix = image_offsets(gi, g.nx, a.bx, a.bx);
+            const Img2 iyA = image_offsets(gj, g.ny, a.by, a.by);
+            const Img2 iyB = image_offsets(gj + 1, g.ny, a.by, a.by);
+            const bool xy_img = (ix.lo | ix.hi | iyA.lo | iyA.hi | iyB.lo | iyB.hi) != 0;
+            // planes whose points have z images or copies in a neighbour's ghost planes
+            int zslow_lo = (a.bz_lo == BM_MIRROR || a.bz_hi == BM_WRAP) ? R : -1;  // k <= zslow_lo
+            int zslow_hi = (a.bz_hi == BM_MIRROR || a.bz_lo == BM_WRAP) ? g.nz - 1 - R : g.nz;
+            double* peer_lo = nullptr;
+            double* peer_hi = nullptr;
+            if (multi) {
+                const long long pair = (long long)gj * g.sy + gi;
+                // my planes 0, 1 are the lower neighbour's ghost planes nz_lo, nz_lo + 1; my
+                // planes nz-2, nz-1 the upper neighbour's ghost planes -2, -1
+                // (pointers to this pair in plane kb of the neighbour's frame, advanced per plane)
+                if (a.peer.has_lo) {
+                    peer_lo = a.peer.lo_p[src ^ 1] + (long long)(a.peer.lo_nz + kb) * g.sz + pair;
+                    zslow_lo = max(zslow_lo, 1);
+                }
+                if (a.peer.has_hi) {
+                    peer_hi = a.peer.hi_p[src ^ 1] + (long long)(kb - g.nz) * g.sz + pair;
+                    zslow_hi = min(zslow_hi, g.nz - 2);
+                }
+            }
+
+            auto nextp = [&](uint32_t x) { return x + PLB == p_end ? sp_s : x + PLB; };
+            auto nextr = [&](uint32_t x) { return x + PLB == r_end ? sr_s : x + PLB; };
+            // SOR update of the cell at byte offset c of the plane at a0 (am / ap = planes below /
+            // above, ar = rhs plane): src/poisson.f90:95-102 with "/ A" as "* (1/A)"; returns the
+            // relaxed value, d = |p_new - p_old|, pc = the old value
+            auto update = [&](uint32_t am, uint32_t a0, uint32_t ap, uint32_t ar, uint32_t c,
+                              double& d, double& pc) -> double {
+                const uint32_t c0 = a0 + c;
+                pc = lds<0>(c0);
+                const double w = lds<-8>(c0), e = lds<8>(c0);
+                const double sn = lds<-GBX * 8>(c0), nn = lds<GBX * 8>(c0);
+                const double bb = lds<0>(am + c), tt = lds<0>(ap + c), rr = lds<0>(ar + c);
+                const double pn =
+                    (-(g.oneondx2 * (w + e)) - g.oneondy2 * (sn + nn) - g.oneondz2 * (bb + tt) + rr) *
+                    g.invA;
+                d = fabs(pn - pc);                     // :100
+                return one_m_omega * pc + omega * pn;  // :102
+            };
+            double dm0 = 0.0, dm1 = 0.0;  // max d of the role-0 / role-1 member
+            // red half-sweep of the plane at a0 (local plane q) for the member of role ROLE and the
+            // ring cell of that role; returns the member's new value (also stored in the stage)
+            auto red_plane = [&](int q, uint32_t am, uint32_t a0, uint32_t ap, uint32_t ar,
+                                 const int role) -> double {
+                const uint32_t c = role ? cell1 : cell0;
+                double d, pc;
+                double v = update(am, a0, ap, ar, c, d, pc);
+                bool ring_on = has_ring;
+                if (SEAM) {
+                    const int zs = zseam(q);
+                    if (zs == 2 || (((role ? par1 : par0) ^ zs) & 1)) v = pc, d = 0.0;  // odd class
+                    const int code = role ? rcode1 : rcode0;
+                    ring_on = ring_on && zs != 2 && code != 2 && !((code ^ zs) & 1);
+                }
+                if (ring_on) {
+                    const uint32_t rc = role ? rcl1 : rcl0;
+                    double dr, pr;
+                    const double vr = update(am, a0, ap, ar, rc, dr, pr);
+                    sts(a0 + rc, vr);
+                }
+                sts(a0 + c, v);
+                if (role) dm1 = d > dm1 ? d : dm1;
+                else dm0 = d > dm0 ? d : dm0;
+                return v;
+            };
+
+            wait_group(0);  // p planes kb-2 .. kb+3 in stages 0 .. 5, rhs kb-1 .. kb+2 in 0 .. 3
+            double vr0, vr1;  // new red value of the role-0 / role-1 member, until its plane is stored
+            (void)red_plane(kb - 1, sp_s, sp_s + PLB, sp_s + 2 * PLB, sr_s, 1);
+            vr0 = red_plane(kb, sp_s + PLB, sp_s + 2 * PLB, sp_s + 3 * PLB, sr_s + PLB, 0);
+            vr1 = red_plane(kb + 1, sp_s + 2 * PLB, sp_s + 3 * PLB, sp_s + 4 * PLB, sr_s + 2 * PLB, 1);
+
+            uint32_t a_m1 = sp_s + PLB, a_0 = sp_s + 2 * PLB, a_1 = sp_s + 3 * PLB,
+                     a_2 = sp_s + 4 * PLB, a_3 = sp_s + 5 * PLB;
+            uint32_t ar_0 = sr_s + PLB, ar_2 = sr_s + 3 * PLB;
+            double* outp = p_new + (long long)kb * g.sz + (long long)gj * g.sy + gi;
+            // the role-0 member is A (outp[0]) unless m0
+            const long long off0 = m0 ? g.sy : 0, off1 = m0 ? 0 : g.sy;
+            const bool in0 = m0 ? inB : inA, in1 = m0 ? inA : inB;
+
+            auto step = [&](int k, const int role) {
+                const int n = k - kb;
+                __syncthreads();  // step k-1 done: its oldest stages may be refilled; red(k+1) visible
+                if (tid == 0 && n + GP < ngroups) issue_group(n + GP);
+                if (n >= 1 && n < ngroups) wait_group(n);
+                // plane k: the member of role ROLE is red (value kept in a register), the other black
+                const double vred = role ? vr1 : vr0;
+                if (k + 2 <= ke) {
+                    const double v = red_plane(k + 2, a_1, a_2, a_3, ar_2, role);
+                    if (role) vr1 = v;
+                    else vr0 = v;
+                }
+                double d, pcb;
+                double vb = update(a_m1, a_0, a_1, ar_0, role ? cell0 : cell1, d, pcb);
+                if (SEAM && (((role ? par0 : par1) ^ zseam(k)) & 1)) vb = pcb, d = 0.0;  // odd class
+                if (role) dm0 = d > dm0 ? d : dm0;
+                else dm1 = d > dm1 ? d : dm1;
+                const double v0 = role ? vb : vred, v1 = role ? vred : vb;
+                if (in0) outp[off0] = v0;
+                if (in1) outp[off1] = v1;
+                if (xy_img || k <= zslow_lo || k >= zslow_hi)
+                    store_pair_extras(outp, m0 ? v1 : v0, m0 ? v0 : v1, inA, inB, ix, iyA, iyB, k,
+                                      g.nz, a.bz_lo, a.bz_hi, g.sy, g.sz, peer_lo, peer_hi);
+                outp += g.sz;
+                if (multi) {
+                    if (peer_lo) peer_lo += g.sz;
+                    if (peer_hi) peer_hi += g.sz;
+                }
+                a_m1 = a_0, a_0 = a_1, a_1 = a_2, a_2 = a_3, a_3 = nextp(a_3);
+                ar_0 = nextr(ar_0), ar_2 = nextr(ar_2);
+            };
+            int k = kb;
+            for (; k + 1 < ke; k += 2) {
+                step(k, 0);
+                step(k + 1, 1);
+            }
+            if (k < ke) step(k, 0);
+            gbase += ngroups;
+            {
+                const double dA = m0 ? dm1 : dm0, dB = m0 ? dm0 : dm1;
+                if (inA) dmax = dA > dmax ? dA : dmax;
+                if (inB) dmax = dB > dmax ? dB : dmax;
+            }
+            if (multi) {
+                // this item's copies in the neighbours' ghost planes are complete: release them
+                const int nlo = a.peer.has_lo ? max(0, min(ke, 2) - kb) : 0;
+                const int nhi = a.peer.has_hi ? max(0, ke - max(kb, g.nz - 2)) : 0;
+                if (nlo | nhi) {
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (nlo) red_release_sys_add(&a.peer.lo->halo_cnt[1], (unsigned long long)nlo);
+                        if (nhi) red_release_sys_add(&a.peer.hi->halo_cnt[0], (unsigned long long)nhi);
+                    }
+                }
+            }
+        }
+        {
+            const double bm = block_max(dmax, red);
+            if (tid == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+        }
+        fence_proxy_async_global();  // this iteration's stores -> the next iteration's TMA loads
+
+        if (SEAM) {
+            // the two thin odd classes, in place on the new iterate, rewriting the ghost images of
+            // what they touch (sor_kernels.cu); single rank only (slabs keep the split launches)
+            SorArgs sa = g;
+            sa.pp = p_new;
+            const long long tot = a.nxf + a.nyf + a.nzf;
+            const long long stride = (long long)G * GNT;
+            double dm = 0.0;
+            for (int colour = 0; colour < 2; ++colour) {
+                grid_barrier([] {});
+                for (long long t = (long long)blockIdx.x * GNT + tid; t < tot; t += stride) {
+                    int i, j, kk;
+                    bool ok;
+                    seam_point_of(sa, t, a.nxf, a.nyf, a.nzf, i, j, kk, ok);
+                    if (ok) {
+                        const int gk = sa.gz0 + kk;
+                        if (((i + j + gk) & 1) == colour && (seam_pop(sa, i, j, gk) & 1))
+                            dm = fmax(dm, sor_point<true>(sa, i, j, kk, omega));
+                    }
+                }
+            }
+            const double bm = block_max(dm, red);
+            if (tid == 0 && bm > 0.0) atomic_max_nonneg(&ctrl->dmax_bits, bm);
+            fence_proxy_async_global();
+        }
+
+        grid_barrier([&] {
+            unsigned long long bits = *((volatile unsigned long long*)&ctrl->dmax_bits);
+            if (multi) {
+                // all-to-all of the local maxima through peer memory: slot (T & 1, me) + flag on
+                // every rank; then the maximum over all ranks' slots (same inputs on every rank)
+                const int me = a.peer.rank, P = a.peer.nranks;
+                for (int r = 0; r < P; ++r) {
+                    PeerBlock* q = a.peer.all[r];
+                    *((volatile unsigned long long*)&q->dmax_slot[T & 1][me]) = bits;
+                }
+                __threadfence_system();
+                for (int r = 0; r < P; ++r) st_release_sys(&a.peer.all[r]->dmax_flag[me], T + 1);
+                const long long t0 = clock64();
+                for (int r = 0; r < P; ++r) {
+                    while (ld_acquire_sys(&a.peer.mine->dmax_flag[r]) < T + 1)
+                        if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                    const unsigned long long b =
+                        *((volatile unsigned long long*)&a.peer.mine->dmax_slot[T & 1][r]);
+                    bits = b > bits ? b : bits;
+                }
+            }
+            if (*((volatile int*)&ctrl->done) != 9)
+                control_step_volatile(ctrl, bits, a.eps, a.kmax, a.idyn, a.factor, a.fixed);
+        });
+    }
+}
+
+int g_persist_ctas = 0;  // co-resident CTAs (3 per SM x SMs), queried once
+
+int persist_capacity() {
+    if (g_persist_ctas) return g_persist_ctas;
+    if (cudaFuncSetAttribute(sor_persist_kernel<false, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(sor_persist_kernel<true, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(sor_persist_kernel<false, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM) != cudaSuccess)
+        return 0;
+    int dev = 0, sms = 0, coop = 0, per_sm = 0, per_sm2 = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return 0;
+    int per_sm3 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sor_persist_kernel<false, false>, GNT,
+                                                  GSMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, sor_persist_kernel<true, false>, GNT,
+                                                  GSMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, sor_persist_kernel<false, true>, GNT,
+                                                  GSMEM);
+    if (per_sm2 < per_sm) per_sm = per_sm2;
+    if (per_sm3 < per_sm) per_sm = per_sm3;
+    if (per_sm > 3) per_sm = 3;
+    g_persist_ctas = per_sm * sms;
+    return g_persist_ctas;
+}
+
+}  // namespace
+
+// z chunks of the persistent pass: every CTA sweeps ceil(items / G) items per iteration, each
+// costing its planes plus ~2.5 plane-equivalents of pipeline prologue (3 extra red planes, the
+// fill latency); pick the chunk count that minimises waves x (chunk + 2.5), fewer chunks on a tie
+int persist_pick_chunks(int ntiles, int nz, int G) {
+    const char* e = getenv("O3D_NCH_P");
+    if (e && atoi(e) > 0) return atoi(e) > nz / 2 ? (nz / 2 > 0 ? nz / 2 : 1) : atoi(e);
+    int best = 1;
+    double best_cost = 1e300;
+    const int maxch = nz / 4 > 0 ? nz / 4 : 1;
+    for (int nch = 1; nch <= maxch && nch <= 256; ++nch) {
+        const int zc = (nz + nch - 1) / nch;
+        const int real = (nz + zc - 1) / zc;
+        const long long items = (long long)ntiles * real;
+        const long long waves = (items + G - 1) / G;
+        const double cost = (double)waves * (zc + 2.5);
+        if (cost < best_cost - 1e-9) best_cost = cost, best = real;
+    }
+    return best;
+}
+
+int sor_persist_available() { return persist_capacity() > 0; }
+
+int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pmap0,
+                       const CUtensorMap* pmap1, const CUtensorMap* rhs_map, double* p0, double* p1,
+                       int first_src, int bx, int by, int bz_lo, int bz_hi, SorCtrl* ctrl,
+                       unsigned long long* sync, int max_iters, double eps, int kmax, int idyn,
+                       double factor, int fixed, const PeerSync* peer) {
+    const int G_max = persist_capacity();
+    if (G_max <= 0) return 2;
+    PersistMaps maps;
+    maps.p[0] = *pmap0, maps.p[1] = *pmap1, maps.rhs = *rhs_map;
+    PersistArgs f;
+    f.s = a;
+    f.s.pp = nullptr;
+    f.p[0] = p0, f.p[1] = p1;
+    f.bx = bx, f.by = by, f.bz_lo = bz_lo, f.bz_hi = bz_hi;
+    f.tiles_x = (a.nx + GTX - 1) / GTX, f.tiles_y = (a.ny + GTY - 1) / GTY;
+    const int ntiles = f.tiles_x * f.tiles_y;
+    f.nch = persist_pick_chunks(ntiles, a.nz, G_max);
+    f.zchunk = (a.nz + f.nch - 1) / f.nch;
+    f.nch = (a.nz + f.zchunk - 1) / f.zchunk;
+    f.first_src = first_src;
+    f.max_iters = max_iters;
+    f.eps = eps, f.factor = factor, f.kmax = kmax, f.idyn = idyn, f.fixed = fixed;
+    const bool seams = a.seam_x || a.seam_y || a.seam_z;
+    f.nxf = a.seam_x ? (long long)a.ny * a.nz : 0;
+    f.nyf = a.seam_y ? (long long)a.nx * a.nz : 0;
+    f.nzf = a.seam_z ? (long long)a.nx * a.ny : 0;
+    if (peer) f.peer = *peer;
+    else memset(&f.peer, 0, sizeof(f.peer));
+    if (seams && f.peer.nranks > 1) return 2;  // slabs + odd periodic extents: split launches
+    const long long items = (long long)ntiles * f.nch;
+    const unsigned G = (unsigned)(items < G_max ? items : G_max);
+    if (cudaMemsetAsync(sync, 0, 32 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
+    void* args[] = {(void*)&maps, (void*)&f, (void*)&ctrl, (void*)&sync};
+    const void* fn = seams ? (const void*)sor_persist_kernel<true, false>
+                           : (f.peer.nranks > 1 ? (const void*)sor_persist_kernel<false, true>
+                                                : (const void*)sor_persist_kernel<false, false>);
+    const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(GNT), args, GSMEM, st);
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("persistent SOR launch failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace o3d

@@ -202,6 +202,12 @@ class Session:
     def omega(self, v):
         check(lib().o3d_set_omega(self._h, C.c_double(v)))
 
+    def sor_path(self):
+        """(persistent, peer) of the last red-black solve: see o3d_s_sor_path"""
+        a, b = C.c_int(0), C.c_int(0)
+        check(lib().o3d_s_sor_path(self._h, C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
+
     def set_poisson(self, eps, kmax, idyn=0, multigrid=0):
         check(lib().o3d_session_set_poisson(self._h, C.c_double(eps), kmax, idyn, multigrid))
 

@@ -227,3 +227,62 @@ def test_fused_pass_equals_inplace_half_sweeps_bitwise(gpu, variant, shape, idyn
         (ra, pa), (rb, pb) = out["off", kmax], out["fused", kmax]
         assert ra == rb, (kmax, ra, rb)
         assert np.array_equal(pa, pb), (kmax, rel_max(pa, pb))
+
+
+@pytest.mark.parametrize("variant,shape", [
+    ("111111", (96, 80, 70)), ("111111", (40, 33, 29)), ("111111", (130, 20, 9)),
+    ("0000", (64, 48, 40)), ("0000", (65, 49, 37)), ("0000", (71, 34, 41)),
+    ("0011", (64, 37, 24)), ("0011", (67, 40, 35)), ("0011", (33, 16, 8)),
+])
+@pytest.mark.parametrize("idyn", [0, 1])
+def test_persistent_solve_equals_launch_per_pass_bitwise(gpu, variant, shape, idyn, monkeypatch):
+    """The persistent kernel (all iterations of a solve in one cooperative launch: grid barrier
+    between passes, exit tests and dynamic omega of src/poisson.f90:110-122 evaluated by the last
+    CTA to arrive, odd seam classes folded in) against the launch-per-pass path (O3D_SOR_PERSIST=0:
+    one sor_tma_kernel launch + control / seam kernel per iteration, host polls): identical
+    iterates, Fortran `iter`, dmax and omega, for every exit (kmax 1 / 2 / odd / converged),
+    2-colourable and odd-periodic grids, one and several items per CTA."""
+    from osinco3d_b200 import modules as M
+    bc = VARIANTS[variant]
+    d = (0.11, 0.13, 0.17)
+    rhs, _ = consistent_problem(shape, d, bc, 31)
+    p0 = rand_field(shape, 32, 0.1)
+    fn = getattr(M, "poisson_solver_" + variant)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("O3D_SOR_PERSIST", mode)
+        for kmax in (1, 2, 7, 500):
+            p = p0.copy(order="F")
+            out[mode, kmax] = (fn(p, rhs, *d, 1.8, 1e-9, kmax, idyn), p)
+    for kmax in (1, 2, 7, 500):
+        (ra, pa), (rb, pb) = out["0", kmax], out["1", kmax]
+        assert ra == rb, (kmax, ra, rb)
+        assert np.array_equal(pa, pb), (kmax, rel_max(pa, pb))
+    assert out["1", 500][0][2] < out["1", 7][0][2]
+
+
+@pytest.mark.parametrize("bc,n", [((1, 1, 1), 64), ((0, 0, 0), 49), ((0, 1, 0), 48)])
+def test_persistent_steps_equal_launch_per_pass_steps_bitwise(gpu, O, bc, n, monkeypatch):
+    """whole time steps (o3d_step: the correction queued behind the persistent kernel, gated on its
+    outcome, ping-pong parity resolved on the device) == the same steps with one launch per pass
+    and host polls; the session reports which path the last solve took"""
+    PI = 3.141592653589793
+    d = tuple((PI if b else 2 * PI) / (n - 1) for b in bc)
+    g = O.grid(n, n, n, *d, bc)
+    ux, uy, uz, pp, phi = O.init_tgv(g, nscr=1)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("O3D_SOR_PERSIST", mode)
+        cfg = gpu.make_config(n, n, n, *d, bc=bc, re=400.0, dt=0.02 * d[0], itscheme=3, iles=1,
+                              cs=0.17, nscr=1, omega=1.7, eps=1e-6, kmax=500, idyn=1)
+        ses = gpu.Session(cfg)
+        ses.set(ux=ux, uy=uy, uz=uz, pp=pp, phi=phi)
+        iters = [ses.step() for _ in range(6)]
+        assert ses.sor_path() == (mode == "1", False)
+        res[mode] = (iters, ses.omega, ses.last_dmax,
+                     {k: ses.download(k) for k in ("ux", "uy", "uz", "pp", "phi")})
+        ses.close()
+    assert res["0"][:3] == res["1"][:3], (res["0"][:3], res["1"][:3])
+    assert max(res["1"][0]) > 1
+    for k, a in res["0"][3].items():
+        assert np.array_equal(a, res["1"][3][k]), (k, rel_max(a, res["1"][3][k]))
