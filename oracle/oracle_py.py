@@ -22,27 +22,39 @@ class Grid(C.Structure):
                 ("bc", C.c_int * 3), ("sim2d", C.c_int)]
 
 
+_SO_O3 = os.path.join(_HERE, "_build", "libo3d_oracle_O3.so")
+
+
 def build(force=False):
-    if force or not os.path.exists(_SO) or \
-            os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "o3d_oracle.c")):
+    src = os.path.getmtime(os.path.join(_HERE, "o3d_oracle.c"))
+    if force or any(not os.path.exists(f) or os.path.getmtime(f) < src for f in (_SO, _SO_O3)):
         subprocess.check_call(["make", "-C", _HERE, "-s"], env=dict(os.environ, CC="gcc"))
     return _SO
 
 
-_lib = None
+_libs = {False: None, True: None}
+_fast = False
+
+
+def use_fast_build(on):
+    """bench.py's CPU-baseline legs only: route lib() to the -O3 build (the reference's own
+    optimisation level) instead of the strict -O2 parity build"""
+    global _fast
+    _fast = bool(on)
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-        _lib.orc_poisson_sor.restype = C.c_int
-        _lib.orc_poisson_solver.restype = C.c_int
-        _lib.orc_correct_pression.restype = C.c_int
-        _lib.orc_sim_create.restype = C.c_void_p
-        _lib.orc_sim_field.restype = dp
-        _lib.orc_sim_step.restype = C.c_int
-    return _lib
+    if _libs[_fast] is None:
+        build()
+        L = C.CDLL(_SO_O3 if _fast else _SO)
+        L.orc_poisson_sor.restype = C.c_int
+        L.orc_poisson_solver.restype = C.c_int
+        L.orc_correct_pression.restype = C.c_int
+        L.orc_sim_create.restype = C.c_void_p
+        L.orc_sim_field.restype = dp
+        L.orc_sim_step.restype = C.c_int
+        _libs[_fast] = L
+    return _libs[_fast]
 
 
 def _p(a):

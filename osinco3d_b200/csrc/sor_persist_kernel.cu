@@ -540,6 +540,10 @@ int persist_capacity() {
     if (per_sm2 < per_sm) per_sm = per_sm2;
     if (per_sm3 < per_sm) per_sm = per_sm3;
     if (per_sm > 3) per_sm = 3;
+    {   // tuning override: co-resident CTAs per SM
+        const char* e = getenv("O3D_PERSIST_CTAS");
+        if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
+    }
     g_persist_ctas = per_sm * sms;
     return g_persist_ctas;
 }
