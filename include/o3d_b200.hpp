@@ -205,6 +205,26 @@ public:
         return iters;
     }
     void sync() { check(o3d_sync(s_), "o3d_sync"); }
+    // ---- what the driver does around the step, src/osinco3d_main.f90:104,116-188 ----
+    // everything :116-128 prints per step (include/o3d_b200.h: o3d_s_step_diagnostics)
+    void step_diagnostics(double out23[23]) {
+        check(o3d_s_step_diagnostics(s_, out23), "o3d_s_step_diagnostics");
+    }
+    void old_values() { check(o3d_s_old_values(s_), "o3d_s_old_values"); }               // :104
+    void calculate_residuals(double dt, double t_ref, double u_ref, double out15[15]) {  // :167
+        check(o3d_s_calculate_residuals(s_, dt, t_ref, u_ref, out15), "o3d_s_calculate_residuals");
+    }
+    void statistics_calc(double t, double out17[17]) {                                   // :178
+        check(o3d_s_statistics(s_, t, out17), "o3d_s_statistics");
+    }
+    void write_all_data(const std::string& dir, int num) {                               // :147
+        check(o3d_s_write_all_data(s_, dir.c_str(), num), "o3d_s_write_all_data");
+    }
+    void save_fields(const std::string& file, double time, const double* x, const double* y,
+                     const double* z) {                                                  // :183
+        check(o3d_s_save_fields(s_, file.c_str(), time, x, y, z), "o3d_s_save_fields");
+    }
+    void io_wait() { check(o3d_s_io_wait(s_), "o3d_s_io_wait"); }
 
 private:
     o3d_session* s_;

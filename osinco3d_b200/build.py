@@ -78,7 +78,29 @@ def build(force=False, verbose=False):
         if r.returncode:
             print(r.stdout)
             raise RuntimeError("link failed")
+    build_mainloop(force)
     return LIB
+
+
+MAINLOOP_SRC = os.path.join(HERE, "host", "o3d_mainloop.cpp")
+MAINLOOP_EXE = os.path.join(OUT_DIR, "o3d_mainloop")
+
+
+def build_mainloop(force=False):
+    """the driver-shaped harness over include/o3d_b200.hpp (host/o3d_mainloop.cpp): plain g++,
+    linked against the in-tree library with an $ORIGIN rpath so that it travels with it"""
+    gxx = shutil.which("g++")
+    if not gxx:
+        return None
+    hpp = os.path.join(HERE, "..", "include", "o3d_b200.hpp")
+    if force or _stale(MAINLOOP_EXE, [MAINLOOP_SRC, hpp, LIB]):
+        cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", MAINLOOP_EXE,
+               MAINLOOP_SRC, "-L" + OUT_DIR, "-lo3d_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode:
+            print(r.stdout)
+            raise RuntimeError("g++ failed for o3d_mainloop.cpp")
+    return MAINLOOP_EXE
 
 
 if __name__ == "__main__":

@@ -56,7 +56,7 @@ struct PersistArgs {
     SorArgs s;            // geometry, operator, neighbour rule; s.pp / s.rhs unused by the pass
     double* p[2];         // interior origins of the two ping-pong buffers
     int bx, by, bz_lo, bz_hi;  // closures for the ghost images of the new iterate
-    int tiles_x, tiles_y, nch, zchunk;
+    int tiles_x, tiles_y, nch, zchunk, zstagger;
     int first_src;        // buffer read by the first iteration of this launch
     int max_iters;        // iterations this launch may run
     double eps, factor;
@@ -231,7 +231,13 @@ __global__ void __launch_bounds__(GNT, 3)
         for (int item = blockIdx.x; item < nitems; item += G) {
             const int tile = item % ntiles, ch = item / ntiles;
             const int i0 = (tile % a.tiles_x) * GTX, j0 = (tile / a.tiles_x) * GTY;
-            const int kb = ch * a.zchunk, ke = min(g.nz, kb + a.zchunk);
+            // z-chunk boundaries of tiles of odd parity are shifted by `zstagger` planes, so that a
+            // tile runs a few planes ahead of its four neighbours: the 2-cell halo they share is
+            // then requested twice a few microseconds apart (one DRAM fetch + one L2 hit) instead
+            // of simultaneously by CTAs marching in lockstep out of the grid barrier (both miss)
+            const int zsh = (((tile % a.tiles_x) + (tile / a.tiles_x)) & 1) ? a.zstagger : 0;
+            const int kb = ch ? ch * a.zchunk + zsh : 0;
+            const int ke = ch + 1 < a.nch ? (ch + 1) * a.zchunk + zsh : g.nz;
             const int niter = ke - kb;
             const int ngroups = niter > 1 ? niter - 1 : 1;  // group n feeds red(kb + n + 2)
             __syncthreads();  // the previous item's stages (and `red`) are no longer read
@@ -591,6 +597,15 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     f.nch = persist_pick_chunks(ntiles, a.nz, G_max);
     f.zchunk = (a.nz + f.nch - 1) / f.nch;
     f.nch = (a.nz + f.zchunk - 1) / f.zchunk;
+    {
+        // the last chunk of a shifted tile is `zstagger` planes shorter: keep it >= 2 planes
+        const char* e = getenv("O3D_PERSIST_STAGGER");
+        int sh = e ? atoi(e) : 4;
+        const int last = a.nz - (f.nch - 1) * f.zchunk;
+        if (f.nch < 2) sh = 0;
+        if (sh > last - 2) sh = last - 2 > 0 ? last - 2 : 0;
+        f.zstagger = sh;
+    }
     f.first_src = first_src;
     f.max_iters = max_iters;
     f.eps = eps, f.factor = factor, f.kmax = kmax, f.idyn = idyn, f.fixed = fixed;
