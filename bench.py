@@ -13,11 +13,12 @@ replicated in z (nz = N (n-1) + 1 planes on [0, N pi], still an exact free-slip 
 
 The same JSON line carries, under `configs`, the other configurations of BASELINE.json / the north
 star, each with its own value, Poisson iterations per step K and per-stage roofline:
-  N = 1 : 512^3 DNS (north-star target), 512^3 LES (configs[2]), periodic 257^3 (odd extents: seam
-          SOR, K ~ 18), coplanar jet 257 x 513 x 129 (configs[4], K ~ 11), mixing layer 241 x 241 x
+  N = 1 : 512^3 DNS (north-star target), 512^3 LES (configs[2]), periodic 256^3 (K ~ 18) and 257^3
+          (odd extents: seam SOR), coplanar jet 257 x 513 x 129 (configs[4], K ~ 11), mixing layer 241 x 241 x
           81 LES + scalar with SOR (K ~ 84) and with multigrid (configs[3])
-  N > 1 : 512 x 512 x 511 planes per GPU DNS (N = 8: the 1024^3 class), and the coplanar jet
-          replicated in z (periodic wrap rank 0 <-> N-1, K > 1)
+  N > 1 : 512 x 512 x 511 planes per GPU DNS (N = 8: the 1024^3 class), periodic 256 x 256 x 256 N
+          (K ~ 18, wrap link rank 0 <-> N-1) and the coplanar jet replicated in z (odd x / y
+          extents: seam classes across slabs)
 and a `parity` object: N = 1 -- a 64^3 side problem against the CPU oracle; N > 1 -- the N-rank
 fields against the same steps on ONE GPU (rank 0), compared bitwise through digests.
 
@@ -171,7 +172,11 @@ def make_workload(kind, nranks=1, n=256, bc="freeslip", les=False, strong=False,
         b = (1, 1, 1) if bc == "freeslip" else (0, 0, 0)
         L = PI if bc == "freeslip" else 2 * PI
         dd = L / (n - 1)                      # dx = xlx/(nx-1), src/initialization.f90:182-184
-        nz = nranks * (n - 1) + 1 if (nranks > 1 and not strong) else n
+        # weak scaling: the box replicated in z -- free-slip: N (n-1) + 1 planes on [0, N pi];
+        # periodic: N n planes (the reference's period is n dx, SURVEY finding 5)
+        nz = n
+        if nranks > 1 and not strong:
+            nz = nranks * (n - 1) + 1 if bc == "freeslip" else nranks * n
         if les:    # examples/tgv_re2500_les, dt scaled with dx from 5e-4 @ 129^3
             phys = dict(re=2500.0, dt=5e-4 * 128.0 / (n - 1), omega=1.999, eps=1e-6, idyn=1,
                         iles=1, cs=0.17, kmax=10000)
@@ -601,7 +606,17 @@ def open_session(env, w, nranks=None, rank=None, nccl_id=None):
                           rank=rank, nranks=nranks,
                           nccl_id=(env.nccl_id() if nccl_id is None and nranks > 1 else nccl_id))
     ses = o3d.Session(cfg)
-    ses.set(**w["init"](ses.z0, ses.nz_local))
+    plane = nx * ny
+    if plane * ses.nz_local <= (96 << 20):
+        ses.set(**w["init"](ses.z0, ses.nz_local))
+    else:
+        # large slabs (512^3 and up) are generated and uploaded in z chunks of <= 512 MB, so that
+        # neither the host nor the device ever holds a second whole-field copy (1024^3: 8.6 GB)
+        step = max(1, (64 << 20) // plane)
+        for k0 in range(0, ses.nz_local, step):
+            nk = min(step, ses.nz_local - k0)
+            for name, arr in w["init"](ses.z0 + k0, nk).items():
+                ses.upload_planes(name, arr, k0)
     return ses
 
 
@@ -847,12 +862,15 @@ def main():
     if world == 1:
         specs = [("tgv512_dns", dict(kind="tgv", n=512)),
                  ("tgv512_les", dict(kind="tgv", n=512, les=True)),
+                 ("tgv256_periodic", dict(kind="tgv", n=256, bc="periodic")),
                  ("tgv257_periodic", dict(kind="tgv", n=257, bc="periodic")),
                  ("cojet", dict(kind="cojet")),
                  ("mixing_layer_sor", dict(kind="mixing_layer")),
                  ("mixing_layer_multigrid", dict(kind="mixing_layer", multigrid=1))]
     else:
-        specs = [("tgv512_dns", dict(kind="tgv", n=512)), ("cojet", dict(kind="cojet"))]
+        specs = [("tgv512_dns", dict(kind="tgv", n=512)),
+                 ("tgv256_periodic", dict(kind="tgv", n=256, bc="periodic")),
+                 ("cojet", dict(kind="cojet"))]
     if legs == "none":
         specs = []
     elif legs != "all":

@@ -277,6 +277,10 @@ int o3d_session_slab(const o3d_session* s, int* z0, int* nz_local);
  * delivered), like o3d_sync. */
 int o3d_upload(o3d_session* s, int field, const double* host);
 int o3d_download(o3d_session* s, int field, double* host);
+/* the same for local planes [k0, k0 + nk) only: host = a contiguous (nx, ny, nk) block.  Lets a
+ * driver fill or read a slab in pieces without holding a whole-field host array (1024^3: 8.6 GB) */
+int o3d_upload_planes(o3d_session* s, int field, const double* host, int k0, int nk);
+int o3d_download_planes(o3d_session* s, int field, double* host, int k0, int nk);
 /* Device fields are PADDED (ghost cells hold the boundary closure, DESIGN.md "Data layout"):
  * element (i,j,k) of a field lives at dptr[i + stride_j*j + stride_k*k].  o3d_device_ptr returns
  * the interior origin (0,0,0) for zero-copy callers; after writing through it call

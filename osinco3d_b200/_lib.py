@@ -101,6 +101,8 @@ def lib():
         _lib.o3d_s_write_all_data.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         _lib.o3d_s_io_wait.argtypes = [C.c_void_p]
         _lib.o3d_s_sor_path.argtypes = [C.c_void_p, ip, ip]
+        _lib.o3d_upload_planes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        _lib.o3d_download_planes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
         _lib.o3d_get_omega.argtypes = [C.c_void_p, dp]
         _lib.o3d_set_omega.argtypes = [C.c_void_p, C.c_double]
         _lib.o3d_session_set_poisson.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int,

@@ -607,21 +607,48 @@ int o3d_session_slab(const o3d_session* s, int* z0, int* nz_local) {
     return O3D_OK;
 }
 
+// staging buffer of up to STAGE_MAX doubles (512 MB): slabs larger than that move in z chunks, so
+// that a 1024^3 session (18 fields x 8.8 GB) still fits one B200
+static const long long STAGE_MAX = 64ll << 20;
+static int stage_planes(const o3d_session* s) {
+    const long long plane = (long long)s->cfg.nx * s->cfg.ny;
+    long long n = STAGE_MAX / plane;
+    if (n < 1) n = 1;
+    if (n > s->nzl) n = s->nzl;
+    return (int)n;
+}
 static int ensure_stage(o3d_session* s) {
     if (s->stage_d) return O3D_OK;
-    O3D_CUDA_CHECK(cudaMalloc(&s->stage_d, (size_t)s->nloc * sizeof(double)));
+    const size_t elems = (size_t)stage_planes(s) * s->cfg.nx * s->cfg.ny;
+    O3D_CUDA_CHECK(cudaMalloc(&s->stage_d, elems * sizeof(double)));
     return O3D_OK;
 }
 
-// Host arrays are the reference's contiguous (nx,ny,nz) allocatables; device fields are padded.
-// A copy goes through one contiguous staging buffer so that the PCIe transfer is a single
-// full-speed DMA, followed / preceded by a pack kernel (HBM traffic, negligible next to PCIe).
-int o3d_upload(o3d_session* s, int fid, const double* host) {
-    if (!s || !host) return O3D_ERR_INVALID;
-    // History ids are LOGICAL levels.  After the first rotation levels 1 and 2 share a physical
-    // buffer (level 1 is always rewritten by the next predictor before it is read, so the
-    // reference's copy fu(:,:,:,2) = fu(:,:,:,1) is a pointer assignment here): an upload to
-    // level 1 must not clobber level 2 -> give level 1 the free buffer first.
+// planes [k0, k0 + nk) of a padded field <- / -> a contiguous (nx, ny, nk) host block
+static int copy_planes(o3d_session* s, double* d, double* host, int k0, int nk, bool up) {
+    int rc = ensure_stage(s);
+    if (rc) return rc;
+    const int step = stage_planes(s);
+    const size_t plane = (size_t)s->cfg.nx * s->cfg.ny;
+    for (int k = 0; k < nk; k += step) {
+        const int m = (nk - k < step) ? nk - k : step;
+        double* h = host + plane * (size_t)k;
+        if (up) {
+            O3D_CUDA_CHECK(cudaMemcpyAsync(s->stage_d, h, plane * m * sizeof(double),
+                                           cudaMemcpyHostToDevice, s->st));
+            if (launch_pack_planes(s->st, s->g, s->stage_d, d, k0 + k, m)) return O3D_ERR_CUDA;
+        } else {
+            if (launch_unpack_planes(s->st, s->g, d, s->stage_d, k0 + k, m)) return O3D_ERR_CUDA;
+            O3D_CUDA_CHECK(cudaMemcpyAsync(h, s->stage_d, plane * m * sizeof(double),
+                                           cudaMemcpyDeviceToHost, s->st));
+        }
+    }
+    return O3D_OK;
+}
+
+// logical history level 1 must not alias level 2 / 3 when it is written from outside (see
+// o3d_upload in include/o3d_b200.h)
+static void unalias_level1(o3d_session* s, int fid) {
     for (int c = 0; c < 4; ++c) {
         const int hb = c < 3 ? O3D_F_FUX1 + 3 * c : O3D_F_FPHI1;
         if (fid == hb && (s->lv[c][0] == s->lv[c][1] || s->lv[c][0] == s->lv[c][2])) {
@@ -629,15 +656,39 @@ int o3d_upload(o3d_session* s, int fid, const double* host) {
                 if (p != s->lv[c][1] && p != s->lv[c][2]) s->lv[c][0] = p;
         }
     }
+}
+
+// Host arrays are the reference's contiguous (nx,ny,nz) allocatables; device fields are padded.
+// A copy goes through one contiguous staging buffer so that the PCIe transfer is a single
+// full-speed DMA, followed / preceded by a pack kernel (HBM traffic, negligible next to PCIe).
+int o3d_upload(o3d_session* s, int fid, const double* host) {
+    if (!s || !host) return O3D_ERR_INVALID;
+    return o3d_upload_planes(s, fid, host, 0, s->nzl);
+}
+
+int o3d_upload_planes(o3d_session* s, int fid, const double* host, int k0, int nk) {
+    if (!s || !host || k0 < 0 || nk < 1 || k0 + nk > s->nzl) return O3D_ERR_INVALID;
+    // History ids are LOGICAL levels.  After the first rotation levels 1 and 2 share a physical
+    // buffer (level 1 is always rewritten by the next predictor before it is read, so the
+    // reference's copy fu(:,:,:,2) = fu(:,:,:,1) is a pointer assignment here): an upload to
+    // level 1 must not clobber level 2 -> give level 1 the free buffer first.
+    unalias_level1(s, fid);
     const int id = phys_id(s, fid);
     double* d = field(s, id);
     if (!d) return O3D_ERR_CUDA;
-    int rc = ensure_stage(s);
+    const int rc = copy_planes(s, d, const_cast<double*>(host), k0, nk, true);
     if (rc) return rc;
-    O3D_CUDA_CHECK(cudaMemcpyAsync(s->stage_d, host, (size_t)s->nloc * sizeof(double),
-                                   cudaMemcpyHostToDevice, s->st));
-    if (launch_pack(s->st, s->g, s->stage_d, d)) return O3D_ERR_CUDA;
     touch(s, id);
+    O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    return O3D_OK;
+}
+
+int o3d_download_planes(o3d_session* s, int fid, double* host, int k0, int nk) {
+    if (!s || !host || k0 < 0 || nk < 1 || k0 + nk > s->nzl) return O3D_ERR_INVALID;
+    double* d = field(s, phys_id(s, fid));
+    if (!d) return O3D_ERR_CUDA;
+    const int rc = copy_planes(s, d, host, k0, nk, false);
+    if (rc) return rc;
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
     return O3D_OK;
 }
@@ -646,11 +697,8 @@ int o3d_download(o3d_session* s, int fid, double* host) {
     if (!s || !host) return O3D_ERR_INVALID;
     double* d = field(s, phys_id(s, fid));
     if (!d) return O3D_ERR_CUDA;
-    int rc = ensure_stage(s);
+    int rc = copy_planes(s, d, host, 0, s->nzl, false);
     if (rc) return rc;
-    if (launch_unpack(s->st, s->g, d, s->stage_d)) return O3D_ERR_CUDA;
-    O3D_CUDA_CHECK(cudaMemcpyAsync(host, s->stage_d, (size_t)s->nloc * sizeof(double),
-                                   cudaMemcpyDeviceToHost, s->st));
     O3D_CUDA_CHECK(cudaStreamSynchronize(s->st));
     // o3d_step leaves the NaN / >1000 guard of its correction in flight: a caller that steps and
     // then downloads without o3d_sync must not get a diverged state silently (the data is still
@@ -820,8 +868,10 @@ int rhs_prepare(o3d_session* s, int itime, RhsArgs& a, int* tgt) {
         a.up[k] = field(s, PRED_IDS[k]);
         if (!a.u[k].p || !a.f2[k] || !a.f3[k] || !a.f1[k] || !a.up[k]) return O3D_ERR_CUDA;
     }
-    a.nu_t = field(s, O3D_F_NU_T);
-    if (!a.nu_t) return O3D_ERR_CUDA;
+    // nu_t is written only when iles == 1 (src/integration.f90:108-112): a DNS session does not
+    // pay a field for it (a 1024^3 DNS state is 18 fields on one B200)
+    a.nu_t = (c.iles == 1) ? field(s, O3D_F_NU_T) : nullptr;
+    if (c.iles == 1 && !a.nu_t) return O3D_ERR_CUDA;
     a.cx = s->cx, a.cy = s->cy, a.cz = s->cz;
     a.onere = 1.0 / c.re;  // src/integration.f90:106
     a.adu = adu, a.bdu = bdu, a.cdu = cdu;
@@ -970,10 +1020,24 @@ int spec_correct_launch(o3d_session* s) {
     for (int k = 0; k < 3; ++k)
         if (!up[k].p || !u[k]) return O3D_ERR_CUDA;
     if (!pp.p || !alt.p) return O3D_ERR_CUDA;
+    if (c.nranks > 1) {
+        // z slabs: the correction differentiates pp across the rank boundaries (3 ghost planes).
+        // Which ping-pong buffer holds the final iterate is only known on the device, so the planes
+        // of BOTH travel (one grouped exchange, 6 planes per side) and the gated kernel picks.
+        const long long ioff = interior_offset(s->g);
+        double* bases[2] = {pp.p - ioff, alt.p - ioff};
+        const int widths[2] = {R, R};
+        const int rc = comm_exchange_async(s, bases, widths, 2, c.nbcz1 == O3D_PERIODIC);
+        if (rc) return rc;
+    }
     span_begin(s, ST_CORR);
-    if (launch_corr(s->st, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d, 0, 0, &alt,
-                    s->ctrl_d))
-        return O3D_ERR_CUDA;
+    {
+        const int rc = launch_overlapped(s, [&](cudaStream_t q, int zm, int ze) {
+            return launch_corr(q, s->g, pp, up, u, s->cx, s->cy, s->cz, c.dt, s->flag_d, zm, ze,
+                               &alt, s->ctrl_d);
+        });
+        if (rc) return rc;
+    }
     span_end(s, ST_CORR, 0);
     O3D_CUDA_CHECK(
         cudaMemcpyAsync(s->flag_h, s->flag_d, sizeof(int), cudaMemcpyDeviceToHost, s->st));

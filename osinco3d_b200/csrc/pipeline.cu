@@ -334,7 +334,10 @@ int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
                 if ((rc2 = r.computed(c))) return rc2;
                 for (int k = 0; k < 3; ++k)
                     if ((rc2 = r.download(a.up[k], up_h[k], c))) return rc2;
-                if ((rc2 = r.download(a.nu_t, nu_t_h, c))) return rc2;
+                // (DNS: the field the caller zeroed -- nu_t = 0.d0, src/integration.f90:112 --
+                // since the kernel arguments carry no nu_t then)
+                if ((rc2 = r.download(a.nu_t ? a.nu_t : field(s, O3D_F_NU_T), nu_t_h, c)))
+                    return rc2;
                 for (int k = 0; k < 3; ++k)
                     for (int l = 0; l < 3; ++l)
                         if ((rc2 = r.download(fout[k][l], f_h[k] + (long long)l * N, c)))

@@ -117,7 +117,7 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     }
     const double factor = sor_factor(s);
     s->last_sor_path = 0;
-    const bool speculate_p = s->spec_arm && tma && same_bc && id_pp == O3D_F_PP && !multi;
+    const bool speculate_p = s->spec_arm && tma && same_bc && id_pp == O3D_F_PP;
     s->spec_state = 0;
     // ---- persistent path: the whole solve in one cooperative launch (sor_persist_kernel.cu) ----
     // O3D_SOR_PERSIST=0 or a forced host poll interval (sor_check_every) keep the launch-per-pass

@@ -49,7 +49,7 @@ constexpr int GTX = 32, GTY = 16, GNT = 256;
 constexpr int GBX = GTX + 4, GBY = GTY + 4, GPL = GBX * GBY;  // 36 x 20 = 720 cells, 5760 B
 constexpr int GP = 2;                                         // planes prefetched ahead
 constexpr int GNP = 5 + GP, GNR = 3 + GP, GNB = GP + 1;       // p stages, rhs stages, barriers
-constexpr int GSMEM = (GNP + GNR) * GPL * 8 + GNB * 8 + 32 * 8;
+constexpr int GSMEM = (GNP + GNR) * GPL * 8 + GNB * 8 + 32 * 8 + 16;
 constexpr long long SPIN_LIMIT = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
 
 struct PersistArgs {
@@ -62,6 +62,8 @@ struct PersistArgs {
     double eps, factor;
     int kmax, idyn;
     int fixed;            // smoother mode: no exit tests, the control step only counts
+    int dynamic;          // items handed out through an atomic ticket counter
+    int oneshot;          // EXPERIMENT: one iteration, one CTA per item, nobody waits at the barrier
     long long nxf, nyf, nzf;  // sizes of the x / y / z seam planes (SEAM)
     // ---- z slabs: peer-mapped neighbours (null: none on that side) ----
     PeerSync peer;
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(GNT, 3)
     double* sr = sp + GNP * GPL;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sr + GNR * GPL);
     double* red = reinterpret_cast<double*>(bars + GNB);
+    int* ticket = reinterpret_cast<int*>(red + 32);
     const int tid = threadIdx.x;
     const uint32_t sp_s = smem_u32(sp), sr_s = smem_u32(sr), bars_s = smem_u32(bars);
     if (tid == 0) {
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(GNT, 3)
                 last();
                 __threadfence();
                 atomicExch(&sync[16], epoch);
-            } else {
+            } else if (!a.oneshot) {
                 const long long t0 = clock64();
                 while (ld_acquire_gpu(&sync[16]) < epoch) {
                     if (clock64() - t0 > SPIN_LIMIT) {
@@ -228,7 +231,17 @@ __global__ void __launch_bounds__(GNT, 3)
         const unsigned long long T = a.peer.iter_base + (unsigned long long)it;
         double dmax = 0.0;
 
-        for (int item = blockIdx.x; item < nitems; item += G) {
+        // items of an iteration: static round-robin (CTA b takes b, b + G, ...) or, a.dynamic,
+        // tickets from a counter per iteration parity (zeroed for the iteration after next by the
+        // controlling CTA) -- the order in which the hardware would hand out CTAs
+        int item = blockIdx.x;
+        if (a.dynamic) {
+            __syncthreads();
+            if (tid == 0) *ticket = (int)atomicAdd(&sync[4 + (it & 1)], 1ull);
+            __syncthreads();
+            item = *ticket;
+        }
+        while (item < nitems) {
             const int tile = item % ntiles, ch = item / ntiles;
             const int i0 = (tile % a.tiles_x) * GTX, j0 = (tile / a.tiles_x) * GTY;
             // z-chunk boundaries of tiles of odd parity are shifted by `zstagger` planes, so that a
@@ -401,8 +414,11 @@ __global__ void __launch_bounds__(GNT, 3)
                      a_2 = sp_s + 4 * PLB, a_3 = sp_s + 5 * PLB;
             uint32_t ar_0 = sr_s + PLB, ar_2 = sr_s + 3 * PLB;
             double* outp = p_new + (long long)kb * g.sz + (long long)gj * g.sy + gi;
-            // the role-0 member is A (outp[0]) unless m0
-            const long long off0 = m0 ? g.sy : 0, off1 = m0 ? 0 : g.sy;
+            // the role-0 member is A (outp[0]) unless m0; its own pointer, so that no stride has to
+            // be re-read from the constant bank in front of every store
+            double* o0 = outp + (m0 ? g.sy : 0);
+            double* o1 = outp + (m0 ? 0 : g.sy);
+            const long long psz = g.sz;
             const bool in0 = m0 ? inB : inA, in1 = m0 ? inA : inB;
 
             auto step = [&](int k, const int role) {
@@ -423,12 +439,12 @@ __global__ void __launch_bounds__(GNT, 3)
                 if (role) dm0 = d > dm0 ? d : dm0;
                 else dm1 = d > dm1 ? d : dm1;
                 const double v0 = role ? vb : vred, v1 = role ? vred : vb;
-                if (in0) outp[off0] = v0;
-                if (in1) outp[off1] = v1;
+                if (in0) *o0 = v0;
+                if (in1) *o1 = v1;
                 if (xy_img || k <= zslow_lo || k >= zslow_hi)
                     store_pair_extras(outp, m0 ? v1 : v0, m0 ? v0 : v1, inA, inB, ix, iyA, iyB, k,
                                       g.nz, a.bz_lo, a.bz_hi, g.sy, g.sz, peer_lo, peer_hi);
-                outp += g.sz;
+                outp += psz, o0 += psz, o1 += psz;
                 if (multi) {
                     if (peer_lo) peer_lo += g.sz;
                     if (peer_hi) peer_hi += g.sz;
@@ -459,6 +475,14 @@ __global__ void __launch_bounds__(GNT, 3)
                         if (nhi) red_release_sys_add(&a.peer.hi->halo_cnt[0], (unsigned long long)nhi);
                     }
                 }
+            }
+            if (a.dynamic) {
+                __syncthreads();
+                if (tid == 0) *ticket = (int)atomicAdd(&sync[4 + (it & 1)], 1ull);
+                __syncthreads();
+                item = *ticket;
+            } else {
+                item += G;
             }
         }
         {
@@ -494,6 +518,8 @@ __global__ void __launch_bounds__(GNT, 3)
         }
 
         grid_barrier([&] {
+            // every CTA has drawn its last ticket of this iteration: re-arm the counter for it + 2
+            if (a.dynamic) *((volatile unsigned long long*)&sync[4 + (it & 1)]) = 0ull;
             unsigned long long bits = *((volatile unsigned long long*)&ctrl->dmax_bits);
             if (multi) {
                 // all-to-all of the local maxima through peer memory: slot (T & 1, me) + flag on
@@ -617,7 +643,22 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     else memset(&f.peer, 0, sizeof(f.peer));
     if (seams && f.peer.nranks > 1) return 2;  // slabs + odd periodic extents: split launches
     const long long items = (long long)ntiles * f.nch;
-    const unsigned G = (unsigned)(items < G_max ? items : G_max);
+    unsigned G = (unsigned)(items < G_max ? items : G_max);
+    {
+        const char* e = getenv("O3D_PERSIST_DYN");
+        f.dynamic = (e && e[0] == '1') ? 1 : 0;
+    }
+    f.oneshot = 0;
+    {
+        const char* e = getenv("O3D_PERSIST_ONESHOT");
+        if (e && e[0] == '1' && !seams && f.peer.nranks <= 1) {
+            f.oneshot = 1, f.max_iters = 1, G = (unsigned)items;
+            if (cudaMemsetAsync(sync, 0, 32 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
+            sor_persist_kernel<false, false><<<G, GNT, GSMEM, st>>>(maps, f, ctrl, sync);
+            count_launch();
+            return cudaGetLastError() == cudaSuccess ? 0 : 1;
+        }
+    }
     if (cudaMemsetAsync(sync, 0, 32 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
     void* args[] = {(void*)&maps, (void*)&f, (void*)&ctrl, (void*)&sync};
     const void* fn = seams ? (const void*)sor_persist_kernel<true, false>

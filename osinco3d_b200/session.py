@@ -65,6 +65,20 @@ class Session:
             raise ValueError("shape %s != slab shape %s" % (a.shape, self.shape))
         check(lib().o3d_upload(self._h, L.FIELD_ID[name], a.ctypes.data_as(C.c_void_p)))
 
+    def upload_planes(self, name, host, k0):
+        """local planes [k0, k0 + host.shape[2]) of a field from a (nx, ny, nk) block"""
+        a = np.asfortranarray(host, dtype=np.float64)
+        if a.shape[:2] != self.shape[:2]:
+            raise ValueError("plane shape %s != %s" % (a.shape[:2], self.shape[:2]))
+        check(lib().o3d_upload_planes(self._h, L.FIELD_ID[name], a.ctypes.data_as(C.c_void_p), k0,
+                                      a.shape[2]))
+
+    def download_planes(self, name, k0, nk):
+        out = np.empty(self.shape[:2] + (nk,), dtype=np.float64, order="F")
+        check(lib().o3d_download_planes(self._h, L.FIELD_ID[name], out.ctypes.data_as(C.c_void_p),
+                                        k0, nk))
+        return out
+
     def upload_ptr(self, name, ptr):
         check(lib().o3d_upload(self._h, L.FIELD_ID[name], C.c_void_p(ptr)))
 

@@ -36,7 +36,7 @@ def test_mainloop_stats_dat_matches_the_shipped_dns_history(gpu, tmp_path):
     lines = open(os.path.join(out, "outputs", "stats.dat")).read().splitlines()
     rows = GOLD["tgv_re1600_dns"]["rows"]
     assert len(lines) == 5 == len(rows)
-    num = r" [ -]\d\.\d{12}E[+-]\d{2}"
+    num = r"  [ -]\d\.\d{12}E[+-]\d{2}"      # es21.12: 21 columns
     for ln, ref in zip(lines, rows):
         assert len(ln) == 17 * 21 and re.fullmatch("(%s){17}" % num, ln), ln
         v = np.array([float(t) for t in ln.split()])

@@ -80,3 +80,29 @@ def test_output_of_a_diverged_state_is_refused(gpu, O, tmp_path):
     assert e.value.code == gpu._lib.ERR_DIVERGED
     assert not (tmp_path / "fields.bin").exists()
     ses.close()
+
+
+def test_plane_range_upload_download_equal_whole_field_copies(gpu, O):
+    """o3d_upload_planes / o3d_download_planes (drivers that fill a 1024^3 slab in pieces) move
+    exactly the planes they name; a field assembled from ragged chunks equals the whole-field
+    upload bit for bit, ghost state included (a step from either gives the same result)"""
+    ses, (ux, uy, uz, pp) = _session(gpu, O, n=40)
+    ref, _ = _session(gpu, O, n=40)
+    rng = np.random.default_rng(5)
+    f = {k: np.asfortranarray(v + 0.01 * rng.standard_normal(v.shape))
+         for k, v in (("ux", ux), ("uy", uy), ("uz", uz), ("pp", pp))}
+    ref.set(**f)
+    for k, v in f.items():
+        for k0, nk in ((0, 7), (7, 1), (8, 19), (27, 13)):
+            ses.upload_planes(k, v[:, :, k0:k0 + nk], k0)
+    for k, v in f.items():
+        assert np.array_equal(ses.download(k), v), k
+        assert np.array_equal(ses.download_planes(k, 11, 6), v[:, :, 11:17]), k
+    for _ in range(3):
+        assert ses.step() == ref.step()
+    for k in ("ux", "uy", "uz", "pp"):
+        assert np.array_equal(ses.download(k), ref.download(k)), k
+    with pytest.raises(gpu.O3DError):
+        ses.upload_planes("ux", f["ux"][:, :, :5], 38)
+    ses.close()
+    ref.close()
