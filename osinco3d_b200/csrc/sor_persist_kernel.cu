@@ -19,16 +19,6 @@
 // launch-per-pass path => bitwise equal iterates, iteration counts and omega history
 // (tests/test_gpu_poisson.py::test_persistent_solve_equals_launch_per_pass_bitwise).
 //
-// Hot loop, written for instruction count (the pass is co-limited by instruction issue):
-//   * a thread owns a y-pair = one red + one black cell per plane, whose roles alternate from
-//     plane to plane: the march is unrolled by two so the roles are compile-time;
-//   * the red value a thread computes for plane k+2 stays in a register until plane k is stored;
-//   * max|p_new - p| is kept per role with a 3-instruction compare/select and masked once per
-//     item (a cell outside the grid never contributes; ring / ghost / next-chunk cells a CTA
-//     recomputes are real grid points with identical bits, and max is idempotent);
-//   * ghost-image stores (boundary tiles / planes only) live in a noinline function so that none of
-//     their address arithmetic is hoisted into the interior path.
-//
 // Z slabs (nranks > 1): the two boundary planes per side of the new iterate are stored straight
 // into the neighbour rank's ghost planes through peer-mapped pointers (CUDA IPC over NVLink) by
 // the CTAs that compute them, followed by a system-scope release on a counter in the neighbour's
@@ -101,35 +91,6 @@ __device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsig
 // generic-proxy global writes <-> async-proxy (TMA) reads of the same addresses
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
-}
-
-// ghost images of the pair (vA at outp[0], vB at outp[sy]) of plane k -- boundary tiles / planes
-// only -- and, on a z slab, the copies of the two planes next to a rank boundary in the
-// neighbour's ghost planes (interior value + its x / y images; the neighbour's TMA boxes read them)
-__device__ __noinline__ void store_pair_extras(double* outp, double vA, double vB, bool inA,
-                                               bool inB, Img2 ix, Img2 iyA, Img2 iyB, int k, int nz,
-                                               int bz_lo, int bz_hi, long long sy, long long sz,
-                                               double* peer_lo, double* peer_hi) {
-    const Img2 iz = image_offsets(k, nz, bz_lo, bz_hi);
-    if (ix.lo | ix.hi | iyA.lo | iyA.hi | iyB.lo | iyB.hi | iz.lo | iz.hi) {
-        if (inA) store_images(outp, 0, vA, ix, iyA.lo * sy, iyA.hi * sy, iz.lo * sz, iz.hi * sz);
-        if (inB) store_images(outp, sy, vB, ix, iyB.lo * sy, iyB.hi * sy, iz.lo * sz, iz.hi * sz);
-    }
-    // peer_lo / peer_hi: this pair's position in plane k of the neighbour's frame (null: no push)
-    double* const pq[2] = {k < 2 ? peer_lo : nullptr, k >= nz - 2 ? peer_hi : nullptr};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        double* o = pq[q];
-        if (!o) continue;
-        if (inA) {
-            o[0] = vA;
-            store_images(o, 0, vA, ix, iyA.lo * sy, iyA.hi * sy, 0, 0);
-        }
-        if (inB) {
-            o[sy] = vB;
-            store_images(o, sy, vB, ix, iyB.lo * sy, iyB.hi * sy, 0, 0);
-        }
-    }
 }
 
 // exit tests + dynamic omega on a private copy (every field of the control block is read and
@@ -301,33 +262,31 @@ __global__ void __launch_bounds__(GNT, 3)
                 for (int n = 0; n < GP && n < ngroups; ++n) issue_group(n);
             }
 
+            // ---- the pass of sor_tma_kernel.cu over this item (same code path, same bits) ----
+            // Own Y-PAIR: column 2+tx, rows 2+2*typ (member A) and 3+2*typ (member B): one red and
+            // one black cell in every plane; pe = colour of member A in global plane 0.
             const int gi = i0 + tx, gj = j0 + 2 * typ;
             const bool inA = gi < g.nx && gj < g.ny, inB = gi < g.nx && gj + 1 < g.ny;
-            // role 0 = the member of the pair that is red in plane kb (and kb+2, ...)
-            const int m0 = (gi + gj + g.gz0 + kb) & 1;  // 1: member B
-            const uint32_t cell0 = m0 ? ownB8 : ownA8, cell1 = m0 ? ownA8 : ownB8;
-            const int rm0 = has_ring ? ((i0 - 2 + rlx + j0 - 2 + rly + g.gz0 + kb) & 1) : 0;
-            const uint32_t rcl0 = rm0 ? ring1 : ring0, rcl1 = rm0 ? ring0 : ring1;
-            // SEAM: seam parity of the pair's members in x,y and of the ring pair's cells (2 bits
-            // each: 0 / 1 = parity, 2 = ghost cell of an odd periodic axis, never updated)
-            int par0 = 0, par1 = 0, rcode0 = 0, rcode1 = 0;
+            const int pe = (gi + gj + g.gz0) & 1;
+            const int rpar = has_ring ? ((i0 - 2 + rlx + j0 - 2 + rly + g.gz0) & 1) : 0;
+            // SEAM: seam parity of the own pair in x,y (bit 0: member A, bit 1: member B) and of the
+            // two cells of the ring pair (2 bits each: 0 / 1 = parity, 2 = ghost cell of an odd
+            // periodic axis, never updated)
+            int own_par = 0, ring_code = 0;
             if (SEAM) {
                 const int sx = (g.seam_x && gi == g.nx - 1) ? 1 : 0;
-                const int pA = sx ^ ((g.seam_y && gj == g.ny - 1) ? 1 : 0);
-                const int pB = sx ^ ((g.seam_y && gj + 1 == g.ny - 1) ? 1 : 0);
-                par0 = m0 ? pB : pA, par1 = m0 ? pA : pB;
+                own_par = (sx ^ ((g.seam_y && gj == g.ny - 1) ? 1 : 0)) |
+                          ((sx ^ ((g.seam_y && gj + 1 == g.ny - 1) ? 1 : 0)) << 1);
                 if (has_ring) {
-                    int code[2];
                     for (int m = 0; m < 2; ++m) {
                         const int c = rcell + m * rstep;
                         const int ri = i0 - 2 + c % GBX, rj = j0 - 2 + c / GBX;
-                        int cd = 0;
-                        if (g.seam_x) cd = (ri < 0 || ri >= g.nx) ? 2 : (ri == g.nx - 1);
-                        if (g.seam_y && cd != 2)
-                            cd = (rj < 0 || rj >= g.ny) ? 2 : (cd ^ (rj == g.ny - 1 ? 1 : 0));
-                        code[m] = cd;
+                        int code = 0;
+                        if (g.seam_x) code = (ri < 0 || ri >= g.nx) ? 2 : (ri == g.nx - 1);
+                        if (g.seam_y && code != 2)
+                            code = (rj < 0 || rj >= g.ny) ? 2 : (code ^ (rj == g.ny - 1 ? 1 : 0));
+                        ring_code |= code << (2 * m);
                     }
-                    rcode0 = rm0 ? code[1] : code[0], rcode1 = rm0 ? code[0] : code[1];
                 }
             }
             auto zseam = [&](int q) -> int {
@@ -339,26 +298,21 @@ __global__ void __launch_bounds__(GNT, 3)
             const Img2 iyA = image_offsets(gj, g.ny, a.by, a.by);
             const Img2 iyB = image_offsets(gj + 1, g.ny, a.by, a.by);
             const bool xy_img = (ix.lo | ix.hi | iyA.lo | iyA.hi | iyB.lo | iyB.hi) != 0;
-            // planes whose points have z images or copies in a neighbour's ghost planes
-            int zslow_lo = (a.bz_lo == BM_MIRROR || a.bz_hi == BM_WRAP) ? R : -1;  // k <= zslow_lo
-            int zslow_hi = (a.bz_hi == BM_MIRROR || a.bz_lo == BM_WRAP) ? g.nz - 1 - R : g.nz;
+            // planes whose points have z images (walls / periodic wrap handled by this rank)
+            const int zimg_lo = (a.bz_lo == BM_MIRROR || a.bz_hi == BM_WRAP) ? R : -1;  // k <= zimg_lo
+            const int zimg_hi = (a.bz_hi == BM_MIRROR || a.bz_lo == BM_WRAP) ? g.nz - 1 - R : g.nz;
+            // z slabs: this pair's position in plane 0 of the neighbours' frames (my planes 0, 1 are
+            // the lower neighbour's ghost planes nz_lo, nz_lo + 1; my planes nz-2, nz-1 the upper
+            // neighbour's ghost planes -2, -1)
             double* peer_lo = nullptr;
             double* peer_hi = nullptr;
-            if (multi) {
+            if (MULTI) {
                 const long long pair = (long long)gj * g.sy + gi;
-                // my planes 0, 1 are the lower neighbour's ghost planes nz_lo, nz_lo + 1; my
-                // planes nz-2, nz-1 the upper neighbour's ghost planes -2, -1
-                // (pointers to this pair in plane kb of the neighbour's frame, advanced per plane)
-                if (a.peer.has_lo) {
-                    peer_lo = a.peer.lo_p[src ^ 1] + (long long)(a.peer.lo_nz + kb) * g.sz + pair;
-                    zslow_lo = max(zslow_lo, 1);
-                }
-                if (a.peer.has_hi) {
-                    peer_hi = a.peer.hi_p[src ^ 1] + (long long)(kb - g.nz) * g.sz + pair;
-                    zslow_hi = min(zslow_hi, g.nz - 2);
-                }
+                if (a.peer.has_lo) peer_lo = a.peer.lo_p[src ^ 1] + (long long)a.peer.lo_nz * g.sz + pair;
+                if (a.peer.has_hi) peer_hi = a.peer.hi_p[src ^ 1] - (long long)g.nz * g.sz + pair;
             }
 
+            double dloc = 0.0;
             auto nextp = [&](uint32_t x) { return x + PLB == p_end ? sp_s : x + PLB; };
             auto nextr = [&](uint32_t x) { return x + PLB == r_end ? sr_s : x + PLB; };
             // SOR update of the cell at byte offset c of the plane at a0 (am / ap = planes below /
@@ -377,93 +331,102 @@ __global__ void __launch_bounds__(GNT, 3)
                 d = fabs(pn - pc);                     // :100
                 return one_m_omega * pc + omega * pn;  // :102
             };
-            double dm0 = 0.0, dm1 = 0.0;  // max d of the role-0 / role-1 member
-            // red half-sweep of the plane at a0 (local plane q) for the member of role ROLE and the
-            // ring cell of that role; returns the member's new value (also stored in the stage)
+            const uint32_t cxor = ownA8 ^ ownB8, rxor = ring0 ^ ring1;
+            // r = 1: member B of the pair is the red one in the current plane (member A otherwise);
+            // c_red / c_blk = byte offsets of the red / black member; rc = the red cell of the ring
+            // pair, rmm = which of its two cells that is.  All flip from plane to plane.
+            int r = (pe + kb) & 1, rmm = (rpar + kb) & 1;
+            uint32_t c_red = r ? ownB8 : ownA8, c_blk = r ? ownA8 : ownB8;
+            uint32_t rc = rmm ? ring1 : ring0;
+            auto flip = [&]() { r ^= 1, rmm ^= 1, c_red ^= cxor, c_blk ^= cxor, rc ^= rxor; };
+            // red half-sweep of the plane at a0 (local plane q) over the own pair and the ring pair;
+            // counted: the plane is owned by this chunk
             auto red_plane = [&](int q, uint32_t am, uint32_t a0, uint32_t ap, uint32_t ar,
-                                 const int role) -> double {
-                const uint32_t c = role ? cell1 : cell0;
+                                 bool counted) {
                 double d, pc;
-                double v = update(am, a0, ap, ar, c, d, pc);
+                double v = update(am, a0, ap, ar, c_red, d, pc);
                 bool ring_on = has_ring;
                 if (SEAM) {
                     const int zs = zseam(q);
-                    if (zs == 2 || (((role ? par1 : par0) ^ zs) & 1)) v = pc, d = 0.0;  // odd class
-                    const int code = role ? rcode1 : rcode0;
+                    if (zs == 2 || (((own_par >> r) ^ zs) & 1)) v = pc, d = 0.0;  // odd class: keep
+                    const int code = (ring_code >> (2 * rmm)) & 3;
                     ring_on = ring_on && zs != 2 && code != 2 && !((code ^ zs) & 1);
                 }
                 if (ring_on) {
-                    const uint32_t rc = role ? rcl1 : rcl0;
                     double dr, pr;
                     const double vr = update(am, a0, ap, ar, rc, dr, pr);
                     sts(a0 + rc, vr);
                 }
-                sts(a0 + c, v);
-                if (role) dm1 = d > dm1 ? d : dm1;
-                else dm0 = d > dm0 ? d : dm0;
-                return v;
+                sts(a0 + c_red, v);
+                if (counted && (r ? inB : inA)) dloc = fmax(dloc, d);
             };
 
             wait_group(0);  // p planes kb-2 .. kb+3 in stages 0 .. 5, rhs kb-1 .. kb+2 in 0 .. 3
-            double vr0, vr1;  // new red value of the role-0 / role-1 member, until its plane is stored
-            (void)red_plane(kb - 1, sp_s, sp_s + PLB, sp_s + 2 * PLB, sr_s, 1);
-            vr0 = red_plane(kb, sp_s + PLB, sp_s + 2 * PLB, sp_s + 3 * PLB, sr_s + PLB, 0);
-            vr1 = red_plane(kb + 1, sp_s + 2 * PLB, sp_s + 3 * PLB, sp_s + 4 * PLB, sr_s + 2 * PLB, 1);
+            flip();  // plane kb-1 has the other parity
+            red_plane(kb - 1, sp_s, sp_s + PLB, sp_s + 2 * PLB, sr_s, false);
+            flip();
+            red_plane(kb, sp_s + PLB, sp_s + 2 * PLB, sp_s + 3 * PLB, sr_s + PLB, true);
+            flip();
+            red_plane(kb + 1, sp_s + 2 * PLB, sp_s + 3 * PLB, sp_s + 4 * PLB, sr_s + 2 * PLB,
+                      kb + 1 < ke);
+            flip();  // back to the parity of plane kb
 
             uint32_t a_m1 = sp_s + PLB, a_0 = sp_s + 2 * PLB, a_1 = sp_s + 3 * PLB,
                      a_2 = sp_s + 4 * PLB, a_3 = sp_s + 5 * PLB;
             uint32_t ar_0 = sr_s + PLB, ar_2 = sr_s + 3 * PLB;
             double* outp = p_new + (long long)kb * g.sz + (long long)gj * g.sy + gi;
-            // the role-0 member is A (outp[0]) unless m0; its own pointer, so that no stride has to
-            // be re-read from the constant bank in front of every store
-            double* o0 = outp + (m0 ? g.sy : 0);
-            double* o1 = outp + (m0 ? 0 : g.sy);
-            const long long psz = g.sz;
-            const bool in0 = m0 ? inB : inA, in1 = m0 ? inA : inB;
-
-            auto step = [&](int k, const int role) {
+            for (int k = kb; k < ke; ++k) {
                 const int n = k - kb;
                 __syncthreads();  // step k-1 done: its oldest stages may be refilled; red(k+1) visible
                 if (tid == 0 && n + GP < ngroups) issue_group(n + GP);
                 if (n >= 1 && n < ngroups) wait_group(n);
-                // plane k: the member of role ROLE is red (value kept in a register), the other black
-                const double vred = role ? vr1 : vr0;
-                if (k + 2 <= ke) {
-                    const double v = red_plane(k + 2, a_1, a_2, a_3, ar_2, role);
-                    if (role) vr1 = v;
-                    else vr0 = v;
+                // planes k+2 and k have the same parity: the same member is red in both
+                if (k + 2 <= ke) red_plane(k + 2, a_1, a_2, a_3, ar_2, k + 2 < ke);
+                {
+                    // black member of the own pair in plane k: all six neighbours hold new red values
+                    double d, pcb;
+                    double vb = update(a_m1, a_0, a_1, ar_0, c_blk, d, pcb);
+                    if (SEAM && (((own_par >> (1 - r)) ^ zseam(k)) & 1))
+                        vb = pcb, d = 0.0;  // odd class: swept after the pass
+                    const double vred = lds<0>(a_0 + c_red);
+                    if (r ? inA : inB) dloc = fmax(dloc, d);
+                    const double vA = r ? vb : vred, vB = r ? vred : vb;
+                    if (inA) outp[0] = vA;
+                    if (inB) outp[g.sy] = vB;
+                    if (xy_img || k <= zimg_lo || k >= zimg_hi) {  // boundary-adjacent points only
+                        const Img2 iz = image_offsets(k, g.nz, a.bz_lo, a.bz_hi);
+                        if (inA)
+                            store_images(outp, 0, vA, ix, iyA.lo * g.sy, iyA.hi * g.sy, iz.lo * g.sz,
+                                         iz.hi * g.sz);
+                        if (inB)
+                            store_images(outp, g.sy, vB, ix, iyB.lo * g.sy, iyB.hi * g.sy,
+                                         iz.lo * g.sz, iz.hi * g.sz);
+                    }
+                    if (MULTI) {
+                        // the two planes next to a rank boundary also go straight into the
+                        // neighbour's ghost planes (value + x / y images: its TMA boxes read them)
+                        double* o = nullptr;
+                        if (k < 2 && peer_lo) o = peer_lo + (long long)k * g.sz;
+                        if (k >= g.nz - 2 && peer_hi) o = peer_hi + (long long)k * g.sz;
+                        if (o) {
+                            if (inA) {
+                                o[0] = vA;
+                                store_images(o, 0, vA, ix, iyA.lo * g.sy, iyA.hi * g.sy, 0, 0);
+                            }
+                            if (inB) {
+                                o[g.sy] = vB;
+                                store_images(o, g.sy, vB, ix, iyB.lo * g.sy, iyB.hi * g.sy, 0, 0);
+                            }
+                        }
+                    }
                 }
-                double d, pcb;
-                double vb = update(a_m1, a_0, a_1, ar_0, role ? cell0 : cell1, d, pcb);
-                if (SEAM && (((role ? par0 : par1) ^ zseam(k)) & 1)) vb = pcb, d = 0.0;  // odd class
-                if (role) dm0 = d > dm0 ? d : dm0;
-                else dm1 = d > dm1 ? d : dm1;
-                const double v0 = role ? vb : vred, v1 = role ? vred : vb;
-                if (in0) *o0 = v0;
-                if (in1) *o1 = v1;
-                if (xy_img || k <= zslow_lo || k >= zslow_hi)
-                    store_pair_extras(outp, m0 ? v1 : v0, m0 ? v0 : v1, inA, inB, ix, iyA, iyB, k,
-                                      g.nz, a.bz_lo, a.bz_hi, g.sy, g.sz, peer_lo, peer_hi);
-                outp += psz, o0 += psz, o1 += psz;
-                if (multi) {
-                    if (peer_lo) peer_lo += g.sz;
-                    if (peer_hi) peer_hi += g.sz;
-                }
+                outp += g.sz;
+                flip();
                 a_m1 = a_0, a_0 = a_1, a_1 = a_2, a_2 = a_3, a_3 = nextp(a_3);
                 ar_0 = nextr(ar_0), ar_2 = nextr(ar_2);
-            };
-            int k = kb;
-            for (; k + 1 < ke; k += 2) {
-                step(k, 0);
-                step(k + 1, 1);
             }
-            if (k < ke) step(k, 0);
             gbase += ngroups;
-            {
-                const double dA = m0 ? dm1 : dm0, dB = m0 ? dm0 : dm1;
-                if (inA) dmax = dA > dmax ? dA : dmax;
-                if (inB) dmax = dB > dmax ? dB : dmax;
-            }
+            dmax = fmax(dmax, dloc);
             if (multi) {
                 // this item's copies in the neighbours' ghost planes are complete: release them
                 const int nlo = a.peer.has_lo ? max(0, min(ke, 2) - kb) : 0;
@@ -620,9 +583,19 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     f.bx = bx, f.by = by, f.bz_lo = bz_lo, f.bz_hi = bz_hi;
     f.tiles_x = (a.nx + GTX - 1) / GTX, f.tiles_y = (a.ny + GTY - 1) / GTY;
     const int ntiles = f.tiles_x * f.tiles_y;
-    f.nch = persist_pick_chunks(ntiles, a.nz, G_max);
-    f.zchunk = (a.nz + f.nch - 1) / f.nch;
-    f.nch = (a.nz + f.zchunk - 1) / f.zchunk;
+    {
+        const char* e = getenv("O3D_PERSIST_DYN");
+        const char* en = getenv("O3D_NCH_P");
+        if ((e && e[0] == '0') || (en && atoi(en) > 0)) {
+            f.nch = persist_pick_chunks(ntiles, a.nz, G_max);
+            f.zchunk = (a.nz + f.nch - 1) / f.nch;
+        } else {
+            // tickets balance like the hardware's CTA scheduler: the chunk model of the
+            // launch-per-pass kernel (throughput + half a chunk of tail) applies
+            f.zchunk = pick_zchunk_slots(ntiles, a.nz, G_max, 3.3);
+        }
+        f.nch = (a.nz + f.zchunk - 1) / f.zchunk;
+    }
     {
         // the last chunk of a shifted tile is `zstagger` planes shorter: keep it >= 2 planes
         const char* e = getenv("O3D_PERSIST_STAGGER");
@@ -645,8 +618,12 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     const long long items = (long long)ntiles * f.nch;
     unsigned G = (unsigned)(items < G_max ? items : G_max);
     {
+        // default: tickets.  CTAs that share an SM draw consecutive tickets, so neighbouring tiles
+        // run on the same SM / GPC and the halo they share is found in L2; with the static
+        // round-robin map (O3D_PERSIST_DYN=0) the same pass re-reads it from DRAM (measured at
+        // 512^3: 3.6 GB instead of 2.4 GB per pass, profiles/r2_sor_scheduling.txt)
         const char* e = getenv("O3D_PERSIST_DYN");
-        f.dynamic = (e && e[0] == '1') ? 1 : 0;
+        f.dynamic = (e && e[0] == '0') ? 0 : 1;
     }
     f.oneshot = 0;
     {
