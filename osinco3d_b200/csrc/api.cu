@@ -524,7 +524,7 @@ int o3d_session_create(const o3d_config* cfg, o3d_session** out) {
     s->ctrl_d = nullptr, s->ctrl_h = nullptr, s->flag_d = nullptr, s->flag_h = nullptr;
     s->seam_sync_d = nullptr;
     s->persist_sync_d = nullptr, s->ev_ctrl = nullptr;
-    s->pp_phys = 0, s->peers = nullptr, s->peers_tried = 0, s->peer_iter_base = 0ull;
+    s->pp_phys = 0, s->peers = nullptr, s->peers_tried = 0, s->peer_iter_base = 0ull, s->peer_solves = 0ull;
     s->last_sor_path = 0;
     s->scal_d = nullptr, s->scal_h = nullptr;
     fill_geom(s);

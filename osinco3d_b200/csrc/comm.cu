@@ -133,7 +133,7 @@ struct PeerState {
     int ok = 0;
     PeerBlock* mine = nullptr;
     PeerBlock* all[16] = {};
-    double* nb_alloc[16][2] = {};  // [rank][physical buffer]: mapped allocation bases (neighbours)
+    double* nb_alloc[16][3] = {};  // [rank][physical pp buffer 0 / 1, rhs]: mapped allocation bases
     int nb_nz[16] = {};
     void* opened[48] = {};
     int nopened = 0;
@@ -141,7 +141,7 @@ struct PeerState {
 
 namespace {
 struct PeerExport {
-    cudaIpcMemHandle_t block, p[2];
+    cudaIpcMemHandle_t block, p[3];  // p[0], p[1]: physical pp buffers, p[2]: O3D_F_RHS
     int nzl, ok, pad[2];
 };
 }  // namespace
@@ -162,13 +162,15 @@ int comm_peer_setup(o3d_session* s) {
     // physical buffer 0 is the allocation that was O3D_F_PP at session start
     double* phys[2] = {s->base[s->pp_phys ? O3D_F_PP2 : O3D_F_PP],
                        s->base[s->pp_phys ? O3D_F_PP : O3D_F_PP2]};
-    if (!phys[0] || !phys[1]) mine.ok = 0;
+    double* rhs_alloc = s->base[O3D_F_RHS];
+    if (!phys[0] || !phys[1] || !rhs_alloc) mine.ok = 0;
     if (mine.ok && (cudaMalloc(&ps->mine, sizeof(PeerBlock)) != cudaSuccess ||
                     cudaMemset(ps->mine, 0, sizeof(PeerBlock)) != cudaSuccess))
         mine.ok = 0;
     if (mine.ok && (cudaIpcGetMemHandle(&mine.block, ps->mine) != cudaSuccess ||
                     cudaIpcGetMemHandle(&mine.p[0], phys[0]) != cudaSuccess ||
-                    cudaIpcGetMemHandle(&mine.p[1], phys[1]) != cudaSuccess)) {
+                    cudaIpcGetMemHandle(&mine.p[1], phys[1]) != cudaSuccess ||
+                    cudaIpcGetMemHandle(&mine.p[2], rhs_alloc) != cudaSuccess)) {
         (void)cudaGetLastError();
         mine.ok = 0;
     }
@@ -200,7 +202,7 @@ int comm_peer_setup(o3d_session* s) {
         ps->opened[ps->nopened++] = ptr;
         ps->all[q] = static_cast<PeerBlock*>(ptr);
         if (q == up || q == dn) {
-            for (int b = 0; b < 2 && ok; ++b) {
+            for (int b = 0; b < 3 && ok; ++b) {
                 if (cudaIpcOpenMemHandle(&ptr, allx[q].p[b], cudaIpcMemLazyEnablePeerAccess) !=
                     cudaSuccess) {
                     ok = false;
@@ -236,6 +238,8 @@ int comm_peer_args(o3d_session* s, PeerSync* out) {
     out->nranks = P, out->rank = me;
     out->has_lo = dn >= 0, out->has_hi = up >= 0;
     out->iter_base = s->peer_iter_base;
+    out->solve_base = s->peer_solves;
+    out->push_init = 1;
     out->mine = ps->mine;
     for (int q = 0; q < P; ++q) out->all[q] = ps->all[q];
     const long long ioff = interior_offset(s->g);
@@ -246,11 +250,13 @@ int comm_peer_args(o3d_session* s, PeerSync* out) {
         out->lo_nz = ps->nb_nz[dn];
         out->lo_p[0] = ps->nb_alloc[dn][s->pp_phys] + ioff;
         out->lo_p[1] = ps->nb_alloc[dn][s->pp_phys ^ 1] + ioff;
+        out->lo_rhs = ps->nb_alloc[dn][2] + ioff;
     }
     if (up >= 0) {
         out->hi = ps->all[up];
         out->hi_p[0] = ps->nb_alloc[up][s->pp_phys] + ioff;
         out->hi_p[1] = ps->nb_alloc[up][s->pp_phys ^ 1] + ioff;
+        out->hi_rhs = ps->nb_alloc[up][2] + ioff;
     }
     return 0;
 }

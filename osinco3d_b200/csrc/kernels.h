@@ -197,7 +197,8 @@ int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_m
 // stored into this rank's pp buffers, all ranks deposit their residual maxima.
 struct PeerBlock {
     unsigned long long halo_cnt[2];       // planes received into my low / high ghost planes (monotone)
-    unsigned long long pad0[14];
+    unsigned long long init_cnt[2];       // solves whose initial ghost planes have arrived (low / high)
+    unsigned long long pad0[12];
     unsigned long long dmax_slot[2][16];  // [global iteration & 1][source rank]
     unsigned long long dmax_flag[16];     // [source rank] = global iterations published so far
 };
@@ -206,6 +207,10 @@ struct PeerSync {
     int has_lo, has_hi;                   // a neighbour rank below / above (periodic wrap included)
     int lo_nz;                            // the lower neighbour's number of owned planes
     unsigned long long iter_base;         // iterations all ranks completed in earlier persistent solves
+    unsigned long long solve_base;        // earlier peer-memory solves of this session
+    int push_init;                        // 1: phase 0 of the kernel delivers the initial ghost planes
+    double* lo_rhs;                       // the neighbours' right-hand-side fields (interior origins)
+    double* hi_rhs;
     PeerBlock* mine;
     PeerBlock* lo;
     PeerBlock* hi;

@@ -88,7 +88,7 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         if (!alt) return O3D_ERR_CUDA;
     }
     int id_pp = -1, id_rhs = -1;
-    bool same_bc = false;
+    bool same_bc = false, fills_pending = false;
     if (tma) {
         // the TMA kernel reads the boundary rule from ghost cells: which session fields are these?
         for (int f = 0; f < O3D_F_COUNT; ++f) {
@@ -104,9 +104,18 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                    a.mz_hi == s->g.bz_hi);
         if (same_bc) {
             int rc;
+            // (a fill launched here rewrites x / y ghost cells inside the z ghost planes, which a
+            // neighbour rank that is ahead may be storing into already: such a solve -- the first
+            // after an upload -- gets its initial ghost planes through NCCL, in stream order)
+            auto valid = [&](int id, bool edges) {
+                const unsigned want = 0x1u | 0x2u | 0x8u | (edges ? 0x10u : 0u);
+                return (s->gaxes[id] & want) == want && (s->gpar[id] & 0x7u) == 0u;
+            };
+            fills_pending = !valid(id_pp, true) || !valid(id_rhs, false);
             if ((rc = ensure_local_ghosts(s, id_pp, 0u, true))) return rc;
             if ((rc = ensure_local_ghosts(s, id_rhs, 0u, false))) return rc;
         } else {
+            fills_pending = true;
             Geom gs = s->g;
             gs.bx = a.mx, gs.by = a.my, gs.bz_lo = a.mz_lo, gs.bz_hi = a.mz_hi;
             if (launch_fill_ghosts_full(s->st, gs, pp, 0u)) return O3D_ERR_CUDA;
@@ -135,10 +144,12 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                 persist = false;  // NCCL halos + all-reduce per sweep, below
         }
         if (persist) {
-            if (multi) {
+            if (multi && (id_rhs != O3D_F_RHS || !peer.push_init || fills_pending)) {
+                // (a right-hand side that is not the session's O3D_F_RHS has no peer mapping:)
                 // ghost planes of the initial iterate (2) and of the right-hand side (1; constant
-                // over the solve): one grouped NCCL exchange, stream-ordered before the kernel.
-                // Every later iterate travels inside the kernel through peer memory.
+                // over the solve) through one grouped NCCL exchange, stream-ordered before the
+                // kernel.  Otherwise phase 0 of the kernel stores them into the neighbours' memory.
+                peer.push_init = 0;
                 const long long ioff0 = interior_offset(s->g);
                 double* bases[2] = {pp - ioff0, const_cast<double*>(rhs) - ioff0};
                 const int widths[2] = {2, 1};
@@ -174,7 +185,10 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                     set_error("persistent SOR: a grid barrier or a peer rank timed out");
                     return O3D_ERR_COMM;
                 }
-                if (multi) s->peer_iter_base += (unsigned long long)h->iter;
+                if (multi) {
+                    s->peer_iter_base += (unsigned long long)h->iter;
+                    if (peer.push_init) s->peer_solves += 1ull;
+                }
                 goto finished;
             }
             // lrc == 2: not applicable here, fall through

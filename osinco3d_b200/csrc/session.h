@@ -55,6 +55,7 @@ struct o3d_session {
     o3d::PeerState* peers; // z slabs: peer-mapped neighbours, set up lazily by the first solve
     int peers_tried;
     unsigned long long peer_iter_base;  // iterations of all earlier peer-memory solves
+    unsigned long long peer_solves;     // peer-memory solves so far
     int last_sor_path;     // bit 0: persistent kernel, bit 1: peer-memory halos (last solve)
     int sor_variant;       // 0: _0000, 1: _0011, 2: _111111
     int last_iters;

@@ -181,6 +181,43 @@ __global__ void __launch_bounds__(GNT, 3)
         __syncthreads();
     };
 
+    if (MULTI && a.peer.push_init) {
+        // phase 0 (z slabs): the ghost planes of the INITIAL iterate (2 per side) and of the
+        // right-hand side (1 per side; constant over the solve) are stored straight into the
+        // neighbours' ghost planes -- whole padded planes, so that the x / y ghost cells travel
+        // too -- by all CTAs together; the last CTA to finish releases one count per neighbour.
+        // No NCCL call in front of the solve: interior items start at once, items that touch a
+        // slab end acquire the neighbour's count first.
+        const long long pl = g.sz, org = (long long)GX + (long long)GH * g.sy;  // plane start
+        const double* ps = a.p[a.first_src] - org;
+        const double* rs = g.rhs - org;
+        const long long stride = (long long)G * GNT;
+        const long long t0i = (long long)blockIdx.x * GNT + tid;
+        if (a.peer.has_lo) {  // my planes 0, 1 (p) and 0 (rhs) -> lower neighbour's planes nz_lo + ..
+            double* pd = a.peer.lo_p[a.first_src] - org + (long long)a.peer.lo_nz * pl;
+            double* rd = a.peer.lo_rhs - org + (long long)a.peer.lo_nz * pl;
+            for (long long q = t0i; q < 2 * pl; q += stride) pd[q] = ps[q];
+            for (long long q = t0i; q < pl; q += stride) rd[q] = rs[q];
+        }
+        if (a.peer.has_hi) {  // my planes nz-2, nz-1 (p) and nz-1 (rhs) -> upper neighbour's -2, -1
+            double* pd = a.peer.hi_p[a.first_src] - org - 2 * pl;
+            double* rd = a.peer.hi_rhs - org - pl;
+            const double* p2 = ps + (long long)(g.nz - 2) * pl;
+            const double* r2 = rs + (long long)(g.nz - 1) * pl;
+            for (long long q = t0i; q < 2 * pl; q += stride) pd[q] = p2[q];
+            for (long long q = t0i; q < pl; q += stride) rd[q] = r2[q];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            if (atomicAdd(&sync[8], 1ull) == (unsigned long long)(G - 1)) {
+                __threadfence_system();
+                if (a.peer.has_lo) red_release_sys_add(&a.peer.lo->init_cnt[1], 1ull);
+                if (a.peer.has_hi) red_release_sys_add(&a.peer.hi->init_cnt[0], 1ull);
+            }
+        }
+    }
+
     for (int it = 0; it < a.max_iters; ++it) {
         if (*((volatile int*)&ctrl->done)) break;  // uniform over the grid (read after a barrier)
         const double omega = *((volatile double*)&ctrl->omega);
@@ -245,10 +282,20 @@ __global__ void __launch_bounds__(GNT, 3)
                 mbar_wait(bars_s + 8 * (q % GNB), (q / GNB) & 1u);
             };
             if (tid == 0) {
-                if (multi && T > 0) {
+                if (multi && it == 0 && a.peer.push_init) {
+                    // the neighbours' phase 0 of THIS solve: one count per solve and side
+                    const unsigned long long need = a.peer.solve_base + 1ull;
+                    const long long t0 = clock64();
+                    if (kb < 2 && a.peer.has_lo)
+                        while (ld_acquire_sys(&a.peer.mine->init_cnt[0]) < need)
+                            if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                    if (ke + 1 >= g.nz && a.peer.has_hi)
+                        while (ld_acquire_sys(&a.peer.mine->init_cnt[1]) < need)
+                            if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                }
+                if (multi && it > 0) {
                     // ghost planes of the previous iterate come from the neighbours' CTAs: two
-                    // planes per tile and side, counted in OUR memory (iteration 0 of a solve was
-                    // exchanged by the host before the launch)
+                    // planes per tile and side, counted in OUR memory over the whole session
                     const unsigned long long need = 2ull * ntiles * T;
                     const long long t0 = clock64();
                     if (kb < 2 && a.peer.has_lo)
