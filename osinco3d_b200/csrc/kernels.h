@@ -198,7 +198,8 @@ int launch_sor_tma(cudaStream_t st, const SorArgs& a, const CUtensorMap* p_old_m
 struct PeerBlock {
     unsigned long long halo_cnt[2];       // planes received into my low / high ghost planes (monotone)
     unsigned long long init_cnt[2];       // solves whose initial ghost planes have arrived (low / high)
-    unsigned long long pad0[12];
+    unsigned long long seam_cnt[2];       // odd seam sweeps (2 per iteration) the neighbour has delivered
+    unsigned long long pad0[10];
     unsigned long long dmax_slot[2][16];  // [global iteration & 1][source rank]
     unsigned long long dmax_flag[16];     // [source rank] = global iterations published so far
 };

@@ -139,7 +139,7 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
         memset(&peer, 0, sizeof(peer));
         if (persist && multi) {
             const char* e_peer = getenv("O3D_SOR_PEER");
-            if (seams || (e_peer && e_peer[0] == '0') || comm_peer_setup(s) ||
+            if ((e_peer && e_peer[0] == '0') || comm_peer_setup(s) ||
                 comm_peer_args(s, &peer))
                 persist = false;  // NCCL halos + all-reduce per sweep, below
         }

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(GNT, 3)
         __syncthreads();
         if (tid == 0) {
             epoch += 1;
-            __threadfence();
+            if (MULTI) __threadfence_system();  // this CTA's stores into peer memory included
+            else __threadfence();
             const unsigned long long t = atomicAdd(&sync[0], 1ull);
             if (t + 1 == epoch * G) {
                 last();
@@ -240,7 +241,14 @@ __global__ void __launch_bounds__(GNT, 3)
             item = *ticket;
         }
         while (item < nitems) {
-            const int tile = item % ntiles, ch = item / ntiles;
+            const int tile = item % ntiles;
+            int ch = item / ntiles;
+            if (MULTI && a.nch > 2) {
+                // z slabs: interior chunks first, the two chunks at the slab ends last -- their
+                // ghost planes come from the neighbours (phase 0 / the previous iteration's
+                // epilogue stores), which then have a whole interior sweep of slack
+                ch = ch < a.nch - 2 ? ch + 1 : (ch == a.nch - 2 ? 0 : a.nch - 1);
+            }
             const int i0 = (tile % a.tiles_x) * GTX, j0 = (tile / a.tiles_x) * GTY;
             // z-chunk boundaries of tiles of odd parity are shifted by `zstagger` planes, so that a
             // tile runs a few planes ahead of its four neighbours: the 2-cell halo they share is
@@ -298,6 +306,14 @@ __global__ void __launch_bounds__(GNT, 3)
                     // planes per tile and side, counted in OUR memory over the whole session
                     const unsigned long long need = 2ull * ntiles * T;
                     const long long t0 = clock64();
+                    if (SEAM) {  // ... and both odd seam sweeps of that iteration
+                        if (kb < 2 && a.peer.has_lo)
+                            while (ld_acquire_sys(&a.peer.mine->seam_cnt[0]) < 2ull * T)
+                                if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                        if (ke + 1 >= g.nz && a.peer.has_hi)
+                            while (ld_acquire_sys(&a.peer.mine->seam_cnt[1]) < 2ull * T)
+                                if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                    }
                     if (kb < 2 && a.peer.has_lo)
                         while (ld_acquire_sys(&a.peer.mine->halo_cnt[0]) < need)
                             if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
@@ -503,22 +519,64 @@ __global__ void __launch_bounds__(GNT, 3)
 
         if (SEAM) {
             // the two thin odd classes, in place on the new iterate, rewriting the ghost images of
-            // what they touch (sor_kernels.cu); single rank only (slabs keep the split launches)
+            // what they touch (sor_kernels.cu)
             SorArgs sa = g;
             sa.pp = p_new;
             const long long tot = a.nxf + a.nyf + a.nzf;
             const long long stride = (long long)G * GNT;
             double dm = 0.0;
             for (int colour = 0; colour < 2; ++colour) {
-                grid_barrier([] {});
+                grid_barrier([&] {
+                    if (!MULTI) return;
+                    // z slabs: an odd point next to a rank boundary reads the neighbour's plane.
+                    // Before the red class that plane must hold the neighbour's PASS of this
+                    // iteration (its epilogue stores: halo_cnt), before the black class its red
+                    // odd sweep (seam_cnt); our own red sweep is released to the neighbours here.
+                    const long long t0 = clock64();
+                    unsigned long long* cnt[2] = {nullptr, nullptr};
+                    unsigned long long need = 0ull;
+                    if (colour == 0) {
+                        cnt[0] = &a.peer.mine->halo_cnt[0], cnt[1] = &a.peer.mine->halo_cnt[1];
+                        need = 2ull * ntiles * (T + 1ull);
+                    } else {
+                        if (a.peer.has_lo) red_release_sys_add(&a.peer.lo->seam_cnt[1], 1ull);
+                        if (a.peer.has_hi) red_release_sys_add(&a.peer.hi->seam_cnt[0], 1ull);
+                        cnt[0] = &a.peer.mine->seam_cnt[0], cnt[1] = &a.peer.mine->seam_cnt[1];
+                        need = 2ull * T + 1ull;
+                    }
+                    for (int side = 0; side < 2; ++side) {
+                        if (!(side ? a.peer.has_hi : a.peer.has_lo)) continue;
+                        while (ld_acquire_sys(cnt[side]) < need)
+                            if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
+                    }
+                });
                 for (long long t = (long long)blockIdx.x * GNT + tid; t < tot; t += stride) {
                     int i, j, kk;
                     bool ok;
                     seam_point_of(sa, t, a.nxf, a.nyf, a.nzf, i, j, kk, ok);
                     if (ok) {
                         const int gk = sa.gz0 + kk;
-                        if (((i + j + gk) & 1) == colour && (seam_pop(sa, i, j, gk) & 1))
+                        if (((i + j + gk) & 1) == colour && (seam_pop(sa, i, j, gk) & 1)) {
                             dm = fmax(dm, sor_point<true>(sa, i, j, kk, omega));
+                            if (MULTI && (kk < 2 || kk >= g.nz - 2)) {
+                                // the point lies in a plane the neighbour keeps as a ghost plane
+                                const long long m = (long long)j * g.sy + i;
+                                const double v = p_new[(long long)kk * g.sz + m];
+                                const Img2 jx = image_offsets(i, g.nx, a.bx, a.bx);
+                                const Img2 jy = image_offsets(j, g.ny, a.by, a.by);
+                                if (kk < 2 && a.peer.has_lo) {
+                                    double* o = a.peer.lo_p[src ^ 1] +
+                                                (long long)(a.peer.lo_nz + kk) * g.sz + m;
+                                    o[0] = v;
+                                    store_images(o, 0, v, jx, jy.lo * g.sy, jy.hi * g.sy, 0, 0);
+                                }
+                                if (kk >= g.nz - 2 && a.peer.has_hi) {
+                                    double* o = a.peer.hi_p[src ^ 1] + (long long)(kk - g.nz) * g.sz + m;
+                                    o[0] = v;
+                                    store_images(o, 0, v, jx, jy.lo * g.sy, jy.hi * g.sy, 0, 0);
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -531,6 +589,10 @@ __global__ void __launch_bounds__(GNT, 3)
             // every CTA has drawn its last ticket of this iteration: re-arm the counter for it + 2
             if (a.dynamic) *((volatile unsigned long long*)&sync[4 + (it & 1)]) = 0ull;
             unsigned long long bits = *((volatile unsigned long long*)&ctrl->dmax_bits);
+            if (MULTI && SEAM) {  // our black odd sweep is complete: 2 (T + 1) sweeps delivered
+                if (a.peer.has_lo) red_release_sys_add(&a.peer.lo->seam_cnt[1], 1ull);
+                if (a.peer.has_hi) red_release_sys_add(&a.peer.hi->seam_cnt[0], 1ull);
+            }
             if (multi) {
                 // all-to-all of the local maxima through peer memory: slot (T & 1, me) + flag on
                 // every rank; then the maximum over all ranks' slots (same inputs on every rank)
@@ -565,6 +627,8 @@ int persist_capacity() {
         cudaFuncSetAttribute(sor_persist_kernel<true, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM) != cudaSuccess ||
         cudaFuncSetAttribute(sor_persist_kernel<false, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(sor_persist_kernel<true, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM) != cudaSuccess)
         return 0;
     int dev = 0, sms = 0, coop = 0, per_sm = 0, per_sm2 = 0;
@@ -579,8 +643,12 @@ int persist_capacity() {
                                                   GSMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, sor_persist_kernel<false, true>, GNT,
                                                   GSMEM);
+    int per_sm4 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, sor_persist_kernel<true, true>, GNT,
+                                                  GSMEM);
     if (per_sm2 < per_sm) per_sm = per_sm2;
     if (per_sm3 < per_sm) per_sm = per_sm3;
+    if (per_sm4 < per_sm) per_sm = per_sm4;
     if (per_sm > 3) per_sm = 3;
     {   // tuning override: co-resident CTAs per SM
         const char* e = getenv("O3D_PERSIST_CTAS");
@@ -658,10 +726,10 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     const bool seams = a.seam_x || a.seam_y || a.seam_z;
     f.nxf = a.seam_x ? (long long)a.ny * a.nz : 0;
     f.nyf = a.seam_y ? (long long)a.nx * a.nz : 0;
-    f.nzf = a.seam_z ? (long long)a.nx * a.ny : 0;
+    // the z seam is the last GLOBAL plane: only the rank that owns it sweeps it
+    f.nzf = (a.seam_z && a.gz0 + a.nz == a.gnz) ? (long long)a.nx * a.ny : 0;
     if (peer) f.peer = *peer;
     else memset(&f.peer, 0, sizeof(f.peer));
-    if (seams && f.peer.nranks > 1) return 2;  // slabs + odd periodic extents: split launches
     const long long items = (long long)ntiles * f.nch;
     unsigned G = (unsigned)(items < G_max ? items : G_max);
     {
@@ -685,9 +753,11 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     }
     if (cudaMemsetAsync(sync, 0, 32 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
     void* args[] = {(void*)&maps, (void*)&f, (void*)&ctrl, (void*)&sync};
-    const void* fn = seams ? (const void*)sor_persist_kernel<true, false>
-                           : (f.peer.nranks > 1 ? (const void*)sor_persist_kernel<false, true>
-                                                : (const void*)sor_persist_kernel<false, false>);
+    const bool mr = f.peer.nranks > 1;
+    const void* fn = seams ? (mr ? (const void*)sor_persist_kernel<true, true>
+                                 : (const void*)sor_persist_kernel<true, false>)
+                           : (mr ? (const void*)sor_persist_kernel<false, true>
+                                 : (const void*)sor_persist_kernel<false, false>);
     const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(GNT), args, GSMEM, st);
     count_launch();
     if (e != cudaSuccess) {

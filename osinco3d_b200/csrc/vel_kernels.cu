@@ -43,8 +43,11 @@ __device__ __forceinline__ Grad gradient(const RG& r, const Coefs3& q, int sim2d
 // FAST: DNS in 3-D with sim2d / iles resolved at compile time (straight-line code, no basic-block
 // breaks between the derivative evaluations).  !FAST: both are runtime flags; the branches keep
 // the live ranges of the LES instantiation inside 128 registers (no spills).
-template <bool FAST>
+// MODE 0: general (sim2d / iles runtime flags); 1: DNS in 3-D; 2: Smagorinsky LES in 3-D -- both
+// compile-time, straight-line code on the split ring.
+template <int MODE>
 struct RhsEpi {
+    static constexpr bool FAST = MODE != 0;
     static constexpr int STREAMS = 15;
     const double* f2[3];
     const double* f3[3];
@@ -95,7 +98,7 @@ struct RhsEpi {
                                           const Pre& pre) {
         const Grad G = gradient(r, q, FAST ? 0 : sim2d);
         double nut = 0.0;
-        if (!FAST && iles) {
+        if (MODE == 2 || (MODE == 0 && iles)) {
             nut = smagorinsky(G, csd2);
             nu_t[m] = nut;
         }
@@ -487,9 +490,10 @@ Coefs3 coefs(const Coef& cx, const Coef& cy, const Coef& cz) {
 
 }  // namespace
 
-template <bool FAST>
+template <int MODE>
 static int launch_rhs_t(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int zedge) {
-    RhsEpi<FAST> e;
+    constexpr bool FAST = MODE != 0;
+    RhsEpi<MODE> e;
     for (int c = 0; c < 3; ++c)
         e.f2[c] = r.f2[c], e.f3[c] = r.f3[c], e.f1[c] = r.f1[c], e.up[c] = r.up[c];
     e.nu_t = r.nu_t;
@@ -507,17 +511,17 @@ static int launch_rhs_t(cudaStream_t st, const Geom& g, const RhsArgs& r, int zm
         MarchMaps<6> m6;
         for (int c = 0; c < 3; ++c) m6.m[c] = *r.u[c].tm, m6.m[3 + c] = *r.u[c].tms;
         if (ring && ring[5] == '3')
-            return launch_march<0, 3, 3, RhsEpi<FAST>, 2, 0, 0, 1, 3>(st, g, m6, e, zmode, zedge);
-        return launch_march<0, 3, 2, RhsEpi<FAST>, 2, 0, 0, 1, 3>(st, g, m6, e, zmode, zedge);
+            return launch_march<0, 3, 3, RhsEpi<MODE>, 2, 0, 0, 1, 3>(st, g, m6, e, zmode, zedge);
+        return launch_march<0, 3, 2, RhsEpi<MODE>, 2, 0, 0, 1, 3>(st, g, m6, e, zmode, zedge);
     }
     // O3D_RHS_UNROLL=1: plane loop unrolled over the 8-stage ring (march.cuh, UNR = 8: ring
     // positions become immediates).  Measured equal at 256^3 and 1-2 % slower at 512^3 than the
     // rolled loop (the kernel is not instruction-bound), so the rolled loop is the default.
     static const bool unrolled = getenv("O3D_RHS_UNROLL") && atoi(getenv("O3D_RHS_UNROLL")) == 1;
     if (unrolled)
-        return launch_march<3, 0, 1, RhsEpi<FAST>, 2, 0, 0, 8>(st, g, maps3(r.u[0], r.u[1], r.u[2]),
+        return launch_march<3, 0, 1, RhsEpi<MODE>, 2, 0, 0, 8>(st, g, maps3(r.u[0], r.u[1], r.u[2]),
                                                                e, zmode, zedge);
-    return launch_march<3, 0, 1, RhsEpi<FAST>, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e, zmode,
+    return launch_march<3, 0, 1, RhsEpi<MODE>, 2>(st, g, maps3(r.u[0], r.u[1], r.u[2]), e, zmode,
                                                   zedge);
 }
 
@@ -533,8 +537,11 @@ int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int 
         const MarchMaps<3> mm = maps3(r.u[0], r.u[1], r.u[2]);
         return launch_march_roles<3, 2, 3, RhsRoleEpi>(st, g, mm, w, zmode, zedge);
     }
-    if (!g.sim2d && !r.iles) return launch_rhs_t<true>(st, g, r, zmode, zedge);
-    return launch_rhs_t<false>(st, g, r, zmode, zedge);
+    if (!g.sim2d && !r.iles) return launch_rhs_t<1>(st, g, r, zmode, zedge);
+    // O3D_RHS_LES=general keeps the LES step on the classic ring with runtime flags (round 1)
+    static const bool les_general = getenv("O3D_RHS_LES") && !strcmp(getenv("O3D_RHS_LES"), "general");
+    if (!g.sim2d && r.iles && !les_general) return launch_rhs_t<2>(st, g, r, zmode, zedge);
+    return launch_rhs_t<0>(st, g, r, zmode, zedge);
 }
 
 int launch_nu_t(cudaStream_t st, const Geom& g, const FieldRef* u, const Coef& cx,
