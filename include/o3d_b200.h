@@ -59,7 +59,14 @@ enum {
     O3D_CLOSURE_00 = 0,   /* der?_00   periodic                    */
     O3D_CLOSURE_P11 = 1,  /* der?p_11  free-slip, even ghost       */
     O3D_CLOSURE_I11 = 2,  /* der?i_11  free-slip, odd ghost        */
-    O3D_CLOSURE_2DSIM = 3 /* derz_2dsim / derzz_2dsim: zeros       */
+    O3D_CLOSURE_2DSIM = 3,/* derz_2dsim / derzz_2dsim: zeros       */
+    /* NEW, no counterpart in the reference: README.md:28 / the north star name a Dirichlet-x
+     * closure, but the source accepts PERIODIC / FREE_SLIP only and stops otherwise
+     * (src/initialization.f90:228-242).  Dirichlet wall on both faces of the axis: planes 1 and n
+     * hold the prescribed values and the field is continued by odd reflection ABOUT them,
+     * f(1-g) = 2 f(1) - f(1+g); der?i_11 is the f_wall = 0 special case.  Operator form only
+     * (o3d_der); verified against manufactured solutions (tests/test_gpu_dirichlet.py). */
+    O3D_CLOSURE_D11 = 4
 };
 
 /* SOR sweep ordering (DESIGN.md "Poisson").  The reference sweeps lexicographically

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const Geom g, const Gh
     const GhostJob jb = a.job[job];
     if (!((jb.axes >> axis) & 1u)) return;
     const bool odd = (jb.par >> axis) & 1u;
+    const bool dirichlet = (jb.par >> (axis + 4)) & 1u;  // GHOST_PAR_DIRICHLET(axis)
     double* __restrict__ p = jb.p;
     const int n = (axis == 0) ? g.nx : (axis == 1) ? g.ny : g.nz;
     const long long s = (axis == 0) ? 1 : (axis == 1) ? g.sy : g.sz;
@@ -52,7 +53,15 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const Geom g, const Gh
         const int src = map_index(q, n, mlo, mhi, refl);
         const long long base = (long long)ia * sa + (long long)ib * sb;
         const double v = p[base + (long long)src * s];
-        p[base + (long long)q * s] = (refl && odd) ? -v : v;
+        double gv = (refl && odd) ? -v : v;
+        if (refl && dirichlet) {
+            // Dirichlet wall (NEW closure, no counterpart in the reference): the stored boundary
+            // plane holds the prescribed value and the field is continued by odd reflection ABOUT
+            // that value, f(-g) = 2 f_wall - f(+g); der?i_11 is its f_wall = 0 special case
+            const double wall = p[base + (long long)(side ? n - 1 : 0) * s];
+            gv = 2.0 * wall - v;
+        }
+        p[base + (long long)q * s] = gv;
     }
 }
 

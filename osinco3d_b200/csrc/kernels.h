@@ -61,7 +61,8 @@ inline int pick_zchunk(int tiles_xy, int nz, int ctas_per_sm, int nfz, int strea
 enum : unsigned { GHOST_Z_LO_ONLY = 0x10u, GHOST_Z_HI_ONLY = 0x20u };
 struct GhostJob {
     double* p;
-    unsigned par;   // bit a set: odd along axis a (der?i_11), else even (der?p_11)
+    unsigned par;   // bit a set: odd along axis a (der?i_11), else even (der?p_11);
+                    // bit a + 4 set: Dirichlet wall along axis a (odd about the stored wall value)
     unsigned axes;  // bit a set: fill the ghosts of axis a (a = 0..2) | GHOST_Z_*_ONLY
 };
 struct GhostArgs {

@@ -74,7 +74,7 @@ void set_ab(o3d_session* s, const double* adt, const double* bdt, const double* 
 int der_impl(int axis, int order, int closure, double* df, const double* f, double d, int nx,
              int ny, int nz) {
     if (!df || !f || axis < 0 || axis > 2 || (order != 1 && order != 2) || closure < 0 ||
-        closure > 3)
+        closure > O3D_CLOSURE_D11)
         return O3D_ERR_INVALID;
     o3d_session* s;
     int rc = scratch(nx, ny, nz, d, d, d, &s);
@@ -94,7 +94,9 @@ int der_impl(int axis, int order, int closure, double* df, const double* f, doub
         GhostArgs ga;
         ga.njobs = 1;
         ga.job[0].p = src;
-        ga.job[0].par = (closure == O3D_CLOSURE_I11) ? (1u << axis) : 0u;
+        ga.job[0].par = (closure == O3D_CLOSURE_I11)   ? (1u << axis)
+                        : (closure == O3D_CLOSURE_D11) ? (1u << (axis + 4))
+                                                       : 0u;
         ga.job[0].axes = 1u << axis;
         if (launch_fill_ghosts(s->st, g, ga)) return O3D_ERR_CUDA;
     }

@@ -538,9 +538,13 @@ int launch_rhs(cudaStream_t st, const Geom& g, const RhsArgs& r, int zmode, int 
         return launch_march_roles<3, 2, 3, RhsRoleEpi>(st, g, mm, w, zmode, zedge);
     }
     if (!g.sim2d && !r.iles) return launch_rhs_t<1>(st, g, r, zmode, zedge);
-    // O3D_RHS_LES=general keeps the LES step on the classic ring with runtime flags (round 1)
-    static const bool les_general = getenv("O3D_RHS_LES") && !strcmp(getenv("O3D_RHS_LES"), "general");
-    if (!g.sim2d && r.iles && !les_general) return launch_rhs_t<2>(st, g, r, zmode, zedge);
+    // MODE 2 (LES resolved at compile time, split ring) is selectable with O3D_RHS_LES=static for
+    // A/B runs only: straight-line LES code holds the nine first derivatives across the Smagorinsky
+    // evaluation AND the three convective terms, ptxas spills 120 B at the 128-register cap and the
+    // kernel is slower than the branchy general instantiation on the classic ring (512^3, round 2:
+    // 4.48 ms split2 / 4.81 split3 / 4.94 classic against 3.81 ms general, profiles/r2g_les_variants.txt)
+    static const bool les_static = getenv("O3D_RHS_LES") && !strcmp(getenv("O3D_RHS_LES"), "static");
+    if (!g.sim2d && r.iles && les_static) return launch_rhs_t<2>(st, g, r, zmode, zedge);
     return launch_rhs_t<0>(st, g, r, zmode, zedge);
 }
 
