@@ -1020,10 +1020,12 @@ int spec_correct_launch(o3d_session* s) {
     for (int k = 0; k < 3; ++k)
         if (!up[k].p || !u[k]) return O3D_ERR_CUDA;
     if (!pp.p || !alt.p) return O3D_ERR_CUDA;
-    if (c.nranks > 1) {
+    if (c.nranks > 1 && !(s->last_sor_path & 2)) {
         // z slabs: the correction differentiates pp across the rank boundaries (3 ghost planes).
-        // Which ping-pong buffer holds the final iterate is only known on the device, so the planes
-        // of BOTH travel (one grouped exchange, 6 planes per side) and the gated kernel picks.
+        // A peer-memory solve has stored them into the neighbours' ghost planes already (both
+        // ping-pong buffers, every iteration); otherwise they travel now -- which buffer holds the
+        // final iterate is only known on the device, so the planes of BOTH go (one grouped
+        // exchange, 6 planes per side) and the gated kernel picks.
         const long long ioff = interior_offset(s->g);
         double* bases[2] = {pp.p - ioff, alt.p - ioff};
         const int widths[2] = {R, R};

@@ -265,6 +265,15 @@ static void peer_destroy(o3d_session* s) {
     PeerState* ps = s->peers;
     if (!ps) return;
     for (int q = 0; q < ps->nopened; ++q) cudaIpcCloseMemHandle(ps->opened[q]);
+    if (ps->ok && s->comm) {
+        // an exporter must not free memory that an importer still maps (undefined behaviour per
+        // the CUDA IPC contract): every rank has closed its mappings once this barrier is passed.
+        // o3d_session_destroy of a multi-rank session is collective.
+        double* flag = s->scal_d + 100;
+        if (g_api.AllReduce(flag, flag, 1, ncclFloat64_, ncclMax_, s->comm->nccl, s->st) ==
+            ncclSuccess_)
+            cudaStreamSynchronize(s->st);
+    }
     if (ps->mine) cudaFree(ps->mine);
     delete ps;
     s->peers = nullptr;

@@ -201,8 +201,9 @@ struct PeerBlock {
     unsigned long long init_cnt[2];       // solves whose initial ghost planes have arrived (low / high)
     unsigned long long seam_cnt[2];       // odd seam sweeps (2 per iteration) the neighbour has delivered
     unsigned long long pad0[10];
-    unsigned long long dmax_slot[2][16];  // [global iteration & 1][source rank]
-    unsigned long long dmax_flag[16];     // [source rank] = global iterations published so far
+    // residual maxima, flag-in-data: [global iteration & 1][2 * source rank + {0, 1}] =
+    // {high / low 32 data bits << 32 | 32-bit tag (iteration + 1)}
+    unsigned long long dmax_slot[2][32];
 };
 struct PeerSync {
     int nranks, rank;                     // nranks <= 1: single rank, nothing below is read

@@ -315,7 +315,10 @@ finished:
     if (tma && same_bc && h->iter > 0) {
         // the last pass wrote the even ghost images (faces, edges) of the iterate it stored:
         // the projection correction and the next solve find the closure in place
-        const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO);
+        // (z slabs, peer-memory solve: the kernel stored 3 planes per side of every iterate into
+        // the neighbours' ghost planes, so the rank-boundary halos are in place as well)
+        const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO) &&
+                           !(s->last_sor_path & 2);
         s->gaxes[O3D_F_PP] = 0x1u | 0x2u | 0x8u | 0x10u | (zhalo ? 0u : 0x4u);
         s->gpar[O3D_F_PP] = 0u;
     }

@@ -40,6 +40,10 @@ constexpr int GBX = GTX + 4, GBY = GTY + 4, GPL = GBX * GBY;  // 36 x 20 = 720 c
 constexpr int GP = 2;                                         // planes prefetched ahead
 constexpr int GNP = 5 + GP, GNR = 3 + GP, GNB = GP + 1;       // p stages, rhs stages, barriers
 constexpr int GSMEM = (GNP + GNR) * GPL * 8 + GNB * 8 + 32 * 8 + 16;
+// planes per side a rank stores into its neighbours' ghost planes: the pass reads 2, the projection
+// correction queued behind the solve differentiates pp with radius 3 -- with the third plane delivered
+// by the solve itself the correction needs no exchange at all
+constexpr int PD = 3;
 constexpr long long SPIN_LIMIT = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
 
 struct PersistArgs {
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(GNT, 3)
                 if (multi && it > 0) {
                     // ghost planes of the previous iterate come from the neighbours' CTAs: two
                     // planes per tile and side, counted in OUR memory over the whole session
-                    const unsigned long long need = 2ull * ntiles * T;
+                    const unsigned long long need = (unsigned long long)PD * ntiles * T;
                     const long long t0 = clock64();
                     if (SEAM) {  // ... and both odd seam sweeps of that iteration
                         if (kb < 2 && a.peer.has_lo)
@@ -470,9 +474,10 @@ __global__ void __launch_bounds__(GNT, 3)
                         // the two planes next to a rank boundary also go straight into the
                         // neighbour's ghost planes (value + x / y images: its TMA boxes read them)
                         double* o = nullptr;
-                        if (k < 2 && peer_lo) o = peer_lo + (long long)k * g.sz;
-                        if (k >= g.nz - 2 && peer_hi) o = peer_hi + (long long)k * g.sz;
-                        if (o) {
+                        if (k < PD && peer_lo) o = peer_lo + (long long)k * g.sz;
+                        double* o2 = (k >= g.nz - PD && peer_hi) ? peer_hi + (long long)k * g.sz : nullptr;
+                        if (!o) o = o2, o2 = nullptr;  // (slabs thinner than 2 PD planes: both sides)
+                        for (; o; o = o2, o2 = nullptr) {
                             if (inA) {
                                 o[0] = vA;
                                 store_images(o, 0, vA, ix, iyA.lo * g.sy, iyA.hi * g.sy, 0, 0);
@@ -493,8 +498,8 @@ __global__ void __launch_bounds__(GNT, 3)
             dmax = fmax(dmax, dloc);
             if (multi) {
                 // this item's copies in the neighbours' ghost planes are complete: release them
-                const int nlo = a.peer.has_lo ? max(0, min(ke, 2) - kb) : 0;
-                const int nhi = a.peer.has_hi ? max(0, ke - max(kb, g.nz - 2)) : 0;
+                const int nlo = a.peer.has_lo ? max(0, min(ke, PD) - kb) : 0;
+                const int nhi = a.peer.has_hi ? max(0, ke - max(kb, g.nz - PD)) : 0;
                 if (nlo | nhi) {
                     __syncthreads();
                     if (tid == 0) {
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(GNT, 3)
                     unsigned long long need = 0ull;
                     if (colour == 0) {
                         cnt[0] = &a.peer.mine->halo_cnt[0], cnt[1] = &a.peer.mine->halo_cnt[1];
-                        need = 2ull * ntiles * (T + 1ull);
+                        need = (unsigned long long)PD * ntiles * (T + 1ull);
                     } else {
                         if (a.peer.has_lo) red_release_sys_add(&a.peer.lo->seam_cnt[1], 1ull);
                         if (a.peer.has_hi) red_release_sys_add(&a.peer.hi->seam_cnt[0], 1ull);
@@ -559,19 +564,19 @@ __global__ void __launch_bounds__(GNT, 3)
                         const int gk = sa.gz0 + kk;
                         if (((i + j + gk) & 1) == colour && (seam_pop(sa, i, j, gk) & 1)) {
                             dm = fmax(dm, sor_point<true>(sa, i, j, kk, omega));
-                            if (MULTI && (kk < 2 || kk >= g.nz - 2)) {
+                            if (MULTI && (kk < PD || kk >= g.nz - PD)) {
                                 // the point lies in a plane the neighbour keeps as a ghost plane
                                 const long long m = (long long)j * g.sy + i;
                                 const double v = p_new[(long long)kk * g.sz + m];
                                 const Img2 jx = image_offsets(i, g.nx, a.bx, a.bx);
                                 const Img2 jy = image_offsets(j, g.ny, a.by, a.by);
-                                if (kk < 2 && a.peer.has_lo) {
+                                if (kk < PD && a.peer.has_lo) {
                                     double* o = a.peer.lo_p[src ^ 1] +
                                                 (long long)(a.peer.lo_nz + kk) * g.sz + m;
                                     o[0] = v;
                                     store_images(o, 0, v, jx, jy.lo * g.sy, jy.hi * g.sy, 0, 0);
                                 }
-                                if (kk >= g.nz - 2 && a.peer.has_hi) {
+                                if (kk >= g.nz - PD && a.peer.has_hi) {
                                     double* o = a.peer.hi_p[src ^ 1] + (long long)(kk - g.nz) * g.sz + m;
                                     o[0] = v;
                                     store_images(o, 0, v, jx, jy.lo * g.sy, jy.hi * g.sy, 0, 0);
@@ -595,21 +600,26 @@ __global__ void __launch_bounds__(GNT, 3)
                 if (a.peer.has_hi) red_release_sys_add(&a.peer.hi->seam_cnt[0], 1ull);
             }
             if (multi) {
-                // all-to-all of the local maxima through peer memory: slot (T & 1, me) + flag on
-                // every rank; then the maximum over all ranks' slots (same inputs on every rank)
+                // all-to-all of the local maxima through peer memory, flag-in-data: the 64-bit
+                // pattern travels as two 8-byte words {32 data bits, 32-bit tag = T + 1}, each a
+                // single store that is its own arrival flag -- no fence, no separate flag round
+                // trip.  Slots alternate with the iteration parity (a rank is at most one iteration
+                // ahead).  Same inputs on every rank -> identical exit / omega decisions.
                 const int me = a.peer.rank, P = a.peer.nranks;
+                const unsigned long long tag = (T + 1ull) & 0xffffffffull;
+                const unsigned long long w0 = (bits >> 32 << 32) | tag;
+                const unsigned long long w1 = (bits << 32) | tag;
                 for (int r = 0; r < P; ++r) {
-                    PeerBlock* q = a.peer.all[r];
-                    *((volatile unsigned long long*)&q->dmax_slot[T & 1][me]) = bits;
+                    volatile unsigned long long* q = &a.peer.all[r]->dmax_slot[T & 1][2 * me];
+                    q[0] = w0, q[1] = w1;
                 }
-                __threadfence_system();
-                for (int r = 0; r < P; ++r) st_release_sys(&a.peer.all[r]->dmax_flag[me], T + 1);
                 const long long t0 = clock64();
                 for (int r = 0; r < P; ++r) {
-                    while (ld_acquire_sys(&a.peer.mine->dmax_flag[r]) < T + 1)
+                    volatile unsigned long long* q = &a.peer.mine->dmax_slot[T & 1][2 * r];
+                    unsigned long long v0, v1;
+                    while (((v0 = q[0]) & 0xffffffffull) != tag || ((v1 = q[1]) & 0xffffffffull) != tag)
                         if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
-                    const unsigned long long b =
-                        *((volatile unsigned long long*)&a.peer.mine->dmax_slot[T & 1][r]);
+                    const unsigned long long b = (v0 >> 32 << 32) | (v1 >> 32);
                     bits = b > bits ? b : bits;
                 }
             }

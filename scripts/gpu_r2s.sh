@@ -9,9 +9,9 @@ echo "mgpu_check exit $?" >> gpurun_out/${TAG}_mgpu${N}_parity.log
 grep -c BITWISE-EQUAL gpurun_out/${TAG}_mgpu${N}_parity.log; grep "MISMATCH\|exit" gpurun_out/${TAG}_mgpu${N}_parity.log | head
 timeout 600 $TR --nproc-per-node $N --master-port 29521 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n${N}.json 2> gpurun_out/${TAG}_bench_n${N}.err
 tail -c 600 gpurun_out/${TAG}_bench_n${N}.err
-timeout 600 $TR --nproc-per-node $N --master-port 29522 bench.py --gpus $N --n 1024 --strong --steps 10 --warmup 4 --no-e2e --legs none > gpurun_out/${TAG}_bench_1024_strong_n${N}.json 2> gpurun_out/${TAG}_bench_1024_strong_n${N}.err
+timeout 600 $TR --nproc-per-node $N --master-port 29522 bench.py --gpus $N --grid 1024 --strong --steps 10 --warmup 4 --no-e2e --legs none > gpurun_out/${TAG}_bench_1024_strong_n${N}.json 2> gpurun_out/${TAG}_bench_1024_strong_n${N}.err
 tail -c 600 gpurun_out/${TAG}_bench_1024_strong_n${N}.err
-O3D_TRACE=8 timeout 300 $TR --nproc-per-node $N --master-port 29523 bench.py --gpus $N --n 512 --steps 6 --warmup 4 --no-e2e --legs none --no-parity > gpurun_out/${TAG}_trace512_n${N}.json 2> gpurun_out/${TAG}_trace512_n${N}.err
+O3D_TRACE=8 timeout 300 $TR --nproc-per-node $N --master-port 29523 bench.py --gpus $N --grid 512 --steps 6 --warmup 4 --no-e2e --legs none --no-parity > gpurun_out/${TAG}_trace512_n${N}.json 2> gpurun_out/${TAG}_trace512_n${N}.err
 grep "o3d trace" gpurun_out/${TAG}_trace512_n${N}.err | grep " r0 \|rank 0" > gpurun_out/${TAG}_trace_n${N}_rank0.txt
 O3D_SOR_PEER=0 timeout 600 $TR --nproc-per-node $N --master-port 29524 bench.py --gpus $N --steps 20 --warmup 5 --no-e2e --legs tgv256_periodic --no-parity > gpurun_out/${TAG}_bench_n${N}_nccl.json 2> gpurun_out/${TAG}_bench_n${N}_nccl.err
 python - <<PY
