@@ -122,6 +122,29 @@ int comm_create(o3d_session* s) {
         return O3D_ERR_COMM;
     }
     s->comm = c;
+    // Establish the point-to-point connections to BOTH ring neighbours now, wrap link included.
+    // NCCL sets a connection up lazily at the first send/recv between a pair, on the host, and
+    // that can take seconds at 8 GPUs.  The stencil halos of a run whose nbcz is free-slip never
+    // use the wrap link, but poisson_solver_0000 / _0011 wrap z whatever nbcz is
+    // (src/initialization.f90:283-301): its first use would then fall inside sor_solve, while the
+    // other ranks' persistent SOR kernels already spin on this rank's residual (observed at 8
+    // GPUs: their bounded spin expired).  One 8-byte ring exchange here takes the set-up out of
+    // the time loop.
+    if (c->nranks > 1) {
+        double* w = nullptr;
+        if (cudaMalloc(&w, 4 * sizeof(double)) == cudaSuccess) {
+            cudaMemsetAsync(w, 0, 4 * sizeof(double), s->st);
+            const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
+            g_api.GroupStart();
+            g_api.Send(w, 1, ncclFloat64_, up, c->nccl, s->st);
+            g_api.Recv(w + 1, 1, ncclFloat64_, dn, c->nccl, s->st);
+            g_api.Send(w + 2, 1, ncclFloat64_, dn, c->nccl, s->st);
+            g_api.Recv(w + 3, 1, ncclFloat64_, up, c->nccl, s->st);
+            g_api.GroupEnd();
+            cudaStreamSynchronize(s->st);
+            cudaFree(w);
+        }
+    }
     return O3D_OK;
 }
 

@@ -44,7 +44,9 @@ constexpr int GSMEM = (GNP + GNR) * GPL * 8 + GNB * 8 + 32 * 8 + 16;
 // correction queued behind the solve differentiates pp with radius 3 -- with the third plane delivered
 // by the solve itself the correction needs no exchange at all
 constexpr int PD = 3;
-constexpr long long SPIN_LIMIT = 6000000000ll;  // ~3 s of SM clocks: a lost peer must not hang the GPU
+// every wait on another CTA / rank is bounded (a lost peer must not hang the GPU): ~20 s of SM
+// clocks, far beyond any legitimate skew between ranks (host-side hiccups included)
+constexpr long long SPIN_LIMIT = 40000000000ll;
 
 struct PersistArgs {
     SorArgs s;            // geometry, operator, neighbour rule; s.pp / s.rhs unused by the pass
