@@ -126,7 +126,14 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
     }
     const double factor = sor_factor(s);
     s->last_sor_path = 0;
-    const bool speculate_p = s->spec_arm && tma && same_bc && id_pp == O3D_F_PP;
+    // `same_bc` is a per-rank fact (an interior rank of a z-slab run sees BM_HALO on both sides
+    // whatever the rules are), but everything that decides WHICH COLLECTIVE STEPS a rank takes
+    // must be the same on every rank: the solver's z rule against the session's z closure,
+    // globally.  They differ when nbcz is free-slip under poisson_solver_0000 / _0011 or periodic
+    // under _111111 (src/initialization.f90:283-301 looks at the x / y flags only).
+    const bool bc_match = a.mx == s->g.bx && a.my == s->g.by &&
+                          ((s->sor_variant != 2) == (c.nbcz1 == O3D_PERIODIC));
+    const bool speculate_p = s->spec_arm && tma && same_bc && bc_match && id_pp == O3D_F_PP;
     s->spec_state = 0;
     // ---- persistent path: the whole solve in one cooperative launch (sor_persist_kernel.cu) ----
     // O3D_SOR_PERSIST=0 or a forced host poll interval (sor_check_every) keep the launch-per-pass
@@ -144,7 +151,7 @@ int sor_solve(o3d_session* s, double* pp, const double* rhs, int* iters, double*
                 persist = false;  // NCCL halos + all-reduce per sweep, below
         }
         if (persist) {
-            if (multi && (id_rhs != O3D_F_RHS || !peer.push_init || fills_pending)) {
+            if (multi && (id_rhs != O3D_F_RHS || !peer.push_init || fills_pending || !bc_match)) {
                 // (a right-hand side that is not the session's O3D_F_RHS has no peer mapping:)
                 // ghost planes of the initial iterate (2) and of the right-hand side (1; constant
                 // over the solve) through one grouped NCCL exchange, stream-ordered before the
@@ -318,7 +325,7 @@ finished:
         // (z slabs, peer-memory solve: the kernel stored 3 planes per side of every iterate into
         // the neighbours' ghost planes, so the rank-boundary halos are in place as well)
         const bool zhalo = (s->g.bz_lo == BM_HALO || s->g.bz_hi == BM_HALO) &&
-                           !(s->last_sor_path & 2);
+                           !((s->last_sor_path & 2) && bc_match);
         s->gaxes[O3D_F_PP] = 0x1u | 0x2u | 0x8u | 0x10u | (zhalo ? 0u : 0x4u);
         s->gpar[O3D_F_PP] = 0u;
     }
