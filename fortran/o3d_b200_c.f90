@@ -290,6 +290,28 @@ module o3d_b200_c
        real(c_double), intent(out) :: host(*)
        integer(c_int) :: rc
      end function o3d_download
+     ! local planes [k0, k0+nk) only (0-based k0): a (nx,ny,nk) block, e.g. ux(:,:,k0+1:k0+nk)
+     function o3d_upload_planes(ses, field, host, k0, nk) bind(C, name="o3d_upload_planes") result(rc)
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ses
+       integer(c_int), value :: field, k0, nk
+       real(c_double), intent(in) :: host(*)
+       integer(c_int) :: rc
+     end function o3d_upload_planes
+     function o3d_download_planes(ses, field, host, k0, nk) bind(C, name="o3d_download_planes") result(rc)
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ses
+       integer(c_int), value :: field, k0, nk
+       real(c_double), intent(out) :: host(*)
+       integer(c_int) :: rc
+     end function o3d_download_planes
+     ! how the last red-black solve ran: persistent kernel / peer-memory halos (1 / 0 each)
+     function o3d_s_sor_path(ses, persistent, peer) bind(C, name="o3d_s_sor_path") result(rc)
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ses
+       integer(c_int), intent(out) :: persistent, peer
+       integer(c_int) :: rc
+     end function o3d_s_sor_path
      function o3d_s_predict_velocity(ses, itime) bind(C, name="o3d_s_predict_velocity") result(rc)
        import :: c_int, c_ptr
        type(c_ptr), value :: ses

@@ -19,13 +19,14 @@
 // launch-per-pass path => bitwise equal iterates, iteration counts and omega history
 // (tests/test_gpu_poisson.py::test_persistent_solve_equals_launch_per_pass_bitwise).
 //
-// Z slabs (nranks > 1): the two boundary planes per side of the new iterate are stored straight
-// into the neighbour rank's ghost planes through peer-mapped pointers (CUDA IPC over NVLink) by
-// the CTAs that compute them, followed by a system-scope release on a counter in the neighbour's
-// memory; a CTA whose chunk touches a slab end acquires that counter before it stages ghost
-// planes.  The residual maximum travels through per-rank slots + flags in peer memory and is
-// combined by the controlling CTA of every rank (identical inputs -> identical decisions).  No
-// NCCL call and no host inside the iteration.
+// Z slabs (nranks > 1): the three boundary planes per side of the new iterate (two for the next
+// pass, the third for the projection correction behind the solve) are stored straight into the
+// neighbour rank's ghost planes through peer-mapped pointers (CUDA IPC over NVLink) by the CTAs
+// that compute them, followed by a system-scope release on a counter in the neighbour's memory; a
+// CTA whose chunk touches a slab end acquires that counter before it stages ghost planes.  The
+// residual maximum travels as flag-in-data words (32 data bits | 32-bit iteration tag) into a slot
+// per source rank on every rank and is combined by the controlling CTA of each rank (identical
+// inputs -> identical decisions).  No NCCL call and no host inside the solve.
 #include <cstring>
 
 #include "kernels.h"
@@ -59,7 +60,6 @@ struct PersistArgs {
     int kmax, idyn;
     int fixed;            // smoother mode: no exit tests, the control step only counts
     int dynamic;          // items handed out through an atomic ticket counter
-    int oneshot;          // EXPERIMENT: one iteration, one CTA per item, nobody waits at the barrier
     long long nxf, nyf, nzf;  // sizes of the x / y / z seam planes (SEAM)
     // ---- z slabs: peer-mapped neighbours (null: none on that side) ----
     PeerSync peer;
@@ -87,9 +87,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
     asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -174,7 +171,7 @@ __global__ void __launch_bounds__(GNT, 3)
                 last();
                 __threadfence();
                 atomicExch(&sync[16], epoch);
-            } else if (!a.oneshot) {
+            } else {
                 const long long t0 = clock64();
                 while (ld_acquire_gpu(&sync[16]) < epoch) {
                     if (clock64() - t0 > SPIN_LIMIT) {
@@ -257,10 +254,8 @@ __global__ void __launch_bounds__(GNT, 3)
                 ch ^= 1;
             }
             const int i0 = (tile % a.tiles_x) * GTX, j0 = (tile / a.tiles_x) * GTY;
-            // z-chunk boundaries of tiles of odd parity are shifted by `zstagger` planes, so that a
-            // tile runs a few planes ahead of its four neighbours: the 2-cell halo they share is
-            // then requested twice a few microseconds apart (one DRAM fetch + one L2 hit) instead
-            // of simultaneously by CTAs marching in lockstep out of the grid barrier (both miss)
+            // (experiment knob, default 0: z-chunk boundaries of tiles of odd parity shifted by
+            // `zstagger` planes, so that a tile runs a few planes ahead of its four neighbours)
             const int zsh = (((tile % a.tiles_x) + (tile / a.tiles_x)) & 1) ? a.zstagger : 0;
             const int kb = ch ? ch * a.zchunk + zsh : 0;
             const int ke = ch + 1 < a.nch ? (ch + 1) * a.zchunk + zsh : g.nz;
@@ -309,7 +304,7 @@ __global__ void __launch_bounds__(GNT, 3)
                             if (clock64() - t0 > SPIN_LIMIT) { atomicExch(&ctrl->done, 9); break; }
                 }
                 if (multi && it > 0) {
-                    // ghost planes of the previous iterate come from the neighbours' CTAs: two
+                    // ghost planes of the previous iterate come from the neighbours' CTAs: PD
                     // planes per tile and side, counted in OUR memory over the whole session
                     const unsigned long long need = (unsigned long long)PD * ntiles * T;
                     const long long t0 = clock64();
@@ -473,7 +468,7 @@ __global__ void __launch_bounds__(GNT, 3)
                                          iz.lo * g.sz, iz.hi * g.sz);
                     }
                     if (MULTI) {
-                        // the two planes next to a rank boundary also go straight into the
+                        // the PD planes next to a rank boundary also go straight into the
                         // neighbour's ghost planes (value + x / y images: its TMA boxes read them)
                         double* o = nullptr;
                         if (k < PD && peer_lo) o = peer_lo + (long long)k * g.sz;
@@ -726,8 +721,10 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     }
     {
         // the last chunk of a shifted tile is `zstagger` planes shorter: keep it >= 2 planes
+        // O3D_PERSIST_STAGGER=<planes>: measured 0 .. 16 planes without any effect on the DRAM
+        // traffic of the static map (profiles/r2_sor_scheduling.txt); off by default
         const char* e = getenv("O3D_PERSIST_STAGGER");
-        int sh = e ? atoi(e) : 4;
+        int sh = e ? atoi(e) : 0;
         const int last = a.nz - (f.nch - 1) * f.zchunk;
         if (f.nch < 2) sh = 0;
         if (sh > last - 2) sh = last - 2 > 0 ? last - 2 : 0;
@@ -744,7 +741,7 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     if (peer) f.peer = *peer;
     else memset(&f.peer, 0, sizeof(f.peer));
     const long long items = (long long)ntiles * f.nch;
-    unsigned G = (unsigned)(items < G_max ? items : G_max);
+    const unsigned G = (unsigned)(items < G_max ? items : G_max);
     {
         // default: tickets.  CTAs that share an SM draw consecutive tickets, so neighbouring tiles
         // run on the same SM / GPC and the halo they share is found in L2; with the static
@@ -752,17 +749,6 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
         // 512^3: 3.6 GB instead of 2.4 GB per pass, profiles/r2_sor_scheduling.txt)
         const char* e = getenv("O3D_PERSIST_DYN");
         f.dynamic = (e && e[0] == '0') ? 0 : 1;
-    }
-    f.oneshot = 0;
-    {
-        const char* e = getenv("O3D_PERSIST_ONESHOT");
-        if (e && e[0] == '1' && !seams && f.peer.nranks <= 1) {
-            f.oneshot = 1, f.max_iters = 1, G = (unsigned)items;
-            if (cudaMemsetAsync(sync, 0, 32 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
-            sor_persist_kernel<false, false><<<G, GNT, GSMEM, st>>>(maps, f, ctrl, sync);
-            count_launch();
-            return cudaGetLastError() == cudaSuccess ? 0 : 1;
-        }
     }
     if (cudaMemsetAsync(sync, 0, 32 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
     void* args[] = {(void*)&maps, (void*)&f, (void*)&ctrl, (void*)&sync};

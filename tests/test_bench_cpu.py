@@ -73,3 +73,56 @@ def test_workload_names_and_weak_strong_grids():
     a = argparse.Namespace(n=512, bc="freeslip", les=True, strong=False)
     w = bench.workload(a, 1)
     assert w["name"] == "tgv_re2500_les_freeslip_512x512x512_ab3_sor" and w["phys"]["iles"] == 1
+
+
+def test_configs_legs_workloads_match_the_shipped_examples():
+    """the extra legs of bench.py (`configs`): grids, closures and Poisson settings of the shipped
+    examples (examples/*/parameters_*.o3d), weak-scaling replication in z, and initial slabs that
+    are consistent pieces of one global field (slab [z0, z0+nk) == the same planes of the whole)"""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    ml = bench.make_workload("mixing_layer")
+    assert ml["grid"] == (241, 241, 81) and ml["bc"] == (0, 1, 0) and ml["nscr"] == 1
+    assert ml["phys"]["iles"] == 1 and ml["phys"]["idyn"] == 1 and ml["phys"]["eps"] == 1e-5
+    assert bench.make_workload("mixing_layer", multigrid=1)["multigrid"] == 1
+    cj1, cj8 = bench.make_workload("cojet"), bench.make_workload("cojet", nranks=8)
+    assert cj1["grid"] == (257, 513, 129) and cj8["grid"] == (257, 513, 8 * 129)
+    assert cj1["bc"] == (0, 0, 0) and cj1["phys"]["omega"] == 1.35 and cj1["phys"]["kmax"] == 1000
+    assert abs(cj1["phys"]["dt"] - 0.07 * min(cj1["d"])) < 1e-18
+    per = bench.make_workload("tgv", nranks=4, n=256, bc="periodic")
+    assert per["grid"] == (256, 256, 4 * 256) and per["bc"] == (0, 0, 0)
+    fs = bench.make_workload("tgv", nranks=4, n=256)
+    assert fs["grid"] == (256, 256, 4 * 255 + 1)
+    # slabs are windows of one global field, whatever the chunking
+    for w in (bench.make_workload("tgv", n=24, perturb=True), bench.make_workload("tgv", n=24, les=True)):
+        whole = w["init"](0, 24)
+        part = w["init"](7, 5)
+        for k in whole:
+            assert np.array_equal(whole[k][:, :, 7:12], part[k]), k
+            assert whole[k].flags["F_CONTIGUOUS"] and whole[k].dtype == np.float64
+    f = ml["init"](0, 3)
+    assert set(f) == {"ux", "uy", "uz", "pp", "phi"} and f["phi"].min() >= 0.0 and f["phi"].max() <= 1.0
+    assert abs(f["ux"]).max() <= 0.5 + 0.03 * 1.2 and not f["uz"].any()
+    g = cj1["init"](0, 2)
+    assert "phi" not in g and 0.99 < g["ux"].max() <= 1.03 and abs(g["uy"]).max() <= 0.03 + 1e-12
+
+
+def test_ncu_traffic_is_keyed_by_kernel_and_grid():
+    sys.path.insert(0, ROOT)
+    import bench
+    k = "march_kernel<0,3,2,RhsEpi<dns>,split ring>"
+    assert bench.ncu_traffic(k, (256, 256, 256)) > 1.9e9
+    assert bench.ncu_traffic(k, (512, 512, 512)) is None       # no capture at that size: null
+    assert bench.ncu_traffic("no_such_kernel", (256, 256, 256)) is None
+
+
+def test_digest_is_a_bitwise_fingerprint():
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    a = np.asfortranarray(np.random.default_rng(1).standard_normal((5, 4, 3)))
+    b = a.copy(order="F")
+    assert bench.digest(a) == bench.digest(b)
+    b[2, 1, 1] = np.nextafter(b[2, 1, 1], 1.0)
+    assert bench.digest(a) != bench.digest(b)

@@ -1,4 +1,5 @@
-"""Multi-GPU parity: P z-slabs over NCCL == one GPU, bit for bit.  Needs >= 2 GPUs
+"""Multi-GPU parity: P z-slabs (stencil halos over NCCL, SOR halos and residuals
+through peer-mapped memory) == one GPU, bit for bit.  Needs >= 2 GPUs
 on the box (`gpurun --gpus 2`); on a 1-GPU box the test is skipped with that reason (two NCCL
 ranks cannot share one device)."""
 import os
@@ -11,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_slab_decomposition_is_bitwise_equal_to_one_gpu(gpu, world):
     if gpu.device_count() < world:
         pytest.skip("needs %d GPUs on one box, found %d" % (world, gpu.device_count()))
