@@ -481,16 +481,20 @@ def run_e2e(o3d, w, steps, warmup, chunks=0):
     pool.close()
     M.set_pipeline(chunks_before)
     # bytes per step, counted from the arrays the three calls copy (see modules.cu)
-    h2d, d2h = M.e2e_bytes_per_step(N) if hasattr(M, "e2e_bytes_per_step") else (
-        (3 + 6) * N * 8 + 4 * N * 8 + 4 * N * 8, (3 + 1 + 9) * N * 8 + 1 * N * 8 + 3 * N * 8)
+    hostshift = bool(chunks) and bool(M.get_hostshift())
+    h2d, d2h = M.e2e_bytes_per_step(N, ph["iles"])
     ms = 1e3 * dt_wall / steps
     return {"value": N / 1e6 / (ms / 1e3), "unit": "Mpts*steps/s", "ms_per_step": ms,
             "steps": steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "sor_iters_per_step": float(np.mean(iters)), "pipeline_chunks": chunks,
+            "host_shift": hostshift,
             "path": "o3d_predict_velocity + o3d_correct_pression + o3d_correct_velocity with "
                     "pinned HOST arrays (stateless drop-in procedures), wall clock"
                     + ("; predict / correct_velocity pipelined over %d z chunks (upload, kernel "
-                       "and download of successive chunks overlap)" % chunks if chunks else "")}
+                       "and download of successive chunks overlap)" % chunks if chunks else "")
+                    + ("; history levels 2 and 3 and the DNS nu_t = 0 are made in the host "
+                       "arrays by worker threads instead of being downloaded "
+                       "(src/integration.f90:176-188)" if hostshift else "")}
 
 
 def run_e2e_resident(o3d, ses, steps):

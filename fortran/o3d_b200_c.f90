@@ -259,6 +259,13 @@ module o3d_b200_c
        integer(c_int), value :: chunks
        integer(c_int) :: rc
      end function o3d_set_pipeline
+     !> 1: the history-level copies at the end of predict_velocity (fu?(:,:,:,3) = fu?(:,:,:,2),
+     !> fu?(:,:,:,2) = fu?(:,:,:,1)) are made in the host arrays instead of being downloaded
+     function o3d_set_hostshift(on) bind(C, name="o3d_set_hostshift") result(rc)
+       import :: c_int
+       integer(c_int), value :: on
+       integer(c_int) :: rc
+     end function o3d_set_hostshift
 
      !=== section B of include/o3d_b200.h: device-resident session ==========================
      function o3d_session_create(cfg, ses) bind(C, name="o3d_session_create") result(rc)

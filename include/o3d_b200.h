@@ -108,6 +108,17 @@ int o3d_host_unregister(void* ptr);
  * are correct but the copies serialise. */
 int o3d_set_pipeline(int chunks);
 int o3d_get_pipeline(void);
+/* Host-side history shift of the pipelined o3d_predict_velocity (process-wide).  The reference
+ * ends predict_velocity with whole-array copies between the time levels of fux / fuy / fuz
+ * (src/integration.f90:176-188: level 3 = old level 2, level 2 = level 1 = new f).  on = 1: only
+ * level 1 is copied back from the device; levels 2 and 3 -- and nu_t = 0.d0 of a DNS call,
+ * src/integration.f90:112 -- are produced in the host arrays by memcpy / memset on worker
+ * threads (O3D_HOSTSHIFT_THREADS, default min(8, cores - 2)), chunk by chunk behind the
+ * transfers: 6 (DNS: 7) of the 13 arrays of the call no longer cross PCIe.  The arrays are bit
+ * for bit those of on = 0.  Default: environment variable O3D_HOSTSHIFT, else see
+ * csrc/pipeline.cu.  No effect on unpipelined calls. */
+int o3d_set_hostshift(int on);
+int o3d_get_hostshift(void);
 /* The schedule a pipelined call would use for nz planes under the current setting (host logic
  * only, no device needed): returns the number of chunks C (0 = plain path); z_bounds[C+1] = plane
  * ranges [z[c], z[c+1]); issue_after[C] = the upload chunk after which the kernels on chunk c are

@@ -24,9 +24,12 @@
 #include <cstdlib>
 #include <vector>
 
+#include "host_copier.h"
 #include "session.h"
 
 namespace o3d {
+
+constexpr int MAX_CHUNKS = 64;
 
 struct Pipe {
     cudaStream_t up[2], dn[2];
@@ -35,17 +38,26 @@ struct Pipe {
     long long slot_elems;
     cudaEvent_t ev_start;
     std::vector<cudaEvent_t> ev;
+    // host-side history shift (host_copier.h): worker threads, the events they wait on (created
+    // with cudaEventBlockingSync: a waiting worker sleeps instead of spinning on a core the
+    // caller may need), one "level 3 <- level 2 done" flag per chunk and component
+    HostCopier* hc;
+    std::vector<cudaEvent_t> hev;
+    std::atomic<int> a_done[3 * MAX_CHUNKS];
 };
 
 namespace {
 
 int g_pipe_setting = -1;  // -1: take O3D_PIPELINE from the environment at first use
+// Host-side history shift of the pipelined o3d_predict_velocity (host_copier.h): -1 = take
+// O3D_HOSTSHIFT from the environment at first use.
+int g_hostshift = -1;
+constexpr int DEFAULT_HOSTSHIFT = 0;
 // Default number of chunks.  Measured end to end on the 256^3 TGV step (B200, PCIe Gen5, pinned
 // arrays; profiles/r1p_e2e_pipeline.jsonl, r1q_e2e_pipeline.jsonl): 86.8 ms unpipelined, 71.3 /
 // 65.8 / 65.1 ms with 4 / 8 / 16 chunks; flat (63.4 - 63.9 ms on a second box) from 12 to 32.
 constexpr int DEFAULT_CHUNKS = 16;
 
-constexpr int MAX_CHUNKS = 64;
 constexpr int MIN_PLANES = 8;  // per chunk: > stencil radius + mirror source planes
 
 const unsigned NAT3[3] = {0x1u, 0x2u, 0x4u};
@@ -86,7 +98,23 @@ void make_plan(int nz, int chunks, bool wrapz, Plan& p) {
     }
 }
 
-int ensure_pipe(o3d_session* s, long long slot_elems, int nev) {
+int hostshift_threads() {
+    const char* e = getenv("O3D_HOSTSHIFT_THREADS");
+    int n = e ? atoi(e) : 0;
+    if (n < 1) {
+        // leave two cores to the caller and the CUDA driver threads; 8 workers saturate what the
+        // PCIe link frees up (6 fields of memcpy against 6 fields of D2H)
+        const unsigned hw = std::thread::hardware_concurrency();
+        n = hw ? (int)hw - 2 : 4;
+        if (n > 8) n = 8;
+    }
+    return n < 1 ? 1 : (n > 64 ? 64 : n);
+}
+
+int wait_event(void* ev) { return (int)cudaEventSynchronize((cudaEvent_t)ev); }
+void enter_device(int dev) { cudaSetDevice(dev); }
+
+int ensure_pipe(o3d_session* s, long long slot_elems, int nev, int nhev = 0) {
     Pipe* p = s->pipe;
     if (!p) {
         p = new (std::nothrow) Pipe();
@@ -94,6 +122,7 @@ int ensure_pipe(o3d_session* s, long long slot_elems, int nev) {
         for (int l = 0; l < 2; ++l) p->up[l] = p->dn[l] = nullptr, p->slot_up[l] = p->slot_dn[l] = nullptr;
         p->slot_elems = 0;
         p->ev_start = nullptr;
+        p->hc = nullptr;
         s->pipe = p;
         for (int l = 0; l < 2; ++l) {
             O3D_CUDA_CHECK(cudaStreamCreateWithFlags(&p->up[l], cudaStreamNonBlocking));
@@ -119,6 +148,18 @@ int ensure_pipe(o3d_session* s, long long slot_elems, int nev) {
         O3D_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         p->ev.push_back(e);
     }
+    while ((int)p->hev.size() < nhev) {
+        cudaEvent_t e;
+        O3D_CUDA_CHECK(
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+        p->hev.push_back(e);
+    }
+    if (nhev && !p->hc) {
+        int dev = 0;
+        O3D_CUDA_CHECK(cudaGetDevice(&dev));
+        p->hc = new (std::nothrow) HostCopier(hostshift_threads(), wait_event, enter_device, dev);
+        if (!p->hc) return O3D_ERR_INVALID;
+    }
     return O3D_OK;
 }
 
@@ -131,8 +172,10 @@ struct Run {
     const int* z;           // = pl.z
     long long plane;        // nx * ny
     int n_up, n_dn;         // transfer counters: lane = counter & 1
+    int dn_lane;            // lane of the last download()
+    bool hostshift;
 
-    int init(o3d_session* ses, int chunks) {
+    int init(o3d_session* ses, int chunks, bool hs = false) {
         s = ses;
         make_plan(s->g.nz, chunks, s->g.bz_lo == BM_WRAP, pl);
         C = pl.C;
@@ -143,9 +186,13 @@ struct Run {
             if (z[c + 1] - z[c] > maxnk) maxnk = z[c + 1] - z[c];
         plane = (long long)s->g.nx * s->g.ny;
         n_up = n_dn = 0;
-        int rc = ensure_pipe(s, plane * maxnk, 3 * C);
+        dn_lane = 0;
+        hostshift = hs;
+        int rc = ensure_pipe(s, plane * maxnk, 3 * C, hs ? 5 * C : 0);
         if (rc) return rc;
         p = s->pipe;
+        if (hs)
+            for (int i = 0; i < 3 * C; ++i) p->a_done[i].store(0, std::memory_order_relaxed);
         // the lanes start behind everything queued on the session stream so far (the lazy
         // zero fill of freshly allocated fields, the memsets of the caller)
         O3D_CUDA_CHECK(cudaEventRecord(p->ev_start, s->st));
@@ -157,6 +204,12 @@ struct Run {
     }
     cudaEvent_t ev_up(int c, int lane) const { return p->ev[2 * c + lane]; }
     cudaEvent_t ev_cmp(int c) const { return p->ev[2 * C + c]; }
+    // events the host workers wait on: upload chunk c complete on lane l; level 1 of component k,
+    // chunk c, has landed in the host array
+    cudaEvent_t hev_up(int c, int lane) const { return p->hev[2 * c + lane]; }
+    cudaEvent_t hev_l1(int c, int k) const { return p->hev[2 * C + 3 * c + k]; }
+    long long chunk_off(int c) const { return (long long)z[c] * plane; }
+    size_t chunk_bytes(int c) const { return (size_t)(plane * (z[c + 1] - z[c])) * sizeof(double); }
     // last upload chunk that chunk c reads
     int need(int c) const { return pl.need[c]; }
     // planes of chunk c: host array -> staging slot -> padded field `d` (interior origin)
@@ -188,7 +241,7 @@ struct Run {
         return O3D_OK;
     }
     int download(const double* d, double* host, int c) {
-        const int lane = (n_dn++) & 1;
+        const int lane = dn_lane = (n_dn++) & 1;
         const int k0 = z[c], nk = z[c + 1] - z[c];
         if (launch_unpack_planes(p->dn[lane], s->g, d, p->slot_dn[lane], k0, nk)) {
             set_error("unpack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -229,6 +282,11 @@ struct Run {
             if ((q = cudaStreamSynchronize(p->dn[l])) != cudaSuccess) e = q;
         }
         if ((q = cudaStreamSynchronize(s->st)) != cudaSuccess) e = q;
+        // ... and every host-made output is in place
+        if (hostshift && p->hc) {
+            const int he = p->hc->drain();
+            if (he && e == cudaSuccess) e = (cudaError_t)he;
+        }
         if (e != cudaSuccess) {
             set_error("pipelined procedure failed: %s", cudaGetErrorString(e));
             return O3D_ERR_CUDA;
@@ -253,9 +311,20 @@ int pipe_chunks(int nz) {
     return p.C;
 }
 
+int hostshift_setting() {
+    if (g_hostshift < 0) {
+        const char* e = getenv("O3D_HOSTSHIFT");
+        g_hostshift = e ? (atoi(e) != 0) : DEFAULT_HOSTSHIFT;
+    }
+    return g_hostshift;
+}
+
 void pipe_destroy(o3d_session* s) {
     Pipe* p = s->pipe;
     if (!p) return;
+    delete p->hc;  // joins the workers (the queue is empty: every call drains it)
+    p->hc = nullptr;
+    for (auto e : p->hev) cudaEventDestroy(e);
     for (int l = 0; l < 2; ++l) {
         if (p->up[l]) cudaStreamSynchronize(p->up[l]);
         if (p->dn[l]) cudaStreamSynchronize(p->dn[l]);
@@ -304,11 +373,24 @@ int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
             fout[k][l] = field(s, hist_id(s, k, l + 1));
             if (!fout[k][l]) return O3D_ERR_CUDA;
         }
+    // Host-side history shift (host_copier.h).  After the call the reference leaves
+    //     itscheme = 3:  level 3 = old level 2,  level 2 = level 1 = new f
+    //     itscheme = 2:  level 2 = level 1 = new f,  level 3 untouched
+    //     otherwise   :  level 1 = new f,  levels 2 and 3 untouched     (src/integration.f90:176-188)
+    // and the host holds the old levels: only level 1 has to cross PCIe.  The copies are memcpy
+    // jobs on worker threads, ordered against the DMA transfers of the same chunk by events; the
+    // result is bit for bit what the downloads would have delivered (memcpy and PCIe both move
+    // bits).  DNS: nu_t = 0.d0 (src/integration.f90:112) is a host memset.
+    const bool hs = hostshift_setting() != 0;
+    const int itscheme = s->cfg.itscheme;
     Run r;
-    if ((rc = r.init(s, C))) return rc;
+    if ((rc = r.init(s, C, hs))) return rc;
     auto body = [&]() -> int {
         int rc2;
         bool issued[MAX_CHUNKS] = {false};
+        if (hs && !a.nu_t)
+            for (int c = 0; c < C; ++c)
+                r.p->hc->push(zero_job(nu_t_h, r.chunk_off(c), r.chunk_bytes(c)));
         for (int j = 0; j < C; ++j) {
             for (int k = 0; k < 3; ++k)
                 if ((rc2 = r.upload(ud[k], u_h[k], j))) return rc2;
@@ -318,6 +400,15 @@ int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
                 if ((rc2 = r.upload(f3d[k], f_h[k] + 2 * N, j))) return rc2;
             }
             if ((rc2 = r.uploaded(j))) return rc2;
+            if (hs && itscheme == 3) {
+                // job A: level 3 <- old level 2 of chunk j, once the DMA engine has read both
+                for (int l = 0; l < 2; ++l)
+                    O3D_CUDA_CHECK(cudaEventRecord(r.hev_up(j, l), r.p->up[l]));
+                for (int k = 0; k < 3; ++k)
+                    r.p->hc->push(shift_job_a(f_h[k], N, r.chunk_off(j), r.chunk_bytes(j),
+                                              r.hev_up(j, 0), r.hev_up(j, 1),
+                                              &r.p->a_done[3 * j + k]));
+            }
             for (int c = 0; c < C; ++c) {
                 if (issued[c] || r.need(c) > j) continue;
                 issued[c] = true;
@@ -332,16 +423,33 @@ int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
                     return O3D_ERR_CUDA;
                 }
                 if ((rc2 = r.computed(c))) return rc2;
+                if (hs) {
+                    // level 1 first: its arrival releases job B
+                    for (int k = 0; k < 3; ++k) {
+                        if ((rc2 = r.download(fout[k][0], f_h[k], c))) return rc2;
+                        if (itscheme != 2 && itscheme != 3) continue;
+                        O3D_CUDA_CHECK(cudaEventRecord(r.hev_l1(c, k), r.p->dn[r.dn_lane]));
+                        // job B: level 2 <- new level 1 of chunk c.  The upload of the old
+                        // level 2 of this chunk is complete (the kernel on chunk c waited for
+                        // upload need(c) >= c); job A (pushed with upload c <= j) has read it
+                        // once a_done is set.
+                        r.p->hc->push(shift_job_b(
+                            f_h[k], N, r.chunk_off(c), r.chunk_bytes(c), r.hev_l1(c, k),
+                            (itscheme == 3) ? &r.p->a_done[3 * c + k] : nullptr));
+                    }
+                }
                 for (int k = 0; k < 3; ++k)
                     if ((rc2 = r.download(a.up[k], up_h[k], c))) return rc2;
                 // (DNS: the field the caller zeroed -- nu_t = 0.d0, src/integration.f90:112 --
                 // since the kernel arguments carry no nu_t then)
-                if ((rc2 = r.download(a.nu_t ? a.nu_t : field(s, O3D_F_NU_T), nu_t_h, c)))
-                    return rc2;
-                for (int k = 0; k < 3; ++k)
-                    for (int l = 0; l < 3; ++l)
-                        if ((rc2 = r.download(fout[k][l], f_h[k] + (long long)l * N, c)))
-                            return rc2;
+                if (!hs || a.nu_t)
+                    if ((rc2 = r.download(a.nu_t ? a.nu_t : field(s, O3D_F_NU_T), nu_t_h, c)))
+                        return rc2;
+                if (!hs)
+                    for (int k = 0; k < 3; ++k)
+                        for (int l = 0; l < 3; ++l)
+                            if ((rc2 = r.download(fout[k][l], f_h[k] + (long long)l * N, c)))
+                                return rc2;
             }
         }
         return O3D_OK;
@@ -433,6 +541,14 @@ extern "C" int o3d_set_pipeline(int chunks) {
 }
 
 extern "C" int o3d_get_pipeline(void) { return o3d::pipe_setting(); }
+
+extern "C" int o3d_set_hostshift(int on) {
+    if (on < 0 || on > 1) return O3D_ERR_INVALID;
+    o3d::g_hostshift = on;
+    return O3D_OK;
+}
+
+extern "C" int o3d_get_hostshift(void) { return o3d::hostshift_setting(); }
 
 extern "C" int o3d_pipeline_plan(int nz, int periodic_z, int* z_bounds, int* issue_after,
                                  int* zfill) {

@@ -48,6 +48,29 @@ def get_pipeline():
     return lib().o3d_get_pipeline()
 
 
+def set_hostshift(on):
+    """1: the pipelined predict_velocity downloads only history level 1 and makes levels 2 and 3
+    (src/integration.f90:176-188) and the DNS nu_t = 0 in the host arrays with worker threads;
+    bitwise the same arrays"""
+    check(lib().o3d_set_hostshift(1 if on else 0))
+
+
+def get_hostshift():
+    return lib().o3d_get_hostshift()
+
+
+def e2e_bytes_per_step(N, iles=0, itscheme=3):
+    """(H2D, D2H) bytes one predict_velocity + correct_pression + correct_velocity chain moves for
+    N grid points under the current settings (csrc/modules.cu, csrc/pipeline.cu)"""
+    h2d = (3 + 6) + 4 + 4
+    if get_hostshift() and get_pipeline() >= 2:
+        down_pred = 3 + 3 + (1 if iles == 1 else 0)
+    else:
+        down_pred = 3 + 1 + 9
+    d2h = down_pred + 1 + 3
+    return h2d * N * 8, d2h * N * 8
+
+
 def der(axis, order, closure, f, d):
     df = _like(f)
     nx, ny, nz = f.shape

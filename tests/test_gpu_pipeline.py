@@ -70,12 +70,16 @@ def _correct(gpu, up, pp, d, dt, pool=None):
     return u, rc == L.ERR_DIVERGED
 
 
-@pytest.fixture
-def pipeline(gpu):
+@pytest.fixture(params=[0, 1], ids=["download", "hostshift"])
+def pipeline(gpu, request):
+    """every test runs twice: history levels 2, 3 (and the DNS nu_t) downloaded, and made in the
+    host arrays by the worker threads of csrc/host_copier.h (o3d_set_hostshift)"""
     from osinco3d_b200 import modules as M
-    before = M.get_pipeline()
+    before, hs_before = M.get_pipeline(), M.get_hostshift()
+    M.set_hostshift(request.param)
     yield M
     M.set_pipeline(before)
+    M.set_hostshift(hs_before)
 
 
 CASES = [
@@ -167,6 +171,34 @@ def test_pipelined_calls_with_pinned_arrays_and_a_whole_projection_step(gpu, pip
         pool.close()
     for a, b in zip(*results):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("itscheme,itime,iles", [(3, 3, 0), (3, 1, 1), (2, 4, 0), (1, 4, 0),
+                                                 (5, 1, 0)])
+def test_hostshift_leaves_untouched_levels_alone_and_fills_the_rest(gpu, pipeline, itscheme,
+                                                                    itime, iles):
+    """src/integration.f90:176-188 on pinned arrays pre-filled so that every level is
+    distinguishable: itscheme 3 -> (new, new, old 2); 2 -> (new, new, old 3); anything else ->
+    (new, old 2, old 3) (`select case` without a default; itscheme = 5 is accepted on the Euler
+    start-up step, src/integration.f90:84-105)"""
+    M = pipeline
+    shape = (40, 24, 64)
+    d = (PI / (shape[0] - 1),) * 3
+    M.schemes(1, 1, 1, 1, 1, 1)
+    M.set_pipeline(5)
+    pool = gpu.PinnedPool()
+    u, f, _ = _inputs(shape, 600, pool)
+    old = [a.copy() for a in f]
+    up, nu_t = _predict(gpu, u, f, d, itime, itscheme, iles, pool)
+    for k in range(3):
+        new = f[k][..., 0]
+        assert not np.array_equal(new, old[k][..., 0])
+        exp2 = new if itscheme in (2, 3) else old[k][..., 1]
+        exp3 = old[k][..., 1] if itscheme == 3 else old[k][..., 2]
+        assert np.array_equal(f[k][..., 1], exp2), (k, "level 2")
+        assert np.array_equal(f[k][..., 2], exp3), (k, "level 3")
+    assert (np.max(nu_t) > 0.0) if iles else (not nu_t.any())
+    pool.close()
 
 
 def test_pipelined_correct_velocity_reports_divergence(gpu, pipeline):

@@ -79,3 +79,59 @@ def test_thin_grids_and_the_off_switch(plib):
     assert plan(plib, 256, 0)[0] == 0           # one chunk = no pipeline
     assert plib.o3d_set_pipeline(-1) != 0       # O3D_ERR_INVALID
     assert plib.o3d_get_pipeline() == 1
+
+
+def test_hostshift_switch(plib):
+    before = plib.o3d_get_hostshift()
+    assert before in (0, 1)
+    assert plib.o3d_set_hostshift(1) == 0 and plib.o3d_get_hostshift() == 1
+    assert plib.o3d_set_hostshift(0) == 0 and plib.o3d_get_hostshift() == 0
+    assert plib.o3d_set_hostshift(2) != 0 and plib.o3d_set_hostshift(-1) != 0
+    assert plib.o3d_get_hostshift() == 0
+    plib.o3d_set_hostshift(before)
+
+
+def test_e2e_byte_accounting_follows_the_switches(plib):
+    from osinco3d_b200 import modules as M
+    before = plib.o3d_get_hostshift()
+    N = 1000
+    plib.o3d_set_pipeline(16)
+    plib.o3d_set_hostshift(0)
+    assert M.e2e_bytes_per_step(N) == (17 * N * 8, 17 * N * 8)
+    plib.o3d_set_hostshift(1)
+    # predict: ux_pred, uy_pred, uz_pred + level 1 of fux, fuy, fuz (+ nu_t when LES);
+    # correct_pression: pp;  correct_velocity: ux, uy, uz
+    assert M.e2e_bytes_per_step(N) == (17 * N * 8, 10 * N * 8)
+    assert M.e2e_bytes_per_step(N, iles=1) == (17 * N * 8, 11 * N * 8)
+    plib.o3d_set_pipeline(0)                     # unpipelined calls download everything
+    assert M.e2e_bytes_per_step(N) == (17 * N * 8, 17 * N * 8)
+    plib.o3d_set_hostshift(before)
+
+
+@pytest.mark.parametrize("tsan", [True, False])
+def test_host_copier_order_protocol(tmp_path, tsan):
+    """csrc/host_copier.h with the device replaced by threads (tests/cpu/host_copier_test.cpp):
+    every history level and nu_t end up as src/integration.f90:176-188 leaves them, for
+    itscheme 1 / 2 / 3, mirror and periodic z schedules, 1 - 5 workers; under ThreadSanitizer an
+    unordered access of a worker and a "DMA" thread to the same host array fails the test."""
+    import os
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_copier_test")
+    cmd = [gxx, "-std=c++17", "-O1", "-g", "-Wall", "-Wextra", "-Werror", "-o", exe,
+           os.path.join(root, "tests", "cpu", "host_copier_test.cpp"), "-lpthread"]
+    if tsan:
+        cmd.insert(1, "-fsanitize=thread")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if tsan and r.returncode != 0 and "sanitize" in (r.stdout + r.stderr):
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    if tsan and "FATAL: ThreadSanitizer" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this sandbox: " + r.stderr.strip()[:120])
+    assert r.returncode == 0 and "host copier OK" in r.stdout, r.stdout + r.stderr
+    assert "ThreadSanitizer" not in r.stderr, r.stderr
