@@ -455,14 +455,19 @@ def run_e2e(o3d, w, steps, warmup, chunks=0):
     A, B, Cc = v3(adt), v3(bdt), v3(cdt)
     cd = C.c_double
 
+    call_s = [0.0, 0.0, 0.0]     # wall time inside each of the three (synchronous) procedures
+
     def step(itime):
+        t = [time.perf_counter()]
         o3d._lib.check(lib.o3d_predict_velocity(
             P(up[0]), P(up[1]), P(up[2]), P(u[0]), P(u[1]), P(u[2]), P(f[0]), P(f[1]), P(f[2]),
             cd(ph["re"]), A, B, Cc, itime, 3, cd(d), cd(d), cd(d), n, n, n, ph["iles"],
             cd(ph["cs"]), cd(delta), P(nu_t)))
+        t.append(time.perf_counter())
         o3d._lib.check(lib.o3d_correct_pression(
             P(pp), P(up[0]), P(up[1]), P(up[2]), cd(d), cd(d), cd(d), n, n, n, cd(ph["dt"]),
             C.byref(omega), cd(ph["eps"]), 10000, ph["idyn"], 0, C.byref(it), C.byref(dmax)))
+        t.append(time.perf_counter())
         o3d._lib.check(lib.o3d_correct_velocity(
             P(u[0]), P(u[1]), P(u[2]), P(up[0]), P(up[1]), P(up[2]), P(pp), cd(ph["dt"]), cd(d),
             cd(d), cd(d), n, n, n))
@@ -488,6 +493,9 @@ def run_e2e(o3d, w, steps, warmup, chunks=0):
             "steps": steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "sor_iters_per_step": float(np.mean(iters)), "pipeline_chunks": chunks,
             "host_shift": hostshift,
+            "ms_per_call": {"predict_velocity": 1e3 * call_s[0] / steps,
+                            "correct_pression": 1e3 * call_s[1] / steps,
+                            "correct_velocity": 1e3 * call_s[2] / steps},
             "path": "o3d_predict_velocity + o3d_correct_pression + o3d_correct_velocity with "
                     "pinned HOST arrays (stateless drop-in procedures), wall clock"
                     + ("; predict / correct_velocity pipelined over %d z chunks (upload, kernel "

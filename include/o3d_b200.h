@@ -115,8 +115,9 @@ int o3d_get_pipeline(void);
  * src/integration.f90:112 -- are produced in the host arrays by memcpy / memset on worker
  * threads (O3D_HOSTSHIFT_THREADS, default min(8, cores - 2)), chunk by chunk behind the
  * transfers: 6 (DNS: 7) of the 13 arrays of the call no longer cross PCIe.  The arrays are bit
- * for bit those of on = 0.  Default: environment variable O3D_HOSTSHIFT, else see
- * csrc/pipeline.cu.  No effect on unpipelined calls. */
+ * for bit those of on = 0.  Default: environment variable O3D_HOSTSHIFT, else on when the host
+ * has at least 10 hardware threads (with fewer workers than 8 the memcpy trails the transfers it
+ * replaces: measured slower).  No effect on unpipelined calls. */
 int o3d_set_hostshift(int on);
 int o3d_get_hostshift(void);
 /* The schedule a pipelined call would use for nz planes under the current setting (host logic

@@ -51,8 +51,12 @@ namespace {
 int g_pipe_setting = -1;  // -1: take O3D_PIPELINE from the environment at first use
 // Host-side history shift of the pipelined o3d_predict_velocity (host_copier.h): -1 = take
 // O3D_HOSTSHIFT from the environment at first use.
+// Default: on where the worker pool reaches its 8 threads (>= 10 hardware threads).  Measured end
+// to end on the 256^3 TGV step (B200, PCIe Gen5, 16-core host, pinned arrays;
+// profiles/r2y_e2e_hostshift_ab.jsonl): 63.9 ms per step with everything downloaded, 59.2 - 60.0 ms
+// with 8 or 16 workers, 69.8 ms with 3 (the memcpy then trails the transfers it replaces).
 int g_hostshift = -1;
-constexpr int DEFAULT_HOSTSHIFT = 0;
+constexpr unsigned HOSTSHIFT_MIN_HW_THREADS = 10;
 // Default number of chunks.  Measured end to end on the 256^3 TGV step (B200, PCIe Gen5, pinned
 // arrays; profiles/r1p_e2e_pipeline.jsonl, r1q_e2e_pipeline.jsonl): 86.8 ms unpipelined, 71.3 /
 // 65.8 / 65.1 ms with 4 / 8 / 16 chunks; flat (63.4 - 63.9 ms on a second box) from 12 to 32.
@@ -314,7 +318,8 @@ int pipe_chunks(int nz) {
 int hostshift_setting() {
     if (g_hostshift < 0) {
         const char* e = getenv("O3D_HOSTSHIFT");
-        g_hostshift = e ? (atoi(e) != 0) : DEFAULT_HOSTSHIFT;
+        g_hostshift = e ? (atoi(e) != 0)
+                        : (std::thread::hardware_concurrency() >= HOSTSHIFT_MIN_HW_THREADS);
     }
     return g_hostshift;
 }
