@@ -471,12 +471,16 @@ def run_e2e(o3d, w, steps, warmup, chunks=0):
         o3d._lib.check(lib.o3d_correct_velocity(
             P(u[0]), P(u[1]), P(u[2]), P(up[0]), P(up[1]), P(up[2]), P(pp), cd(ph["dt"]), cd(d),
             cd(d), cd(d), n, n, n))
+        t.append(time.perf_counter())
+        for q in range(3):
+            call_s[q] += t[q + 1] - t[q]
         return it.value
 
     itime = 0
     for _ in range(warmup):
         itime += 1
         step(itime)
+    call_s[:] = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     iters = []
     for _ in range(steps):
