@@ -394,6 +394,10 @@ def run_reference(args):
             n = max(32, int((REF_BUDGET_S / (K + W) * REF_RATE_PTS_S) ** (1.0 / 3.0)))
             n = min(n, n_full)
     w = workload(args, 1)
+    ph = dict(w["phys"])
+    if n != n_full:    # the bounded sample keeps the CFL number: dt follows the grid (cpu_sample)
+        L = PI if args.bc == "freeslip" else 2 * PI
+        ph["dt"] = 0.05 * L / (n - 1) if not args.les else 5e-4 * 128.0 / (n - 1)
     times, iters = cpu_sample(args, W + K, n, opt=True)
     t = times[W:]
     ms = 1e3 * sum(t) / len(t)
@@ -408,7 +412,15 @@ def run_reference(args):
             "value": val, "unit": "Mpts*steps/s", "n_gpus": args.gpus, "steps": len(t),
             "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "grid": [n, n, n], "host": "cpu"},
+            # the keys of the b200 arm's `config`, with this arm's own values where they differ
+            "config": {"workload": w["name"], "grid": [n, n, n], "dt": ph["dt"], "re": ph["re"],
+                       "omega": ph["omega"], "eps": ph["eps"], "idyn": ph["idyn"],
+                       "iles": ph["iles"], "sor_order": "lexicographic (src/poisson.f90)",
+                       "sor_iters_per_step": float(np.mean(iters[W:])),
+                       "sor_path": {"persistent": False, "peer_memory": False},
+                       "parallelism": "serial cpu x1",
+                       "l2": "host arrays (18 fields x %.0f MB), no device" % (n ** 3 * 8 / 1e6),
+                       "host": "cpu"},
             "cpu_baseline": {"value": val, "unit": "Mpts*steps/s", "cores": 1, "kind": "port",
                              "sample": sample, "build": "gcc -O3 -ffp-contract=off",
                              "value_strict_O2_build": val_o2,
