@@ -722,9 +722,11 @@ int launch_sor_persist(cudaStream_t st, const SorArgs& a, const CUtensorMap* pma
     {
         // the last chunk of a shifted tile is `zstagger` planes shorter: keep it >= 2 planes
         // O3D_PERSIST_STAGGER=<planes>: measured 0 .. 16 planes without any effect on the DRAM
-        // traffic of the static map (profiles/r2_sor_scheduling.txt); off by default
+        // traffic of the static map (profiles/r2_sor_scheduling.txt).  Default: off on one GPU; 4
+        // planes on z slabs -- no measurable effect there either, but it is the setting every
+        // multi-GPU parity and scaling run of round 2 was recorded with (profiles/r2t_*, r2u_*)
         const char* e = getenv("O3D_PERSIST_STAGGER");
-        int sh = e ? atoi(e) : 0;
+        int sh = e ? atoi(e) : ((peer && peer->nranks > 1) ? 4 : 0);
         const int last = a.nz - (f.nch - 1) * f.zchunk;
         if (f.nch < 2) sh = 0;
         if (sh > last - 2) sh = last - 2 > 0 ? last - 2 : 0;
