@@ -16,7 +16,8 @@ star, each with its own value, Poisson iterations per step K and per-stage roofl
   N = 1 : 512^3 DNS (north-star target), 512^3 LES (configs[2]), periodic 256^3 (K ~ 18) and 257^3
           (odd extents: seam SOR), coplanar jet 257 x 513 x 129 (configs[4], K ~ 11), mixing layer 241 x 241 x
           81 LES + scalar with SOR (K ~ 84) and with multigrid (configs[3])
-  N > 1 : 512 x 512 x 511 planes per GPU DNS (N = 8: the 1024^3 class), periodic 256 x 256 x 256 N
+  N > 1 : 512 x 512 x 511 planes per GPU DNS (N = 8: the 1024^3 class), 512^3 LES cut into N z
+          slabs (configs[2]: the N = 1 leg strong-scaled), periodic 256 x 256 x 256 N
           (K ~ 18, wrap link rank 0 <-> N-1) and the coplanar jet replicated in z (odd x / y
           extents: seam classes across slabs)
 and a `parity` object: N = 1 -- a 64^3 side problem against the CPU oracle; N > 1 -- the N-rank
@@ -209,6 +210,24 @@ def make_workload(kind, nranks=1, n=256, bc="freeslip", les=False, strong=False,
                     multigrid=0, n=nx,
                     init=lambda z0, nzl: shear_fields("cojet", nx, ny, nzl, z0, d3, -5.5, 5.5))
     raise ValueError(kind)
+
+
+def leg_specs(world):
+    """the `configs` legs of the JSON line: (key, make_workload arguments)"""
+    if world == 1:
+        return [("tgv512_dns", dict(kind="tgv", n=512)),
+                ("tgv512_les", dict(kind="tgv", n=512, les=True)),
+                ("tgv256_periodic", dict(kind="tgv", n=256, bc="periodic")),
+                ("tgv257_periodic", dict(kind="tgv", n=257, bc="periodic")),
+                ("cojet", dict(kind="cojet")),
+                ("mixing_layer_sor", dict(kind="mixing_layer")),
+                ("mixing_layer_multigrid", dict(kind="mixing_layer", multigrid=1))]
+    return [("tgv512_dns", dict(kind="tgv", n=512)),
+            # BASELINE configs[2], "LES at 512^3, 1/2/4/8 GPUs": the SAME 512^3 grid as the N = 1
+            # leg `tgv512_les`, cut into z slabs (strong scaling; same workload name)
+            ("tgv512_les_strong", dict(kind="tgv", n=512, les=True, strong=True)),
+            ("tgv256_periodic", dict(kind="tgv", n=256, bc="periodic")),
+            ("cojet", dict(kind="cojet"))]
 
 
 def workload(args, nranks):
@@ -886,19 +905,7 @@ def main():
         line["e2e"] = e2e_slabs
 
     # ---- the other configurations (each a full leg of its own) ----
-    specs = []
-    if world == 1:
-        specs = [("tgv512_dns", dict(kind="tgv", n=512)),
-                 ("tgv512_les", dict(kind="tgv", n=512, les=True)),
-                 ("tgv256_periodic", dict(kind="tgv", n=256, bc="periodic")),
-                 ("tgv257_periodic", dict(kind="tgv", n=257, bc="periodic")),
-                 ("cojet", dict(kind="cojet")),
-                 ("mixing_layer_sor", dict(kind="mixing_layer")),
-                 ("mixing_layer_multigrid", dict(kind="mixing_layer", multigrid=1))]
-    else:
-        specs = [("tgv512_dns", dict(kind="tgv", n=512)),
-                 ("tgv256_periodic", dict(kind="tgv", n=256, bc="periodic")),
-                 ("cojet", dict(kind="cojet"))]
+    specs = leg_specs(world)
     if legs == "none":
         specs = []
     elif legs != "all":

@@ -126,3 +126,22 @@ def test_digest_is_a_bitwise_fingerprint():
     assert bench.digest(a) == bench.digest(b)
     b[2, 1, 1] = np.nextafter(b[2, 1, 1], 1.0)
     assert bench.digest(a) != bench.digest(b)
+
+
+def test_leg_specs_cover_the_baseline_configs():
+    """N = 1: every single-GPU configuration of BASELINE.json; N > 1: the weak-scaled legs plus the
+    512^3 LES grid of configs[2] cut into z slabs (same workload as the N = 1 leg)"""
+    sys.path.insert(0, ROOT)
+    import bench
+    one = dict(bench.leg_specs(1))
+    assert set(one) == {"tgv512_dns", "tgv512_les", "tgv256_periodic", "tgv257_periodic", "cojet",
+                        "mixing_layer_sor", "mixing_layer_multigrid"}
+    for world in (2, 4, 8):
+        many = dict(bench.leg_specs(world))
+        assert set(many) == {"tgv512_dns", "tgv512_les_strong", "tgv256_periodic", "cojet"}
+        les1 = bench.make_workload(nranks=1, **one["tgv512_les"])
+        lesn = bench.make_workload(nranks=world, **many["tgv512_les_strong"])
+        assert lesn["name"] == les1["name"] and lesn["grid"] == (512, 512, 512)
+        assert lesn["phys"] == les1["phys"] and lesn["phys"]["iles"] == 1
+        assert bench.make_workload(nranks=world, **many["tgv512_dns"])["grid"] == \
+            (512, 512, world * 511 + 1)
