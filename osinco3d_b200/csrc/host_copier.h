@@ -48,7 +48,14 @@ public:
     HostCopier(int nthreads, WaitFn wait, EnterFn enter = nullptr, int enter_arg = 0)
         : wait_(wait), enter_(enter), enter_arg_(enter_arg) {
         if (nthreads < 1) nthreads = 1;
-        for (int i = 0; i < nthreads; ++i) th_.emplace_back([this] { run(); });
+        th_.reserve(nthreads);
+        try {
+            for (int i = 0; i < nthreads; ++i) th_.emplace_back([this] { run(); });
+        } catch (...) {
+            // thread limit reached: work with the threads that did start; none at all -> throw
+            // (no joinable thread is left behind then)
+            if (th_.empty()) throw;
+        }
     }
     ~HostCopier() {
         {

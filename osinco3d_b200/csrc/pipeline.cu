@@ -161,8 +161,12 @@ int ensure_pipe(o3d_session* s, long long slot_elems, int nev, int nhev = 0) {
     if (nhev && !p->hc) {
         int dev = 0;
         O3D_CUDA_CHECK(cudaGetDevice(&dev));
-        p->hc = new (std::nothrow) HostCopier(hostshift_threads(), wait_event, enter_device, dev);
-        if (!p->hc) return O3D_ERR_INVALID;
+        // a host that cannot start the workers (thread limit) keeps the download path
+        try {
+            p->hc = new HostCopier(hostshift_threads(), wait_event, enter_device, dev);
+        } catch (...) {
+            p->hc = nullptr;
+        }
     }
     return O3D_OK;
 }
@@ -195,7 +199,8 @@ struct Run {
         int rc = ensure_pipe(s, plane * maxnk, 3 * C, hs ? 5 * C : 0);
         if (rc) return rc;
         p = s->pipe;
-        if (hs)
+        hostshift = hs && p->hc != nullptr;
+        if (hostshift)
             for (int i = 0; i < 3 * C; ++i) p->a_done[i].store(0, std::memory_order_relaxed);
         // the lanes start behind everything queued on the session stream so far (the lazy
         // zero fill of freshly allocated fields, the memsets of the caller)
@@ -386,10 +391,10 @@ int pipe_predict_velocity(o3d_session* s, int itime, double* const* up_h,
     // jobs on worker threads, ordered against the DMA transfers of the same chunk by events; the
     // result is bit for bit what the downloads would have delivered (memcpy and PCIe both move
     // bits).  DNS: nu_t = 0.d0 (src/integration.f90:112) is a host memset.
-    const bool hs = hostshift_setting() != 0;
     const int itscheme = s->cfg.itscheme;
     Run r;
-    if ((rc = r.init(s, C, hs))) return rc;
+    if ((rc = r.init(s, C, hostshift_setting() != 0))) return rc;
+    const bool hs = r.hostshift;
     auto body = [&]() -> int {
         int rc2;
         bool issued[MAX_CHUNKS] = {false};
