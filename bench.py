@@ -412,7 +412,12 @@ def run_reference(args):
         if (K + W) * per_step > REF_BUDGET_S:
             n = max(32, int((REF_BUDGET_S / (K + W) * REF_RATE_PTS_S) ** (1.0 / 3.0)))
             n = min(n, n_full)
+    # the arm is launched like the b200 arm: at N > 1 its workload is the N-rank grid (weak scaling:
+    # the n^3 box replicated N times in z; --strong: the n^3 box itself), and each step times a
+    # bounded sample of it -- ONE box (or a smaller one) -- since the metric is per grid point
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), int(args.gpus or 1))
     w = workload(args, 1)
+    w_full = workload(args, world)
     ph = dict(w["phys"])
     if n != n_full:    # the bounded sample keeps the CFL number: dt follows the grid (cpu_sample)
         L = PI if args.bc == "freeslip" else 2 * PI
@@ -423,16 +428,19 @@ def run_reference(args):
     val = (n ** 3) / 1e6 / (ms / 1e3)
     t2, _ = cpu_sample(args, 3, n, opt=False)
     val_o2 = (n ** 3) / 1e6 / (sum(t2[1:]) / len(t2[1:]))
-    sample = ("%d timed steps (after %d warm-up) of %s at %d^3%s, SOR iters/step %s"
+    sample = ("%d timed steps (after %d warm-up) of %s at %d^3%s%s, SOR iters/step %s"
               % (len(t), W, w["name"], n,
                  "" if n == n_full else " (bounded sample of the %d^3 workload)" % n_full,
+                 "" if w_full["name"] == w["name"] else
+                 " = one of the %d z replicas of the weak-scaled grid %s" % (world, w_full["name"]),
                  iters[W:]))
     line = {"impl": "reference", "metric": "Mpts*steps/s (full AB3+SOR time step)",
             "value": val, "unit": "Mpts*steps/s", "n_gpus": args.gpus, "steps": len(t),
             "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             # the keys of the b200 arm's `config`, with this arm's own values where they differ
-            "config": {"workload": w["name"], "grid": [n, n, n], "dt": ph["dt"], "re": ph["re"],
+            "config": {"workload": w_full["name"], "grid": [n, n, n],
+                       "workload_grid": list(w_full["grid"]), "dt": ph["dt"], "re": ph["re"],
                        "omega": ph["omega"], "eps": ph["eps"], "idyn": ph["idyn"],
                        "iles": ph["iles"], "sor_order": "lexicographic (src/poisson.f90)",
                        "sor_iters_per_step": float(np.mean(iters[W:])),

@@ -145,3 +145,17 @@ def test_leg_specs_cover_the_baseline_configs():
         assert lesn["phys"] == les1["phys"] and lesn["phys"]["iles"] == 1
         assert bench.make_workload(nranks=world, **many["tgv512_dns"])["grid"] == \
             (512, 512, world * 511 + 1)
+
+
+def test_reference_arm_names_the_n_rank_workload():
+    """launched like the b200 arm at N > 1, rank 0 reports the arm's workload (the box replicated
+    N times in z) and says that each step timed one replica of it"""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="4", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--gpus", "4", "--n", "24", "--steps", "1", "--warmup", "0"], env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip())
+    assert d["n_gpus"] == 4 and d["config"]["workload"] == "tgv_re1600_dns_freeslip_24x24x93_ab3_sor"
+    assert d["config"]["workload_grid"] == [24, 24, 93] and d["config"]["grid"] == [24, 24, 24]
+    assert "one of the 4 z replicas" in d["cpu_baseline"]["sample"]
