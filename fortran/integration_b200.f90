@@ -81,7 +81,9 @@ contains
   subroutine predict_velocity(ux_pred, uy_pred, uz_pred, ux, uy, uz, &
        fux, fuy, fuz, re, adt, bdt, cdt, itime, itscheme, &
        dx, dy, dz, nx, ny, nz, iles, cs, delta, nu_t)
-    real(kind=8), intent(in) :: ux(:,:,:), uy(:,:,:), uz(:,:,:)
+    ! (intents as in the reference, src/integration.f90:53-61: ux, uy, uz are intent(inout)
+    ! there although predict_velocity never assigns them)
+    real(kind=8), intent(inout) :: ux(:,:,:), uy(:,:,:), uz(:,:,:)
     real(kind=8), intent(inout) :: fux(:,:,:,:), fuy(:,:,:,:), fuz(:,:,:,:)
     real(kind=8), intent(in) :: re, adt(3), bdt(3), cdt(3)
     real(kind=8), intent(in) :: dx, dy, dz, cs, delta
@@ -141,7 +143,9 @@ contains
     real(kind=8), intent(in) :: ux_pred(:,:,:), uy_pred(:,:,:), uz_pred(:,:,:), pp(:,:,:)
     real(kind=8), intent(in) :: dt, dx, dy, dz
     integer, intent(in) :: nx, ny, nz
-    real(kind=8), intent(out) :: ux(:,:,:), uy(:,:,:), uz(:,:,:)
+    ! intent(inout) as in the reference (src/integration.f90:287); with o3d_mirror = 0 the host
+    ! copies are deliberately left as they are
+    real(kind=8), intent(inout) :: ux(:,:,:), uy(:,:,:), uz(:,:,:)
     integer(c_int) :: rc
     print *, "* Correct velocity"
     if (.not. o3d_resident) then

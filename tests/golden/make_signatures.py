@@ -16,12 +16,41 @@ MODULES = {"derivation": "derivation.f90", "diffoper": "differential_operators.f
            "poisson_multigrid": "poisson_multigrid.f90", "integration": "integration.f90"}
 
 
+def typed_signatures(path):
+    """{module: {procedure: [[dummy, typespec, kind, intent, rank], ...]}} of the module procedures
+    of a Fortran file, from numpy.f2py's crackfortran (a second, independent parser: f90np reads
+    names only).  kind is the text of the kind selector ('8', 'dp', 'c_double', None = default)."""
+    import contextlib
+    import io
+    from numpy.f2py import crackfortran
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        crackfortran.verbose = 0
+        tree = crackfortran.crackfortran([path])
+    out = {}
+    for m in tree:
+        if m["block"] != "module":
+            continue
+        for p in m["body"]:
+            if p["block"] not in ("subroutine", "function"):
+                continue
+            sig = []
+            for a in p["args"]:
+                v = p["vars"][a]
+                ks = v.get("kindselector") or {}
+                kind = ks.get("kind") or ks.get("*")
+                sig.append([a, v.get("typespec"), str(kind) if kind else None,
+                            (v.get("intent") or [None])[0], len(v.get("dimension") or [])])
+            out.setdefault(m["name"], {})[p["name"]] = sig
+    return out
+
+
 def main():
     out = {}
     for mod, fn in MODULES.items():
         rs = f90np.routines(open(os.path.join(REF, fn)).read())
         out[mod] = {"file": "src/" + fn,
-                    "procedures": {r.name: r.dummies for r in rs.values()}}
+                    "procedures": {r.name: r.dummies for r in rs.values()},
+                    "typed": typed_signatures(os.path.join(REF, fn))[mod]}
     with open(os.path.join(HERE, "reference_signatures.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print({m: len(v["procedures"]) for m, v in out.items()})

@@ -2,8 +2,13 @@
 image): (1) the replacement modules in fortran/ define every hot-path procedure of the reference
 modules they replace, under the reference's module and procedure names and with the reference's
 dummy-argument lists (tests/golden/reference_signatures.json, extracted from the reference source
-by tests/golden/make_signatures.py); (2) every bind(C) interface block of fortran/o3d_b200_c.f90
-names a function that include/o3d_b200.h declares, with the same number of arguments."""
+by tests/golden/make_signatures.py), each dummy with the reference's type, kind, intent and
+rank; (2) every bind(C) interface block of fortran/o3d_b200_c.f90 names a function that
+include/o3d_b200.h declares, with the same number of arguments, and -- argument by argument -- what
+a Fortran compiler would pass (by value / by reference, c_int / c_long_long / c_double / c_ptr,
+intent(in) <-> const) is the C parameter type; (3) every call of a bind(C) function in the shim
+bodies passes the declared number of arguments.  (2) and (3) use numpy.f2py's crackfortran as a
+second, independent Fortran parser."""
 import json
 import os
 import re
@@ -85,3 +90,186 @@ def test_config_type_mirrors_the_c_struct():
             for ent in f90np.split_top(line.split("::", 1)[1]):
                 names.append(re.match(r"\s*(\w+)", ent).group(1))
     assert names == [f[0] for f in _lib.Config._fields_]
+
+
+# ---------------------------------------------------------------------------------------------
+# Typed check of the bind(C) interfaces with an independent Fortran parser (numpy.f2py's
+# crackfortran): argument by argument, the C type a Fortran compiler would pass must be the
+# parameter type of the prototype in include/o3d_b200.h.  A by-reference integer where C takes it
+# by value, a c_int where C takes a long long, or an intent(out) array behind a `const double*`
+# compiles and links silently -- this is the check a compiler + linker would NOT make.
+# ---------------------------------------------------------------------------------------------
+def c_typed_prototypes():
+    txt = open(os.path.join(ROOT, "include", "o3d_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+    ders = re.findall(r"O3D_DECL_DER\((\w+)\)", txt)
+    der_ret, der_args = re.search(r"#define\s+O3D_DECL_DER\(name\)\s*\\\s*\n\s*(\w+)\s+"
+                                  r"o3d_##name\(([^)]*)\)", txt).groups()
+    txt = re.sub(r"^[ \t]*#(?:[^\n]*\\\n)*[^\n]*$", "", txt, flags=re.M)   # preprocessor lines
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(o3d_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt,
+                         flags=re.S):
+        protos[m.group(2)] = (m.group(1).strip(), m.group(3).strip())
+    for nm in ders:
+        if nm != "name":
+            protos["o3d_" + nm] = (der_ret, der_args)
+    return protos
+
+
+def c_param_class(p):
+    """'const double* adt' -> ('double', 1, True): base type, pointer depth, const-qualified"""
+    const = bool(re.search(r"\bconst\b", p))
+    q = re.sub(r"\bconst\b", "", p)
+    depth = q.count("*") + (1 if "[" in q else 0)
+    q = re.sub(r"\[[^\]]*\]", "", q.replace("*", " "))
+    toks = [t for t in q.split() if t != "struct"]
+    types = {"int", "double", "char", "void", "long", "unsigned", "size_t", "o3d_session",
+             "o3d_config"}
+    if len(toks) >= 2 and toks[-1] not in types:
+        toks = toks[:-1]                      # the parameter name
+    base = " ".join(toks)
+    if base in ("long long", "unsigned long long", "size_t", "long long int"):
+        base = "i64"
+    return base, depth, const
+
+
+def fortran_arg_class(v):
+    """crackfortran variable -> (base, depth, read_only): what a bind(C) call passes for it"""
+    by_value = "value" in v.get("attrspec", [])
+    ts = v["typespec"]
+    if ts == "integer":
+        base = {"c_int": "int", "c_long_long": "i64", "c_size_t": "i64"}[v["kindselector"]["kind"]]
+    elif ts == "real":
+        assert v["kindselector"]["kind"] == "c_double"
+        base = "double"
+    elif ts == "character":
+        assert v["charselector"]["kind"] == "c_char"
+        base = "char"
+    elif ts == "type":
+        base = {"c_ptr": "ptr", "o3d_config": "o3d_config"}[v["typename"]]
+    else:
+        raise AssertionError("unexpected type %s" % ts)
+    read_only = by_value or v.get("intent") == ["in"]
+    if base == "ptr":                          # type(c_ptr): a C pointer, by value or by reference
+        return "ptr", (1 if by_value else 2), read_only
+    return base, (0 if by_value else 1), read_only
+
+
+def test_bind_c_argument_types_match_the_c_prototypes():
+    f2py = __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        f2py.verbose = 0
+        tree = f2py.crackfortran([os.path.join(ROOT, "fortran", "o3d_b200_c.f90")])
+    mod = [b for b in tree if b["block"] == "module" and b["name"] == "o3d_b200_c"][0]
+    funcs = [f for b in mod["body"] if b["block"] == "interface" for f in b["body"]]
+    assert len(funcs) > 40
+    protos = c_typed_prototypes()
+    checked = 0
+    for f in funcs:
+        name = f["name"]
+        assert name in protos, "%s is not declared in include/o3d_b200.h" % name
+        ret, args = protos[name]
+        cparams = [] if args in ("", "void") else [c_param_class(a) for a in args.split(",")]
+        assert len(cparams) == len(f["args"]), (name, f["args"], args)
+        # result: integer(c_int) <-> int; type(c_ptr) <-> any pointer
+        rv = f["vars"][f.get("result") or name]
+        rbase, rdepth, _ = c_param_class(ret + " r")
+        if rv["typespec"] == "type":
+            assert rv["typename"] == "c_ptr" and rdepth >= 1, (name, ret)
+        else:
+            assert rv["typespec"] == "integer" and rv["kindselector"]["kind"] == "c_int" and \
+                (rbase, rdepth) == ("int", 0), (name, ret)
+        for a, (cb, cd, cconst) in zip(f["args"], cparams):
+            fb, fd, ro = fortran_arg_class(f["vars"][a])
+            where = "%s(%s)" % (name, a)
+            if fb == "ptr":
+                # opaque handle / raw address: any C pointer of that depth (void*, o3d_session*,
+                # double* ...; o3d_session** / void** by reference)
+                assert cd == fd, (where, "pointer depth", cd, fd)
+            else:
+                assert (cb, cd) == (fb, fd), (where, "C has", (cb, cd), "Fortran passes", (fb, fd))
+            if cd >= 1 and fb != "ptr":
+                # const-correctness: what Fortran declares intent(in) is const in C and vice versa
+                assert cconst == ro, (where, "const in C:", cconst, "intent(in) in Fortran:", ro)
+            checked += 1
+    assert checked > 250
+
+
+def test_shim_call_sites_pass_the_declared_number_of_arguments():
+    """every reference to a bind(C) function in the shim bodies (rc = o3d_xxx(...), call
+    o3d_check(o3d_xxx(...))) has as many actual arguments as its interface declares -- the arity
+    error a Fortran compiler would stop on"""
+    f2py = __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        f2py.verbose = 0
+        tree = f2py.crackfortran([os.path.join(ROOT, "fortran", "o3d_b200_c.f90")])
+    mod = [b for b in tree if b["block"] == "module" and b["name"] == "o3d_b200_c"][0]
+    arity = {f["name"]: len(f["args"]) for b in mod["body"] if b["block"] == "interface"
+             for f in b["body"]}
+    calls = 0
+    for fn in sorted(os.listdir(os.path.join(ROOT, "fortran"))):
+        if not fn.endswith(".f90"):
+            continue
+        text = "\n".join(f90np.logical_lines(shim_text(fn)))
+        if fn == "o3d_b200_c.f90":          # skip the interface block itself
+            text = re.sub(r"(?is)^\s*interface\b.*?^\s*end interface", "", text, flags=re.M)
+        for m in re.finditer(r"\b(o3d_[a-z0-9_]+)\s*\(", text, flags=re.I):
+            name = m.group(1).lower()
+            if name not in arity:
+                continue
+            line_start = text.rfind("\n", 0, m.start()) + 1
+            if re.match(r"\s*(end\s+)?function\b", text[line_start:m.start() + 1], re.I):
+                continue
+            depth, i, n, any_arg = 1, m.end(), 0, False
+            while depth and i < len(text):
+                c = text[i]
+                if c in "([":
+                    depth += 1
+                elif c in ")]":
+                    depth -= 1
+                elif c == "," and depth == 1:
+                    n += 1
+                elif not c.isspace():
+                    any_arg = True
+                i += 1
+            nargs = n + 1 if any_arg else 0
+            assert nargs == arity[name], (fn, name, nargs, arity[name])
+            calls += 1
+    assert calls > 40
+
+
+def test_shim_dummy_arguments_have_the_reference_types_intents_and_ranks():
+    """drop-in at the level a Fortran compiler checks an explicit interface: for every replaced
+    module procedure, each dummy of the shim has the reference's type, kind, intent and rank
+    (tests/golden/reference_signatures.json "typed", extracted from /root/reference/src by
+    make_signatures.py with numpy.f2py's crackfortran; the shims are parsed the same way here)"""
+    __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    from make_signatures import typed_signatures
+
+    def norm(sig):
+        name, ts, kind, intent, rank = sig
+        kind = {"8": "double", "dp": "double", "c_double": "double", "c_int": "int",
+                None: "default"}.get(kind, kind)
+        return (name, ts, kind, intent, rank)
+
+    checked = 0
+    for mod, ref in SIG.items():
+        shim = typed_signatures(os.path.join(ROOT, "fortran", SHIM_OF[mod]))[mod]
+        for proc, sig in ref["typed"].items():
+            if proc in NOT_REPLACED.get(mod, ()):
+                continue
+            assert proc in shim, (mod, proc)
+            got = [norm(s) for s in shim[proc]]
+            want = [norm(s) for s in sig]
+            if mod == "derivation":
+                # der_type(df, f, d): the spacing dummy is named dx / dy / dz in the reference
+                got = [g[1:] if i == 2 else g for i, g in enumerate(got)]
+                want = [w[1:] if i == 2 else w for i, w in enumerate(want)]
+            assert got == want, (mod, proc, got, want)
+            checked += len(want)
+    assert checked > 150
