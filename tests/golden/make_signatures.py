@@ -51,9 +51,16 @@ def main():
         out[mod] = {"file": "src/" + fn,
                     "procedures": {r.name: r.dummies for r in rs.values()},
                     "typed": typed_signatures(os.path.join(REF, fn))[mod]}
+    # fortran/output_b200.f90 replaces two procedures that live in two other reference modules
+    # (keys starting with "_" are not module -> shim entries)
+    io = typed_signatures(os.path.join(REF, "IOfunctions.f90"))["iofunctions"]
+    vis = typed_signatures(os.path.join(REF, "visualization.f90"))["visualization"]
+    out["_output_b200"] = {"file": "src/IOfunctions.f90, src/visualization.f90",
+                           "typed": {"save_fields": io["save_fields"],
+                                     "write_all_data": vis["write_all_data"]}}
     with open(os.path.join(HERE, "reference_signatures.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
-    print({m: len(v["procedures"]) for m, v in out.items()})
+    print({m: len(v.get("procedures", v["typed"])) for m, v in out.items()})
 
 
 if __name__ == "__main__":

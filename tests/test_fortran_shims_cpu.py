@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import f90np  # noqa: E402
 
-SIG = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_signatures.json")))
+_ALL = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_signatures.json")))
+SIG = {k: v for k, v in _ALL.items() if not k.startswith("_")}
 SHIM_OF = {"derivation": "derivation_b200.f90", "diffoper": "differential_operators_b200.f90",
            "les_turbulence": "les_turbulence_b200.f90", "poisson": "poisson_b200.f90",
            "poisson_multigrid": "poisson_multigrid_b200.f90", "integration": "integration_b200.f90"}
@@ -272,4 +273,9 @@ def test_shim_dummy_arguments_have_the_reference_types_intents_and_ranks():
                 want = [w[1:] if i == 2 else w for i, w in enumerate(want)]
             assert got == want, (mod, proc, got, want)
             checked += len(want)
-    assert checked > 150
+    # save_fields (src/IOfunctions.f90) and write_all_data (src/visualization.f90) -> output_b200
+    shim = typed_signatures(os.path.join(ROOT, "fortran", "output_b200.f90"))["output_b200"]
+    for proc, sig in _ALL["_output_b200"]["typed"].items():
+        assert [norm(s) for s in shim[proc]] == [norm(s) for s in sig], proc
+        checked += len(sig)
+    assert checked > 170
