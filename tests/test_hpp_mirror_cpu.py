@@ -41,6 +41,8 @@ def test_cpp_mirror_covers_the_reference_procedures():
     skip = {"calculate_tau_ij", "calculate_dtau_ij_dxj", "v_cycle", "gauss_seidel", "compute_residual",
             "restrict_full_weighting", "prolongation_add", "dery1d"}
     for mod, ref in sig.items():
+        if mod.startswith("_"):     # not a module -> namespace entry (output_b200 procedures)
+            continue
         m = re.search(r"namespace %s \{(.*?)\}  // namespace %s" % (mod, mod), txt, re.S)
         assert m, mod
         body = m.group(1).lower()
