@@ -14,6 +14,7 @@ contains
     real(kind=8), intent(in) :: fx(nx,ny,nz), fy(nx,ny,nz), fz(nx,ny,nz)
     real(kind=8), intent(in) :: dx, dy, dz
     real(kind=8), intent(out) :: divf(nx,ny,nz)
+    call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
     call o3d_check(o3d_divergence(divf, fx, fy, fz, dx, dy, dz, nx, ny, nz, odd), "divergence")
   end subroutine divergence
 
@@ -22,6 +23,7 @@ contains
     real(kind=8), intent(in) :: ux(nx,ny,nz), uy(nx,ny,nz), uz(nx,ny,nz)
     real(kind=8), intent(in) :: dx, dy, dz
     real(kind=8), intent(out) :: rotx(nx,ny,nz), roty(nx,ny,nz), rotz(nx,ny,nz)
+    call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
     call o3d_check(o3d_rotational(rotx, roty, rotz, ux, uy, uz, dx, dy, dz, nx, ny, nz), &
          "rotational")
   end subroutine rotational
@@ -31,6 +33,7 @@ contains
     real(kind=8), intent(in) :: ux(nx,ny,nz), uy(nx,ny,nz), uz(nx,ny,nz)
     real(kind=8), intent(in) :: dx, dy, dz
     real(kind=8), intent(out) :: Q(nx,ny,nz)
+    call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
     call o3d_check(o3d_calculate_q_criterion(Q, ux, uy, uz, dx, dy, dz, nx, ny, nz), &
          "calculate_Q_criterion")
   end subroutine calculate_Q_criterion

@@ -92,6 +92,7 @@ contains
     real(kind=8), intent(inout) :: nu_t(:,:,:)
     print *, "* Predict velocity"
     if (.not. o3d_resident) then
+       call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
        call o3d_check(o3d_predict_velocity(ux_pred, uy_pred, uz_pred, ux, uy, uz, fux, fuy, fuz, &
             re, adt, bdt, cdt, itime, itscheme, dx, dy, dz, nx, ny, nz, iles, cs, delta, nu_t), &
             "predict_velocity")
@@ -121,6 +122,7 @@ contains
     real(c_double) :: dmax
     print *, "* Correction pression"
     if (.not. o3d_resident) then
+       call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
        call o3d_check(o3d_correct_pression(pp, ux_pred, uy_pred, uz_pred, dx, dy, dz, nx, ny, nz, &
             dt, omega, eps, kmax, idyn, multigrid, iters, dmax), "correct_pression")
        return
@@ -149,6 +151,7 @@ contains
     integer(c_int) :: rc
     print *, "* Correct velocity"
     if (.not. o3d_resident) then
+       call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
        rc = o3d_correct_velocity(ux, uy, uz, ux_pred, uy_pred, uz_pred, pp, dt, dx, dy, dz, &
             nx, ny, nz)
     else
@@ -176,6 +179,7 @@ contains
     integer, intent(in) :: itime, itscheme, nx, ny, nz, iles
     logical, save :: phi_up = .false.
     if (.not. o3d_resident) then
+       call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
        call o3d_check(o3d_transeq(phi, ux, uy, uz, src, fphi, re, sc, adt, bdt, cdt, itime, &
             itscheme, dx, dy, dz, nx, ny, nz, iles, nu_t), "transeq")
        return

@@ -15,6 +15,7 @@ contains
     real(kind=8), intent(in) :: ux(:,:,:), uy(:,:,:), uz(:,:,:)
     real(kind=8), intent(in) :: dx, dy, dz, cs, delta
     real(c_double) :: st(6)
+    call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
     call o3d_check(o3d_calculate_nu_t(nu_t, ux, uy, uz, dx, dy, dz, cs, delta, &
          int(size(ux,1),c_int), int(size(ux,2),c_int), int(size(ux,3),c_int), st), &
          "calculate_nu_t")

@@ -473,4 +473,14 @@ contains
     stop
   end subroutine o3d_check
 
+  !> C mirror of schemes() (src/initialization.f90:226-304): binds the closures of the composite
+  !> operators and the Poisson variant on the C side to the boundary flags of module
+  !> `initialization`.  The stateless shims call it before every composite operator (a few host
+  !> instructions), so the unchanged driver needs no extra line after its own `call schemes()`.
+  subroutine o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
+    integer, intent(in) :: nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d
+    call o3d_check(o3d_schemes(int(nbcx1, c_int), int(nbcxn, c_int), int(nbcy1, c_int), &
+         int(nbcyn, c_int), int(nbcz1, c_int), int(nbczn, c_int), int(sim2d, c_int)), "schemes")
+  end subroutine o3d_bind_schemes
+
 end module o3d_b200_c

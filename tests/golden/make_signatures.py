@@ -44,6 +44,25 @@ def typed_signatures(path):
     return out
 
 
+def module_exports(path):
+    """{module: {"vars": [...], "procedures": [...]}} (lower case) of a Fortran file"""
+    import contextlib
+    import io
+    from numpy.f2py import crackfortran
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        crackfortran.verbose = 0
+        tree = crackfortran.crackfortran([path])
+    out = {}
+    for m in tree:
+        if m["block"] != "module":
+            continue
+        procs = sorted(p["name"].lower() for p in m["body"] if p["block"] in ("subroutine", "function"))
+        # procedure-pointer / abstract-interface names are module entities too
+        names = sorted(set(v.lower() for v in m.get("vars", {})) - set(procs))
+        out[m["name"].lower()] = {"vars": names, "procedures": procs}
+    return out
+
+
 def main():
     out = {}
     for mod, fn in MODULES.items():
@@ -58,9 +77,15 @@ def main():
     out["_output_b200"] = {"file": "src/IOfunctions.f90, src/visualization.f90",
                            "typed": {"save_fields": io["save_fields"],
                                      "write_all_data": vis["write_all_data"]}}
+    # what the shims import from the reference modules they keep using (`use initialization`,
+    # `use IOfunctions`): the names those modules export
+    out["_exports"] = {}
+    for fn in ("initialization.f90", "IOfunctions.f90"):
+        for mod, ex in module_exports(os.path.join(REF, fn)).items():
+            out["_exports"][mod] = dict(ex, file="src/" + fn)
     with open(os.path.join(HERE, "reference_signatures.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
-    print({m: len(v.get("procedures", v["typed"])) for m, v in out.items()})
+    print({m: len(v.get("procedures", v.get("typed", v))) for m, v in out.items()})
 
 
 if __name__ == "__main__":

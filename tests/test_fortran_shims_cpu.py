@@ -279,3 +279,52 @@ def test_shim_dummy_arguments_have_the_reference_types_intents_and_ranks():
         assert [norm(s) for s in shim[proc]] == [norm(s) for s in sig], proc
         checked += len(sig)
     assert checked > 170
+
+
+def test_shims_only_use_names_the_reference_modules_export():
+    """the shims keep using two unchanged reference modules (`use initialization`, `use
+    IOfunctions`): every name imported with `only:` exists there, and every `call` in a shim body
+    resolves to a procedure of the shim itself, of o3d_b200_c, or of a used reference module
+    (tests/golden/reference_signatures.json "_exports", from /root/reference/src)"""
+    f2py = __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    import contextlib
+    import io
+    exports = _ALL["_exports"]
+    parsed = {}
+    for fn in sorted(os.listdir(os.path.join(ROOT, "fortran"))):
+        if fn.endswith(".f90"):
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                f2py.verbose = 0
+                tree = f2py.crackfortran([os.path.join(ROOT, "fortran", fn)])
+            parsed[fn] = [b for b in tree if b["block"] == "module"][0]
+    shim_procs = {}
+    for fn, mod in parsed.items():
+        names = set()
+        for b in mod["body"]:
+            if b["block"] in ("subroutine", "function"):
+                names.add(b["name"].lower())
+            elif b["block"] == "interface":
+                names |= {f["name"].lower() for f in b["body"]}
+        shim_procs[mod["name"].lower()] = names
+    n_only = n_calls = 0
+    for fn, mod in parsed.items():
+        uses = {k.lower(): v for k, v in (mod.get("use") or {}).items()}
+        for used, spec in uses.items():
+            if used in exports and spec.get("only"):
+                known = set(exports[used]["vars"]) | set(exports[used]["procedures"])
+                for local, remote in spec["map"].items():
+                    assert remote.lower() in known, (fn, used, remote)
+                    n_only += 1
+        visible = set(shim_procs[mod["name"].lower()])
+        for used in uses:
+            if used in exports:
+                visible |= set(exports[used]["procedures"])
+            visible |= shim_procs.get(used, set())
+        text = "\n".join(f90np.logical_lines(shim_text(fn)))
+        for m in re.finditer(r"(?im)(?:^|[\s)])call\s+(\w+)", text):
+            name = m.group(1).lower()
+            if name in ("c_f_pointer",):          # iso_c_binding intrinsic
+                continue
+            assert name in visible, (fn, "call", name)
+            n_calls += 1
+    assert n_only >= 9 and n_calls > 60
