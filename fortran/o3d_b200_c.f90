@@ -385,6 +385,16 @@ module o3d_b200_c
        real(c_double), value :: omega
        integer(c_int) :: rc
      end function o3d_set_omega
+     !> the Poisson controls are per-call arguments of correct_pression in the reference
+     !> (src/integration.f90:199-200); the resident shim pushes them into the session with this
+     function o3d_session_set_poisson(ses, eps, kmax, idyn, multigrid) &
+          bind(C, name="o3d_session_set_poisson") result(rc)
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ses
+       real(c_double), value :: eps
+       integer(c_int), value :: kmax, idyn, multigrid
+       integer(c_int) :: rc
+     end function o3d_session_set_poisson
      function o3d_s_step_diagnostics(ses, out23) bind(C, name="o3d_s_step_diagnostics") result(rc)
        import :: c_int, c_ptr, c_double
        type(c_ptr), value :: ses

@@ -328,3 +328,84 @@ def test_shims_only_use_names_the_reference_modules_export():
             assert name in visible, (fn, "call", name)
             n_calls += 1
     assert n_only >= 9 and n_calls > 60
+
+
+_F_KEYWORDS = set("""if then else elseif endif end do enddo while call return stop print subroutine
+function module contains use only implicit none integer real logical character type kind len intent
+in out inout value save parameter dimension pointer target allocatable allocate deallocate result
+bind c name interface import select case default exit cycle not and or eq ne lt gt le ge true false
+procedure public private optional write read open close unit file status form access iostat
+fmt""".split())
+_F_INTRINSICS = set("""size int real dble abs max min maxval minval trim adjustl len_trim c_loc
+c_associated c_f_pointer c_null_char c_null_ptr c_ptr c_int c_double c_long_long c_char c_sizeof
+present shape reshape sum sqrt mod merge any all huge tiny epsilon associated null""".split())
+
+
+def test_shim_bodies_reference_only_declared_names():
+    """`implicit none` without a compiler: every identifier in the executable part of every shim
+    procedure is a dummy, a local, an entity of the enclosing module, imported from a used module
+    (the other shims, o3d_b200_c, or the reference's `initialization` / `IOfunctions` exports), a
+    keyword or an intrinsic.  (Found: a bind(C) function called without an interface.)"""
+    f2py = __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    import contextlib
+    import io
+    exports = _ALL["_exports"]
+    mods = {}
+    for fn in sorted(os.listdir(os.path.join(ROOT, "fortran"))):
+        if fn.endswith(".f90"):
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                f2py.verbose = 0
+                tree = f2py.crackfortran([os.path.join(ROOT, "fortran", fn)])
+            mods[fn] = [b for b in tree if b["block"] == "module"][0]
+
+    def module_names(m):
+        names = set(v.lower() for v in m.get("vars", {}))
+        for b in m["body"]:
+            if b["block"] in ("subroutine", "function"):
+                names.add(b["name"].lower())
+            elif b["block"] == "interface":
+                names |= {f["name"].lower() for f in b["body"]}
+            elif b["block"] == "type":
+                names.add(b["name"].lower())
+        return names
+
+    by_module = {m["name"].lower(): module_names(m) for m in mods.values()}
+
+    def code(line):
+        line = re.sub(r'"[^"]*"', '""', line)
+        line = re.sub(r"'[^']*'", "''", line)
+        return line.split("!")[0].lower()
+
+    checked = 0
+    for fn, m in mods.items():
+        visible = set(by_module[m["name"].lower()])
+        for used, spec in (m.get("use") or {}).items():
+            u = used.lower()
+            if spec.get("only"):
+                visible |= set(k.lower() for k in spec["map"])
+            elif u in exports:
+                visible |= set(exports[u]["vars"]) | set(exports[u]["procedures"])
+            elif u in by_module:
+                visible |= by_module[u]
+        routines = f90np.routines(shim_text(fn))
+        for b in m["body"]:
+            if b["block"] not in ("subroutine", "function"):
+                continue
+            body = routines[b["name"].lower()].body
+            local = set(v.lower() for v in b.get("vars", {})) | {b["name"].lower()}
+            for line in body:
+                ln = code(line)
+                if "::" in ln and re.match(r"\s*(integer|real|logical|character|type)\b", ln):
+                    for ent in f90np.split_top(ln.split("::", 1)[1]):
+                        local.add(re.match(r"\s*(\w+)", ent).group(1))
+            unknown = set()
+            for line in body:
+                ln = re.sub(r"%\s*\w+", "", code(line))                    # type components
+                ln = re.sub(r"\b\d+(\.\d*)?([de][+-]?\d+)?(_\w+)?", "", ln)  # numeric literals
+                for tok in re.findall(r"[a-z_]\w*", ln):
+                    if not (tok in _F_KEYWORDS or tok in _F_INTRINSICS or tok in local or
+                            tok in visible):
+                        unknown.add(tok)
+            assert not unknown, (fn, b["name"], sorted(unknown))
+            checked += 1
+    assert checked >= 40
