@@ -409,3 +409,129 @@ def test_shim_bodies_reference_only_declared_names():
             assert not unknown, (fn, b["name"], sorted(unknown))
             checked += 1
     assert checked >= 40
+
+
+# ---------------------------------------------------------------------------------------------
+# A small type checker for the calls the shims make into the bind(C) interfaces: the class
+# (integer / real / character / type(c_ptr) / type(o3d_config)) and the scalar-vs-array shape of
+# every actual argument that can be typed from its text (identifiers, array sections, int(...),
+# literals, scalar arithmetic on named constants) against the dummy it is passed to -- what a
+# compiler checks through the explicit interface, and what catches two swapped arguments.
+# ---------------------------------------------------------------------------------------------
+def _vclass(v):
+    """crackfortran variable -> (type class, is_array)"""
+    ts = v.get("typespec")
+    if ts == "type":
+        ts = "type(%s)" % v["typename"].lower()
+    return ts, bool(v.get("dimension"))
+
+
+def _decl_types(lines):
+    """local declarations `type-spec [, attrs] :: a, b(3)` -> {name: (class, is_array)}"""
+    out = {}
+    for line in lines:
+        m = re.match(r"\s*(integer|real|logical|character|type\s*\(\s*(\w+)\s*\))\b(.*?)::(.*)$",
+                     line.split("!")[0], re.I)
+        if not m:
+            continue
+        ts = m.group(1).lower()
+        if ts.startswith("type"):
+            ts = "type(%s)" % m.group(2).lower()
+        dim = "dimension" in m.group(3).lower()
+        for ent in f90np.split_top(m.group(4)):
+            mm = re.match(r"\s*(\w+)\s*(\()?", ent)
+            out[mm.group(1).lower()] = (ts, dim or bool(mm.group(2)))
+    return out
+
+
+def _actual_class(e, names):
+    """(class, is_array) of an actual-argument expression, or None when not decidable here"""
+    el = e.strip().lower()
+    if re.fullmatch(r"[a-z_]\w*", el):
+        return names.get(el)
+    if re.match(r"^(int|size|len_trim|nint)\s*\(", el):
+        return ("integer", False)
+    if re.match(r"^(real|dble)\s*\(", el):
+        return ("real", False)
+    if re.match(r"^c_loc\s*\(", el) or el == "c_null_ptr":
+        return ("type(c_ptr)", False)
+    if re.fullmatch(r"[+-]?\d+(_\w+)?", el):
+        return ("integer", False)
+    if re.fullmatch(r"[+-]?\d+\.\d*([de][+-]?\d+)?(_\w+)?|[+-]?\d+[de][+-]?\d+", el):
+        return ("real", False)
+    if el.startswith('"') or el.startswith("'") or "//" in el:
+        return ("character", False)
+    m = re.match(r"^([a-z_]\w*)\s*\((.*)\)$", el)
+    if m and m.group(1) in names:                 # array element / section
+        cls, arr = names[m.group(1)]
+        if arr:
+            return (cls, ":" in m.group(2))
+    if m and m.group(1) in names.get("__funcs__", {}):
+        return names["__funcs__"][m.group(1)]
+    m = re.match(r"^([a-z_]\w*)\s*([+\-*/])", el)
+    if m and m.group(1) in names and not names[m.group(1)][1]:
+        return (names[m.group(1)][0], False)      # scalar arithmetic: O3D_F_FPHI1 + 1
+    return None
+
+
+def test_shim_call_sites_pass_arguments_of_the_declared_type_and_shape():
+    f2py = __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    import contextlib
+    import io
+    mods = {}
+    for fn in sorted(os.listdir(os.path.join(ROOT, "fortran"))):
+        if fn.endswith(".f90"):
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                f2py.verbose = 0
+                tree = f2py.crackfortran([os.path.join(ROOT, "fortran", fn)])
+            mods[fn] = [b for b in tree if b["block"] == "module"][0]
+    cmod = mods["o3d_b200_c.f90"]
+    ifaces = {f["name"].lower(): f for b in cmod["body"] if b["block"] == "interface"
+              for f in b["body"]}
+    cvars = {k.lower(): _vclass(v) for k, v in cmod.get("vars", {}).items()}
+
+    def functions_of(m):
+        return {b["name"].lower(): _vclass(b["vars"][b.get("result") or b["name"]])
+                for b in m["body"] if b["block"] == "function"}
+
+    checked = undecided = 0
+    problems = []
+    for fn, m in mods.items():
+        modvars = {k.lower(): _vclass(v) for k, v in m.get("vars", {}).items()}
+        funcs = functions_of(m)
+        used = [u.lower() for u in (m.get("use") or {})]
+        for other in mods.values():
+            if other["name"].lower() in used:
+                funcs.update(functions_of(other))
+        routines = f90np.routines(shim_text(fn))
+        for b in m["body"]:
+            if b["block"] not in ("subroutine", "function"):
+                continue
+            body = routines[b["name"].lower()].body
+            names = dict(cvars)
+            names.update(modvars)
+            names.update({k.lower(): _vclass(v) for k, v in b.get("vars", {}).items()})
+            names.update(_decl_types(body))
+            names["__funcs__"] = funcs
+            text = "\n".join(ln.split("!")[0] for ln in body)
+            for mm in re.finditer(r"\b(o3d_[a-z0-9_]+)\s*\(", text, re.I):
+                nm = mm.group(1).lower()
+                if nm not in ifaces:
+                    continue
+                end = f90np.matching_paren(text, mm.end() - 1)
+                args = f90np.split_top(text[mm.end():end])
+                f = ifaces[nm]
+                assert len(args) == len(f["args"]), (fn, b["name"], nm)
+                for a, d in zip(args, f["args"]):
+                    want = _vclass(f["vars"][d])
+                    got = _actual_class(a, names)
+                    if got is None:
+                        undecided += 1
+                        continue
+                    checked += 1
+                    if got[0] != want[0]:
+                        problems.append((fn, b["name"], nm, d, "type", a.strip(), got, want))
+                    elif want[0] != "character" and got[1] != want[1]:
+                        problems.append((fn, b["name"], nm, d, "shape", a.strip(), got, want))
+    assert not problems, problems
+    assert checked > 400 and undecided <= 5, (checked, undecided)
