@@ -535,3 +535,39 @@ def test_shim_call_sites_pass_arguments_of_the_declared_type_and_shape():
                         problems.append((fn, b["name"], nm, d, "shape", a.strip(), got, want))
     assert not problems, problems
     assert checked > 400 and undecided <= 5, (checked, undecided)
+
+
+def test_shim_block_constructs_are_balanced():
+    """if / do / select case constructs of every shim procedure open and close in order (the parse
+    error a compiler reports first); one-line `if (...) statement` forms do not open a block"""
+    n = 0
+    for fn in sorted(os.listdir(os.path.join(ROOT, "fortran"))):
+        if not fn.endswith(".f90"):
+            continue
+        for name, r in f90np.routines(shim_text(fn)).items():
+            stack = []
+            for line in r.body:
+                ln = re.sub(r'"[^"]*"|\'[^\']*\'', '""', line).split("!")[0].strip().lower()
+                if not ln:
+                    continue
+                if re.match(r"(\w+\s*:\s*)?if\s*\(.*\)\s*then$", ln):
+                    stack.append("if")
+                elif re.match(r"else\s*if\s*\(.*\)\s*then$", ln) or ln == "else":
+                    assert stack and stack[-1] == "if", (fn, name, line)
+                elif re.match(r"end\s*if$", ln):
+                    assert stack and stack.pop() == "if", (fn, name, line)
+                elif re.match(r"(\w+\s*:\s*)?do(\s+\w+\s*=.*|\s+while\s*\(.*\)|)$", ln):
+                    stack.append("do")
+                elif re.match(r"end\s*do$", ln):
+                    assert stack and stack.pop() == "do", (fn, name, line)
+                elif re.match(r"select\s+case\s*\(.*\)$", ln):
+                    stack.append("select")
+                elif re.match(r"end\s*select$", ln):
+                    assert stack and stack.pop() == "select", (fn, name, line)
+                elif re.match(r"(case\s*\(.*\)|case\s+default)$", ln):
+                    assert stack and stack[-1] == "select", (fn, name, line)
+                # every `(` of a statement closes on the same logical line
+                assert ln.count("(") == ln.count(")"), (fn, name, line)
+            assert not stack, (fn, name, stack)
+            n += 1
+    assert n >= 40
