@@ -571,3 +571,55 @@ def test_shim_block_constructs_are_balanced():
             assert not stack, (fn, name, stack)
             n += 1
     assert n >= 40
+
+
+def c_enum_values():
+    """every enumerator of include/o3d_b200.h with its value (implicit increments included)"""
+    txt = open(os.path.join(ROOT, "include", "o3d_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    vals = {}
+    for body in re.findall(r"\benum\s*\w*\s*\{(.*?)\}", txt, flags=re.S):
+        nxt = 0
+        for ent in body.split(","):
+            ent = ent.strip()
+            if not ent:
+                continue
+            m = re.match(r"(\w+)\s*(?:=\s*(-?\d+))?$", ent)
+            assert m, ent
+            if m.group(2) is not None:
+                nxt = int(m.group(2))
+            vals[m.group(1)] = nxt
+            nxt += 1
+    return vals
+
+
+def test_fortran_constants_equal_the_c_enumerators():
+    """integer(c_int), parameter :: O3D_* = value in o3d_b200_c.f90 == the enumerator of the same
+    name in include/o3d_b200.h (field ids, reduction ops, status codes)"""
+    enums = c_enum_values()
+    assert enums["O3D_F_UX"] == 0 and enums["O3D_F_FUX2"] == enums["O3D_F_FUX1"] + 1
+    text = "\n".join(f90np.logical_lines(shim_text("o3d_b200_c.f90")))
+    n = 0
+    for decl in re.findall(r"(?im)^\s*integer\s*\(\s*c_int\s*\)\s*,\s*parameter\s*::(.*)$", text):
+        for ent in f90np.split_top(decl):
+            name, value = [t.strip() for t in ent.split("=")]
+            assert name.upper() in enums, name
+            assert int(value) == enums[name.upper()], (name, value, enums[name.upper()])
+            n += 1
+    assert n >= 20
+
+
+def test_open_session_fills_every_field_of_the_config():
+    """o3d_open_session (integration_b200.f90) assigns each component of type(o3d_config): a field
+    added to the struct and forgotten in the shim would reach the library uninitialised"""
+    text = "\n".join(f90np.logical_lines(shim_text("o3d_b200_c.f90")))
+    body = re.search(r"type,\s*bind\(C\)\s*::\s*o3d_config(.*?)end type", text, re.S | re.I).group(1)
+    fields = set()
+    for line in body.splitlines():
+        if "::" in line:
+            for ent in f90np.split_top(line.split("::", 1)[1]):
+                fields.add(re.match(r"\s*(\w+)", ent).group(1).lower())
+    r = f90np.routines(shim_text("integration_b200.f90"))["o3d_open_session"]
+    assigned = set(m.lower() for line in r.body
+                   for m in re.findall(r"\bc%(\w+)\s*=", line.split("!")[0]))
+    assert assigned == fields, (sorted(fields - assigned), sorted(assigned - fields))
