@@ -5,7 +5,7 @@
 !> Two modes, chosen by `o3d_resident`:
 !>  .false. (pure drop-in): every call forwards its HOST arrays to the stateless C entry points
 !>          (o3d_predict_velocity ...); inputs are copied to the device and outputs back on each
-!>          call.  Bit-for-bit the reference's data flow; PCIe-bound (34 N doubles per step).
+!>          call.  Bit-for-bit the reference's data flow; PCIe-bound (27 - 34 N doubles per step, INTEGRATION.md section 3).
 !>  .true.  (resident, the intended production mode): the fields live in a device session created
 !>          on the first call from the module `initialization` globals.  ux, uy, uz, pp, phi and
 !>          the AB histories are uploaded ONCE.  What comes back per step is `o3d_mirror`:
