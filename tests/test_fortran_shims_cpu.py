@@ -623,3 +623,27 @@ def test_open_session_fills_every_field_of_the_config():
     assigned = set(m.lower() for line in r.body
                    for m in re.findall(r"\bc%(\w+)\s*=", line.split("!")[0]))
     assert assigned == fields, (sorted(fields - assigned), sorted(assigned - fields))
+
+
+def test_derivation_shim_routines_forward_their_own_axis_order_and_closure():
+    """der<axis>[<axis>][p|i]_<00|11|2dsim> -> o3d_der(axis, order, closure, ...) with the triple
+    the NAME says (O3D_CLOSURE_00 = 0, _P11 = 1, _I11 = 2, _2DSIM = 3, include/o3d_b200.h)"""
+    enums = c_enum_values()
+    n = 0
+    for name, r in f90np.routines(shim_text("derivation_b200.f90")).items():
+        m = re.fullmatch(r"der([xyz])(\1?)([pi]?)_(00|11|2dsim)", name)
+        if not m:
+            assert name == "dery1d", name
+            continue
+        axis = "xyz".index(m.group(1))
+        order = 2 if m.group(2) else 1
+        closure = {"00": "O3D_CLOSURE_00", "2dsim": "O3D_CLOSURE_2DSIM"}.get(
+            m.group(4), "O3D_CLOSURE_I11" if m.group(3) == "i" else "O3D_CLOSURE_P11")
+        text = " ".join(r.body)
+        call = re.search(r"o3d_der\(\s*(\d+)_c_int\s*,\s*(\d+)_c_int\s*,\s*(\d+)_c_int\s*,\s*df\s*,"
+                         r"\s*f\s*,\s*d\s*,", text)
+        assert call, name
+        assert tuple(int(g) for g in call.groups()) == (axis, order, enums[closure]), name
+        assert '"%s"' % name in text.lower()           # the error label names the routine
+        n += 1
+    assert n == 20
