@@ -86,3 +86,55 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle_py" not in txt and "o3d_oracle" not in txt, fn
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_ctypes_argtypes_match_the_c_prototypes(built_lib):
+    """every `argtypes` list osinco3d_b200/_lib.py declares agrees, parameter by parameter, with
+    the prototype in include/o3d_b200.h (ctypes converts silently: a c_int declared where C takes
+    a double would pass garbage)"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_fortran_shims_cpu import c_param_class, c_typed_prototypes
+    lib = built_lib.lib()
+    L = built_lib._lib
+    protos = c_typed_prototypes()
+
+    def cls(t):
+        if t in (C.c_int,):
+            return ("int", 0)
+        if t is C.c_double:
+            return ("double", 0)
+        if t in (C.c_longlong, C.c_ulonglong, C.c_size_t):
+            return ("i64", 0)
+        if t is C.c_void_p:
+            return ("ptr", 1)
+        if t is C.c_char_p:
+            return ("char", 1)
+        if hasattr(t, "_type_"):                      # POINTER(x)
+            inner = t._type_
+            if inner is C.c_void_p:
+                return ("ptr", 2)
+            if inner is L.Config:
+                return ("o3d_config", 1)
+            if inner is C.c_ubyte:
+                return ("unsigned char", 1)
+            b, d = cls(inner)
+            return (b, d + 1)
+        raise AssertionError(t)
+
+    checked = 0
+    for name in protos:
+        fn = getattr(lib, name, None)
+        if fn is None or fn.argtypes is None:
+            continue
+        ret, args = protos[name]
+        cparams = [] if args in ("", "void") else [c_param_class(a) for a in args.split(",")]
+        assert len(cparams) == len(fn.argtypes), (name, args, fn.argtypes)
+        for t, (cb, cd, _) in zip(fn.argtypes, cparams):
+            pb, pd = cls(t)
+            if pb == "ptr":
+                assert cd == pd, (name, t, cb, cd)    # opaque handle / raw address
+            else:
+                assert (pb, pd) == (cb, cd), (name, t, (cb, cd))
+            checked += 1
+    assert checked > 120
