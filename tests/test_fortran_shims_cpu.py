@@ -647,3 +647,44 @@ def test_derivation_shim_routines_forward_their_own_axis_order_and_closure():
         assert '"%s"' % name in text.lower()           # the error label names the routine
         n += 1
     assert n == 20
+
+
+def test_shim_call_sites_pass_same_named_arguments_in_place():
+    """what the type checker cannot see: two arguments of the same type swapped (dx <-> dy,
+    nx <-> nz, kmax <-> idyn).  The bind(C) interfaces name their dummies like the reference's
+    procedures do, so wherever a dummy of an interface has the name of a dummy of the calling
+    shim procedure, the actual argument in that position must be that very variable (possibly
+    wrapped: int(nx, c_int))."""
+    f2py = __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    import contextlib
+    import io
+    mods = {}
+    for fn in sorted(os.listdir(os.path.join(ROOT, "fortran"))):
+        if fn.endswith(".f90"):
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                f2py.verbose = 0
+                tree = f2py.crackfortran([os.path.join(ROOT, "fortran", fn)])
+            mods[fn] = [b for b in tree if b["block"] == "module"][0]
+    ifaces = {f["name"].lower(): f for b in mods["o3d_b200_c.f90"]["body"]
+              if b["block"] == "interface" for f in b["body"]}
+    n = 0
+    for fn, m in mods.items():
+        routines = f90np.routines(shim_text(fn))
+        for b in m["body"]:
+            if b["block"] not in ("subroutine", "function"):
+                continue
+            caller = set(a.lower() for a in b["args"])
+            text = "\n".join(ln.split("!")[0] for ln in routines[b["name"].lower()].body)
+            for mm in re.finditer(r"\b(o3d_[a-z0-9_]+)\s*\(", text, re.I):
+                nm = mm.group(1).lower()
+                if nm not in ifaces:
+                    continue
+                end = f90np.matching_paren(text, mm.end() - 1)
+                actuals = [a.strip().lower() for a in f90np.split_top(text[mm.end():end])]
+                for a, d in zip(actuals, [x.lower() for x in ifaces[nm]["args"]]):
+                    if d not in caller:
+                        continue
+                    used = set(re.findall(r"[a-z_]\w*", a)) & caller
+                    assert used == {d}, (fn, b["name"], nm, "dummy", d, "<- actual", a)
+                    n += 1
+    assert n > 200
