@@ -135,6 +135,11 @@ def c_param_class(p):
     return base, depth, const
 
 
+def c_param_name(p):
+    toks = re.sub(r"\[[^\]]*\]", "", p).replace("*", " ").split()
+    return toks[-1].lower() if len(toks) >= 2 else None
+
+
 def fortran_arg_class(v):
     """crackfortran variable -> (base, depth, read_only): what a bind(C) call passes for it"""
     by_value = "value" in v.get("attrspec", [])
@@ -183,6 +188,12 @@ def test_bind_c_argument_types_match_the_c_prototypes():
         else:
             assert rv["typespec"] == "integer" and rv["kindselector"]["kind"] == "c_int" and \
                 (rbase, rdepth) == ("int", 0), (name, ret)
+        # parameter NAMES agree too (the order of dx, dy, dz / nx, ny, nz / kmax, idyn is only
+        # visible in the names); the session handle is `s` / `out` in C and `ses` here
+        cnames = [] if args in ("", "void") else [c_param_name(a) for a in args.split(",")]
+        for cn, a in zip(cnames, f["args"]):
+            assert cn == a.lower() or (cn, a.lower()) in (("s", "ses"), ("out", "ses"),
+                                                         ("out", "res")), (name, cn, a)
         for a, (cb, cd, cconst) in zip(f["args"], cparams):
             fb, fd, ro = fortran_arg_class(f["vars"][a])
             where = "%s(%s)" % (name, a)
