@@ -6,10 +6,11 @@
 !> on the device until max|rhs - L phi| / |A| < tol (DESIGN.md "Multigrid").
 module poisson_multigrid
   use iso_c_binding
-  ! the boundary rule of the operator is the Poisson variant schemes() picked from these flags
-  ! (src/initialization.f90:283-301); module initialization uses poisson and derivation only, so
-  ! there is no cycle
-  use initialization, only : nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d
+  ! The boundary rule of the operator is the Poisson variant of the C-side schemes().  This module
+  ! cannot bind it itself: src/Makefile compiles poisson_multigrid BEFORE initialization, whose
+  ! flags it would need.  Its only caller, correct_pression (src/integration.f90:227-244), takes
+  ! the divergence first -- through the diffoper shim, which binds the closures -- and the
+  ! integration shim does not come through here at all (o3d_correct_pression runs the V-cycles).
   use o3d_b200_c
   implicit none
   private
@@ -24,7 +25,6 @@ contains
     real(kind=8), intent(in) :: dx, dy, dz, tol
     integer(c_int) :: cycles
     real(c_double) :: dmax
-    call o3d_bind_schemes(nbcx1, nbcxn, nbcy1, nbcyn, nbcz1, nbczn, sim2d)
     call o3d_check(o3d_solve_poisson_multigrid(phi, rhs, dx, dy, dz, nx, ny, nz, nlevels, npre, &
          npost, tol, cycles, dmax), "solve_poisson_multigrid")
     print *, "* Multigrid: V-cycles, max|r|/|A| = ", cycles, dmax

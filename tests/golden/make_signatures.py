@@ -63,6 +63,20 @@ def module_exports(path):
     return out
 
 
+def build_order():
+    import re
+    mk = open(os.path.join(REF, "Makefile")).read()
+    block = re.search(r"^SOURCES\s*=(.*?)(?:\n\s*\n|\n#)", mk, re.S | re.M).group(1)
+    files = re.findall(r"\$\(SRCDIR\)/(\w+\.f90)", block)
+    order = []
+    for fn in files:
+        text = "\n".join(f90np.logical_lines(open(os.path.join(REF, fn)).read()))
+        defines = [m.lower() for m in re.findall(r"(?im)^\s*module\s+(\w+)\s*$", text)]
+        uses = sorted(set(m.lower() for m in re.findall(r"(?im)^\s*use\s+(\w+)", text)))
+        order.append({"file": fn, "defines": defines, "uses": uses})
+    return order
+
+
 def main():
     out = {}
     for mod, fn in MODULES.items():
@@ -83,9 +97,13 @@ def main():
     for fn in ("initialization.f90", "IOfunctions.f90"):
         for mod, ex in module_exports(os.path.join(REF, fn)).items():
             out["_exports"][mod] = dict(ex, file="src/" + fn)
+    # compile order of the reference (SOURCES of src/Makefile: gfortran needs a module's .mod
+    # before its first `use`) with, per file, the module it defines and the modules it uses
+    out["_build"] = build_order()
     with open(os.path.join(HERE, "reference_signatures.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
-    print({m: len(v.get("procedures", v.get("typed", v))) for m, v in out.items()})
+    print({m: len(v.get("procedures", v.get("typed", v)) if isinstance(v, dict) else v)
+           for m, v in out.items()})
 
 
 if __name__ == "__main__":

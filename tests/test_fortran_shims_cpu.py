@@ -699,3 +699,39 @@ def test_shim_call_sites_pass_same_named_arguments_in_place():
                     assert used == {d}, (fn, b["name"], nm, "dummy", d, "<- actual", a)
                     n += 1
     assert n > 200
+
+
+def test_shims_compile_in_the_reference_makefile_order():
+    """swap the six sources of src/Makefile's SOURCES for their _b200
+    counterparts, put o3d_b200_c.f90 first (and output_b200.f90 behind integration).  gfortran
+    needs a module's .mod before its first `use`: in that list every module a file uses --
+    unchanged reference files included -- is defined by an EARLIER file
+    (tests/golden/reference_signatures.json "_build": SOURCES order, defines / uses per file)."""
+    build = _ALL["_build"]
+    shim_for = {ref["file"].split("/")[-1]: SHIM_OF[mod] for mod, ref in SIG.items()}
+    order = [("o3d_b200_c.f90", None)]
+    for ent in build:
+        if ent["file"] in shim_for:
+            order.append((shim_for[ent["file"]], None))
+        else:
+            order.append((ent["file"], ent))
+        if ent["file"] == "integration.f90":
+            order.append(("output_b200.f90", None))
+    assert len([f for f, e in order if e is None]) == 8       # all eight shim files are placed
+    defined = {"iso_c_binding", "iso_fortran_env"}
+    for fn, ent in order:
+        if ent is None:
+            text = "\n".join(f90np.logical_lines(shim_text(fn)))
+            defines = [m.lower() for m in re.findall(r"(?im)^\s*module\s+(\w+)\s*$", text)]
+            uses = set(m.lower() for m in re.findall(r"(?im)^\s*use\s+(\w+)", text))
+        else:
+            defines, uses = ent["defines"], set(ent["uses"])
+        missing = uses - defined - set(defines)
+        assert not missing, "%s uses %s before any earlier file defines it" % (fn, sorted(missing))
+        defined |= set(defines)
+    # the shims define exactly the modules of the files they replace
+    for ent in build:
+        if ent["file"] in shim_for:
+            text = "\n".join(f90np.logical_lines(shim_text(shim_for[ent["file"]])))
+            assert [m.lower() for m in re.findall(r"(?im)^\s*module\s+(\w+)\s*$", text)] == \
+                ent["defines"], ent["file"]
