@@ -735,3 +735,52 @@ def test_shims_compile_in_the_reference_makefile_order():
             text = "\n".join(f90np.logical_lines(shim_text(shim_for[ent["file"]])))
             assert [m.lower() for m in re.findall(r"(?im)^\s*module\s+(\w+)\s*$", text)] == \
                 ent["defines"], ent["file"]
+
+
+def test_config_type_components_have_the_c_struct_types():
+    """type(o3d_config) component by component against struct o3d_config of the header and the
+    ctypes mirror: base type, byte size and array extent (a c_int where the struct has a double
+    shifts every later field)"""
+    f2py = __import__("pytest").importorskip("numpy.f2py.crackfortran")
+    import contextlib
+    import ctypes as C
+    import io
+    from osinco3d_b200 import _lib
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        f2py.verbose = 0
+        tree = f2py.crackfortran([os.path.join(ROOT, "fortran", "o3d_b200_c.f90")])
+    mod = [b for b in tree if b["block"] == "module"][0]
+    ty = [b for b in mod["body"] if b["block"] == "type" and b["name"].lower() == "o3d_config"][0]
+    fort = []
+    for k in ty["varnames"]:
+        v = ty["vars"][k]
+        kind = v["kindselector"]["kind"]
+        n = int(v["dimension"][0]) if v.get("dimension") else 1
+        fort.append(({"c_int": ("int", 4), "c_double": ("double", 8),
+                      "c_signed_char": ("char", 1)}[kind], n))
+    # the C struct
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "o3d_b200.h")).read(),
+                 flags=re.S)
+    body = re.search(r"typedef\s+struct\s+o3d_config\s*\{(.*?)\}\s*o3d_config\s*;", txt, re.S).group(1)
+    cstruct = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"(unsigned\s+char|int|double)\s+(.*)$", decl, re.S)
+        assert m, decl
+        base = {"int": ("int", 4), "double": ("double", 8), "unsigned char": ("char", 1)}[
+            re.sub(r"\s+", " ", m.group(1))]
+        for ent in m.group(2).split(","):
+            mm = re.match(r"\s*(\w+)\s*(?:\[(\d+)\])?\s*$", ent)
+            assert mm, ent
+            cstruct.append((base, int(mm.group(2) or 1)))
+    assert fort == cstruct
+    # the ctypes mirror
+    py = []
+    for _, t in _lib.Config._fields_:
+        n = 1
+        if hasattr(t, "_length_"):
+            n, t = t._length_, t._type_
+        py.append(({C.c_int: ("int", 4), C.c_double: ("double", 8), C.c_ubyte: ("char", 1)}[t], n))
+    assert py == cstruct
