@@ -159,3 +159,15 @@ def test_reference_arm_names_the_n_rank_workload():
     assert d["n_gpus"] == 4 and d["config"]["workload"] == "tgv_re1600_dns_freeslip_24x24x93_ab3_sor"
     assert d["config"]["workload_grid"] == [24, 24, 93] and d["config"]["grid"] == [24, 24, 24]
     assert "one of the 4 z replicas" in d["cpu_baseline"]["sample"]
+
+
+def test_secondary_legs_are_guarded_and_cpu_baseline_object(capsys):
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.guarded(lambda: {}["missing"])
+    assert set(r) == {"error"} and r["error"].startswith("KeyError")
+    capsys.readouterr()                               # the traceback goes to stderr
+    a = argparse.Namespace(n=24, bc="freeslip", les=False, strong=False, cpu_n=0)
+    cb = bench.cpu_baseline(a, 24)
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["unit"] == "Mpts*steps/s"
+    assert cb["value"] > 0 and cb["value_strict_O2_build"] > 0 and "24^3" in cb["sample"]
